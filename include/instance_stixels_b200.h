@@ -1,0 +1,247 @@
+/*
+ * instance_stixels_b200 -- C ABI of the Blackwell-native stixel hot path.
+ *
+ * This is the drop-in boundary for ONE path of tudelft-iv/instance_stixels:
+ *   column join -> per-column cost tables -> ground/object/sky DP ->
+ *   backtracking/emission -> instance grouping,
+ * i.e. everything `Stixels::Compute` + its setters/getters do in the
+ * reference (InstanceStixels/src/Stixels.cu:43-776).  Plain pointers and
+ * sizes only; no C++/torch types.  Every entry point cites the reference
+ * interface it replaces (paths relative to the reference repository root).
+ *
+ * The C++ class `Stixels` in include/InstanceStixels/Stixels.hpp has the
+ * reference's public signatures and forwards to these functions, so
+ * apps/run_cityscapes.cu and apps/stixels_wrapper.cu compile against it
+ * unchanged.
+ *
+ * All functions return ISX_OK (0) or a negative isx_status; the text of the
+ * last failure is available through isx_last_error().  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with
+ * ISX_ERR_CUDA.
+ */
+#ifndef INSTANCE_STIXELS_B200_H_
+#define INSTANCE_STIXELS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISX_ABI_VERSION 1
+
+typedef enum isx_status {
+  ISX_OK = 0,
+  ISX_ERR_INVALID_ARGUMENT = -1, /* reference: throws std::invalid_argument (Stixels.cu:292-313) */
+  ISX_ERR_NOT_INITIALIZED = -2,
+  ISX_ERR_CUDA = -3,             /* reference: CUDA_CHECK_RETURN -> exit(1) (util.h:27-42) */
+  ISX_ERR_CAPACITY = -4,         /* batch larger than isx_initialize(max_batch), column with >= 200 stixels */
+  ISX_ERR_UNSUPPORTED = -5
+} isx_status;
+
+/* Geometric stixel types, InstanceStixels/include/InstanceStixels/types.h:22-24 */
+#define ISX_GROUND 0
+#define ISX_OBJECT 1
+#define ISX_SKY 2
+
+/* configuration.h:29-34 */
+#define ISX_MAX_STIXELS_PER_COLUMN 200
+#define ISX_DOWNSAMPLE_FACTOR 8
+#define ISX_INSTANCE_CLASSES 8      /* Cityscapes trainIds 11..18 (Stixels.cu:47) */
+#define ISX_FIRST_INSTANCE_CLASS 11 /* StixelsKernels.cu:926 */
+
+/* Same members, defaults and "-1 == unset" sentinels as `StixelConfig`
+ * (types.h:30-141).  isx_config_init() writes the reference's defaults. */
+typedef struct isx_config {
+  float rows, cols; /* floats in the reference too (types.h:33-34) */
+  int32_t max_dis;
+  float invalid_disparity;
+  float eps;
+  int32_t min_pts;
+  int32_t size_filter;
+  int32_t n_semantic_classes;
+  int32_t n_offset_channels;
+  float prior_weight, segmentation_weight, instance_weight, disparity_weight;
+  int32_t pairwise; /* convenience storage only, like types.h:57-60 */
+  int32_t column_step;
+  float focal, baseline, camera_center_x, camera_center_y;
+  float sigma_disparity_object, sigma_disparity_ground, sigma_sky;
+  float pout, pout_sky, pord, pgrav, pblg;
+  float pground_given_nexist, pobject_given_nexist, psky_given_nexist;
+  float pnexist_dis, pground, pobject, psky;
+  int32_t width_margin;
+  float sigma_camera_tilt, sigma_camera_height;
+  int32_t median_join;
+  float epsilon, range_objects_z;
+  float road_vdisparity_threshold;
+} isx_config;
+
+/* Bit-identical to `Section` (types.h:186-194): 8 x 4 bytes. */
+typedef struct isx_section {
+  int32_t type; /* ISX_GROUND/OBJECT/SKY; -1 terminates a column */
+  int32_t vB, vT;
+  float disparity;
+  int32_t semantic_class;
+  float cost;
+  float instance_meanx;
+  float instance_meany;
+} isx_section;
+
+/* The scalar members of `StixelsData` (types.h:196-205). */
+typedef struct isx_frame_meta {
+  int32_t rows, cols, realcols, max_sections, max_dis, column_step;
+  int32_t semantic_classes;
+  float alpha_ground;
+  int32_t vhor; /* flipped: rows - vhor_in - 1 (Stixels.cu:377,627) */
+} isx_frame_meta;
+
+/* Arguments of Stixels::SetRoadParameters (Stixels.cu:375-381), per frame. */
+typedef struct isx_road {
+  int32_t vhor; /* horizon image row, top-left origin */
+  float camera_tilt, camera_height, alpha_ground;
+} isx_road;
+
+/* One entry of the map Stixels::GetInstanceStixels returns
+ * (Stixels.cu:744-776): key (column, index-from-top), value DBSCAN label
+ * (-1 = noise; labels are per semantic class like the reference's). */
+typedef struct isx_instance {
+  int32_t column;
+  int32_t index;
+  int32_t label;
+  int32_t semantic_class;
+} isx_instance;
+
+typedef struct isx_context *isx_handle;
+
+/* ------------------------------------------------------------------ */
+/* Library                                                            */
+int isx_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (the
+ * bench reports it as gpu_launches). */
+uint64_t isx_kernel_launch_count(void);
+const char *isx_last_error(isx_handle h); /* h may be NULL: last global error */
+
+/* ------------------------------------------------------------------ */
+/* Object lifetime and configuration                                  */
+
+/* StixelConfig default member initialisers (types.h:30-141). */
+void isx_config_init(isx_config *cfg);
+/* Stixels::Stixels() (Stixels.cu:33); `device` = CUDA ordinal. */
+int isx_create(isx_handle *out, int device);
+/* Stixels::~Stixels(); also performs Finish() if still initialised. */
+int isx_destroy(isx_handle h);
+/* Stixels::SetConfig (Stixels.cu:292-338): ISX_ERR_INVALID_ARGUMENT where
+ * the reference throws. */
+int isx_set_config(isx_handle h, const isx_config *cfg);
+/* The fine-grained setters the reference keeps public (Stixels.hpp:58-88). */
+int isx_set_disparity_parameters(isx_handle h, int rows, int cols, int max_dis, float invalid_disparity,
+                                 float sigma_disparity_object, float sigma_disparity_ground,
+                                 float sigma_sky); /* Stixels.cu:425-437 */
+int isx_set_segmentation_parameters(isx_handle h, int classes, int instance_channels); /* :402-406 */
+int isx_set_clustering_parameters(isx_handle h, float eps, int min_pts, int size_filter); /* :395-400 */
+int isx_set_weight_parameters(isx_handle h, float prior_weight, float disparity_weight,
+                              float segmentation_weight, float instance_weight); /* :408-423 */
+int isx_set_probabilities(isx_handle h, float pout, float pout_sky, float pground_given_nexist,
+                          float pobject_given_nexist, float psky_given_nexist, float pnexist_dis,
+                          float pground, float pobject, float psky, float pord, float pgrav,
+                          float pblg); /* :361-373 */
+int isx_set_camera_parameters(isx_handle h, float focal, float baseline, float sigma_camera_tilt,
+                              float sigma_camera_height, float camera_center_x,
+                              float camera_center_y); /* :383-393 */
+int isx_set_model_parameters(isx_handle h, int column_step, int median_join, float epsilon,
+                             float range_objects_z, int width_margin); /* :439-446 */
+/* Stixels::Initialize (Stixels.cu:43-248): allocations + LUT precompute.
+ * `max_batch` >= 1 is the number of frames one batched call may carry (the
+ * reference has no batching; its Initialize is max_batch == 1). */
+int isx_initialize(isx_handle h, int max_batch);
+/* Stixels::Finish (Stixels.cu:250-283). */
+int isx_finish(isx_handle h);
+/* Stixels::IsInitialized (Stixels.hpp:96). */
+int isx_is_initialized(isx_handle h);
+/* Stixels::GetRealCols / GetMaxSections (Stixels.cu:778-784). */
+int isx_real_cols(isx_handle h);
+int isx_max_sections(isx_handle h);
+/* Length (in int32) of one frame's segmentation tensor
+ * [realcols][classes+offsets][rows_power2_segmentation] (Stixels.cu:136-139). */
+size_t isx_segmentation_elems(isx_handle h);
+
+/* ------------------------------------------------------------------ */
+/* Single-frame path: the reference's call sequence                   */
+/* (apps/run_cityscapes.cu:346,383-387,406-411,430-431)               */
+
+/* Stixels::SetDisparityImage (Stixels.cu:348-355): host [rows][cols] fp32. */
+int isx_set_disparity_image(isx_handle h, const float *host, size_t n);
+/* Stixels::GetInputDisparityImageOnDevice (Stixels.cu:357-359). */
+float *isx_input_disparity_device(isx_handle h);
+/* Stixels::SetSegmentation (Stixels.cu:340-346): host int32
+ * [realcols][21][rows_power2_segmentation]. */
+int isx_set_segmentation(isx_handle h, const int32_t *host, size_t n);
+/* Stixels::SetRoadParameters (Stixels.cu:375-381). */
+int isx_set_road_parameters(isx_handle h, int vhor, float camera_tilt, float camera_height,
+                            float alpha_ground);
+/* Stixels::Compute (Stixels.cu:449-637).  `sections` receives
+ * realcols*max_sections entries, `meta` the StixelsData scalars.
+ * `d_segmentation_local` is the optional borrowed DEVICE tensor of the ROS
+ * path (apps/stixels_wrapper.cu:208-209); unlike the reference it is NOT
+ * modified.  Instance grouping (ClusterInstances, :639-681) runs inside. */
+int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_meta *meta,
+                const int32_t *d_segmentation_local);
+/* Stixels::ClusterInstances (Stixels.cu:639-681).  Grouping already ran in
+ * isx_compute; kept because the reference exposes it publicly. Idempotent. */
+int isx_cluster_instances(isx_handle h);
+/* Stixels::GetInstanceStixels (Stixels.cu:744-776).  Writes up to `capacity`
+ * entries, ordered by (semantic class, column, index); *n = total count. */
+int isx_get_instance_stixels(isx_handle h, isx_instance *out, int capacity, int *n);
+
+/* ------------------------------------------------------------------ */
+/* Batched paths (no reference counterpart: the reference processes one
+ * frame per Compute call).  Frames are independent.                   */
+
+/* Host buffers in, host buffers out; H2D/D2H copies are inside the call,
+ * pipelined over CUDA streams.  `disparity` = [n][rows][cols],
+ * `segmentation` = [n][isx_segmentation_elems], `roads` = [n].
+ * `sections` = [n][realcols][max_sections]; `instances` receives frame after
+ * frame at most `instances_capacity` entries in total, `instance_offsets`
+ * = [n+1] prefix of per-frame counts.  instances/instance_offsets may be NULL. */
+int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *disparity,
+                           const int32_t *segmentation, const isx_road *roads, isx_section *sections,
+                           isx_instance *instances, int instances_capacity, int32_t *instance_offsets);
+
+/* Inputs already resident in device memory (the bench's `value` leg): runs
+ * the kernels on the handle's stream and leaves results on the device.
+ * Layouts as above. Returns after enqueueing; isx_synchronize() waits. */
+int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_disparity,
+                             const int32_t *d_segmentation, const isx_road *roads);
+int isx_synchronize(isx_handle h);
+/* Copy results of the last device batch to host buffers (same layouts as
+ * isx_compute_batch_host). */
+int isx_fetch_batch_results(isx_handle h, int n, isx_section *sections, isx_instance *instances,
+                            int instances_capacity, int32_t *instance_offsets);
+/* cudaStream_t of the handle as an integer (for CUDA-event timing by the
+ * caller on the stream the kernels are launched on). */
+uint64_t isx_stream(isx_handle h);
+
+/* ------------------------------------------------------------------ */
+/* Introspection for parity tests / profiling (device -> host copies of
+ * the intermediates of the LAST batch, frame `frame`).                */
+typedef enum isx_tensor {
+  ISX_T_JOINED_DISPARITY = 0, /* float [realcols][rows], bottom-up (StixelsKernels.cu:980-1095) */
+  ISX_T_OBJECT_LUT = 1,       /* float [realcols][max_dis][rows+1] (StixelsKernels.cu:959-978) */
+  ISX_T_DISPARITY_PS = 2,     /* float [realcols][rows+1] Blelloch-order prefix (StixelsKernels.h:73-103) */
+  ISX_T_VALID_PS = 3,         /* float [realcols][rows+1] */
+  ISX_T_GROUND_PS = 4,        /* float [realcols][rows+1] */
+  ISX_T_SKY_PS = 5,           /* float [realcols][rows+1] */
+  ISX_T_COST_TABLE = 6,       /* float [realcols][rows][3] final DP costs (cost_table, StixelsKernels.cu:339) */
+  ISX_T_INDEX_TABLE = 7,      /* int32 [realcols][rows][3] = vB*3+prev_type like index_table (:340) */
+  ISX_T_GROUND_TABLES = 8,    /* float [3][rows]: ground_function | normalization_ground | inv_sigma2_ground (Stixels.cu:790-817) */
+  ISX_T_OBJ_COST_LUT = 9,     /* float [max_dis][max_dis] (Stixels.cu:122-129) */
+  ISX_T_OBJECT_DISPARITY_RANGE = 10 /* float [max_dis] (Stixels.cu:111-115) */
+} isx_tensor;
+size_t isx_tensor_elems(isx_handle h, int tensor);
+int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSTANCE_STIXELS_B200_H_ */

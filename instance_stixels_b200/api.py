@@ -1,0 +1,227 @@
+"""Python mirror of the reference's `Stixels` class over the C ABI.
+
+Method names, argument meaning and error behaviour follow
+InstanceStixels/include/InstanceStixels/Stixels.hpp:40-96 so that tests read
+like the call sequence of apps/run_cityscapes.cu:335-449.  The product path is
+the CUDA library; nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+class StixelsError(RuntimeError):
+    pass
+
+
+class InvalidArgument(ValueError):
+    """Where the reference throws std::invalid_argument (Stixels.cu:292-313, 685-687)."""
+
+
+def StixelConfig(**fields) -> L.Config:
+    """`StixelConfig` with the reference's defaults (types.h:30-141) + overrides."""
+    lib = L.load()
+    cfg = L.Config()
+    lib.isx_config_init(C.byref(cfg))
+    names = {n for n, _ in L.Config._fields_}
+    for k, v in fields.items():
+        if k not in names:
+            raise AttributeError(f"StixelConfig has no field {k!r}")
+        setattr(cfg, k, int(v) if isinstance(v, bool) else v)
+    return cfg
+
+
+def _roads(roads: Sequence[dict]):
+    arr = (L.Road * len(roads))()
+    for i, r in enumerate(roads):
+        arr[i] = L.Road(int(r["vhor"]), float(r["camera_tilt"]), float(r["camera_height"]),
+                        float(r["alpha_ground"]))
+    return arr
+
+
+class StixelsData:
+    """types.h:196-205."""
+
+    def __init__(self, sections: np.ndarray, meta: L.FrameMeta):
+        self.sections = sections
+        for n, _ in L.FrameMeta._fields_:
+            setattr(self, n, getattr(meta, n))
+
+
+class Stixels:
+    def __init__(self, device: int = 0):
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        self._check(self._lib.isx_create(C.byref(self._h), device), None)
+        self._pairwise = False
+
+    # -- plumbing ---------------------------------------------------------
+    def _check(self, rc, h="self"):
+        if rc == L.ISX_OK:
+            return
+        msg = self._lib.isx_last_error(self._h if h == "self" else None)
+        msg = msg.decode() if msg else ""
+        if rc == -1:
+            raise InvalidArgument(msg)
+        raise StixelsError(f"isx error {rc}: {msg}")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.isx_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- reference API ----------------------------------------------------
+    def SetConfig(self, config: L.Config):
+        self._check(self._lib.isx_set_config(self._h, C.byref(config)))
+        self._pairwise = bool(config.pairwise)
+
+    def Initialize(self, max_batch: int = 1):
+        self._check(self._lib.isx_initialize(self._h, max_batch))
+
+    def Finish(self):
+        self._check(self._lib.isx_finish(self._h))
+
+    def IsInitialized(self) -> bool:
+        return bool(self._lib.isx_is_initialized(self._h))
+
+    def GetRealCols(self) -> int:
+        return self._lib.isx_real_cols(self._h)
+
+    def GetMaxSections(self) -> int:
+        return self._lib.isx_max_sections(self._h)
+
+    def segmentation_elems(self) -> int:
+        return self._lib.isx_segmentation_elems(self._h)
+
+    def SetDisparityImage(self, disp_im: np.ndarray):
+        a = np.ascontiguousarray(disp_im, dtype=np.float32)
+        self._keep_disp = a
+        self._check(self._lib.isx_set_disparity_image(self._h, a.ctypes.data, a.size))
+
+    def GetInputDisparityImageOnDevice(self) -> int:
+        return self._lib.isx_input_disparity_device(self._h)
+
+    def SetSegmentation(self, segmentation: np.ndarray):
+        a = np.ascontiguousarray(segmentation, dtype=np.int32)
+        self._keep_seg = a
+        self._check(self._lib.isx_set_segmentation(self._h, a.ctypes.data, a.size))
+
+    def SetRoadParameters(self, vhor: int, camera_tilt: float, camera_height: float, alpha_ground: float):
+        self._check(self._lib.isx_set_road_parameters(self._h, vhor, camera_tilt, camera_height, alpha_ground))
+
+    def SetSegmentationParameters(self, classes, instance_channels):
+        self._check(self._lib.isx_set_segmentation_parameters(self._h, classes, instance_channels))
+
+    def SetClusteringParameters(self, eps, min_pts, size_filter):
+        self._check(self._lib.isx_set_clustering_parameters(self._h, eps, min_pts, size_filter))
+
+    def SetWeightParameters(self, prior_weight, disparity_weight, segmentation_weight, instance_weight):
+        self._check(self._lib.isx_set_weight_parameters(self._h, prior_weight, disparity_weight,
+                                                        segmentation_weight, instance_weight))
+
+    def SetProbabilities(self, *a):
+        self._check(self._lib.isx_set_probabilities(self._h, *a))
+
+    def SetCameraParameters(self, focal, baseline, sigma_camera_tilt, sigma_camera_height,
+                            camera_center_x=-1.0, camera_center_y=-1.0):
+        self._check(self._lib.isx_set_camera_parameters(self._h, focal, baseline, sigma_camera_tilt,
+                                                        sigma_camera_height, camera_center_x, camera_center_y))
+
+    def SetDisparityParameters(self, rows, cols, max_dis, invalid_disparity, sigma_disparity_object,
+                               sigma_disparity_ground, sigma_sky):
+        self._check(self._lib.isx_set_disparity_parameters(self._h, rows, cols, max_dis, invalid_disparity,
+                                                           sigma_disparity_object, sigma_disparity_ground,
+                                                           sigma_sky))
+
+    def SetModelParameters(self, column_step, median_join, epsilon, range_objects_z, width_margin):
+        self._check(self._lib.isx_set_model_parameters(self._h, column_step, int(median_join), epsilon,
+                                                       range_objects_z, width_margin))
+
+    def Compute(self, pairwise: bool, d_segmentation_local: Optional[int] = None) -> StixelsData:
+        """Returns the StixelsData the reference fills through its out-parameter."""
+        n = self.GetRealCols() * self.GetMaxSections()
+        sections = np.zeros(n, dtype=L.SECTION_DTYPE)
+        meta = L.FrameMeta()
+        self._check(self._lib.isx_compute(self._h, int(pairwise), sections.ctypes.data, C.byref(meta),
+                                          d_segmentation_local))
+        return StixelsData(sections.reshape(self.GetRealCols(), self.GetMaxSections()), meta)
+
+    def ClusterInstances(self):
+        self._check(self._lib.isx_cluster_instances(self._h))
+
+    def GetInstanceStixels(self) -> dict:
+        """{(column, index): label} like the reference's std::map (Stixels.cu:744-776)."""
+        inst = self.instance_records()
+        return {(int(r["column"]), int(r["index"])): int(r["label"]) for r in inst}
+
+    def instance_records(self) -> np.ndarray:
+        n = C.c_int(0)
+        self._check(self._lib.isx_get_instance_stixels(self._h, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=L.INSTANCE_DTYPE)
+        self._check(self._lib.isx_get_instance_stixels(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out[:n.value]
+
+    # -- batched extensions (no reference counterpart) ---------------------
+    def ComputeBatch(self, pairwise: bool, disparity: np.ndarray, segmentation: np.ndarray,
+                     roads: Sequence[dict], sections_out: Optional[np.ndarray] = None,
+                     want_instances: bool = True):
+        """Host buffers in, host results out (H2D/D2H inside). Returns (sections, instances, offsets)."""
+        n = len(roads)
+        disparity = np.ascontiguousarray(disparity, dtype=np.float32)
+        segmentation = np.ascontiguousarray(segmentation, dtype=np.int32)
+        C_, S = self.GetRealCols(), self.GetMaxSections()
+        if sections_out is None:
+            sections_out = np.zeros((n, C_, S), dtype=L.SECTION_DTYPE)
+        cap = 16384 * n
+        inst = np.zeros(cap if want_instances else 1, dtype=L.INSTANCE_DTYPE)
+        offs = np.zeros(n + 1, dtype=np.int32)
+        self._check(self._lib.isx_compute_batch_host(
+            self._h, int(pairwise), n, disparity.ctypes.data, segmentation.ctypes.data, _roads(roads),
+            sections_out.ctypes.data, inst.ctypes.data if want_instances else None,
+            cap if want_instances else 0, offs.ctypes.data if want_instances else None))
+        return sections_out, inst[:offs[n]], offs
+
+    def ComputeBatchDevice(self, pairwise: bool, n: int, d_disparity: int, d_segmentation: int,
+                           roads: Sequence[dict]):
+        """Device pointers in, results stay on the device; asynchronous."""
+        self._check(self._lib.isx_compute_batch_device(self._h, int(pairwise), n, d_disparity, d_segmentation,
+                                                       _roads(roads)))
+
+    def Synchronize(self):
+        self._check(self._lib.isx_synchronize(self._h))
+
+    def FetchBatchResults(self, n: int, want_instances: bool = True):
+        C_, S = self.GetRealCols(), self.GetMaxSections()
+        sections = np.zeros((n, C_, S), dtype=L.SECTION_DTYPE)
+        cap = 16384 * n
+        inst = np.zeros(cap if want_instances else 1, dtype=L.INSTANCE_DTYPE)
+        offs = np.zeros(n + 1, dtype=np.int32)
+        self._check(self._lib.isx_fetch_batch_results(
+            self._h, n, sections.ctypes.data, inst.ctypes.data if want_instances else None,
+            cap if want_instances else 0, offs.ctypes.data if want_instances else None))
+        return sections, inst[:offs[n]], offs
+
+    def stream(self) -> int:
+        return self._lib.isx_stream(self._h)
+
+    def read_tensor(self, tensor: int, frame: int = 0) -> np.ndarray:
+        n = self._lib.isx_tensor_elems(self._h, tensor)
+        out = np.zeros(n, dtype=np.int32 if tensor == L.T_INDEX_TABLE else np.float32)
+        self._check(self._lib.isx_read_tensor(self._h, tensor, frame, out.ctypes.data, out.nbytes))
+        return out
+
+
+def make_stixels(preset: dict, max_batch: int = 1, device: int = 0) -> Stixels:
+    """SetConfig + Initialize from a synth.preset() dict."""
+    s = Stixels(device)
+    s.SetConfig(StixelConfig(**preset))
+    s.Initialize(max_batch)
+    return s

@@ -1,0 +1,107 @@
+// Shared declarations of the sm_100a stixel kernels.
+//
+// Arithmetic contract: the reference is built with `-O3 --use_fast_math`
+// (CMakeLists.txt:138-141), i.e. every fp32 op is .ftz, division is
+// x * MUFU.RCP(y), __logf(x) is MUFU.LG2(x) * ln2 and nvcc contracts a*b+c
+// into FFMA.  Results depend on those exact shapes, so the kernels here spell
+// every float operation with an explicit intrinsic (fmul/fadd/ffma/rcp/lg2)
+// in the order the reference's sm_100a SASS performs it;
+// this translation unit is compiled with -ftz=true -fmad=false so nothing is
+// contracted or reordered behind our back.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace isx {
+
+constexpr int kWarp = 32;
+constexpr int kMaxSections = 200;      // configuration.h:32
+constexpr int kDownsample = 8;         // configuration.h:31
+constexpr int kInstanceClasses = 8;    // Stixels.cu:47
+constexpr int kFirstInstanceClass = 11;  // StixelsKernels.cu:926
+constexpr int kSkyClass = 10;          // Cityscapes.h:117
+constexpr int GROUND = 0, OBJECT = 1, SKY = 2;  // types.h:22-24
+
+constexpr float kLn2 = 0.69314718246459960938f;        // 0x3f317218, fast-math __logf scale
+constexpr float kNegLog07 = 0.35667496919631958008f;   // -logf(0.7f) folded by nvcc (StixelsKernels.cu:124,151)
+constexpr float kLg2_03 = -1.7369655370712280273f;     // lg2(0.3f) folded by nvcc (StixelsKernels.cu:186)
+
+// ---- per-row record of the column tables (one 128-byte line per v in [0,H]) ----
+// Prefix sums over rows [0, v) of one stixel column; the DP reads R[vT+1]
+// ("A side", once per 32-row tile) and R[vB] ("B side", warp-uniform).
+constexpr int kRecWords = 32;
+constexpr int kRecSeg = 0;     // 19 words: full-resolution prefix of class c, exact int
+                               //   P_c(v) = 8*ps_c[v/8] + seg_c[v/8]*(v%8)   (Cityscapes.h:28-42)
+constexpr int kRecOff = 19;    // prefix of squared offsets x^2+y^2 (StixelsKernels.cu:62-70, 411-416)
+constexpr int kRecMx = 20;     // int64 prefix of instance_meansx (2 words)   (StixelsKernels.cu:401-403)
+constexpr int kRecMy = 22;     // int64 prefix of instance_meansy             (:404-405)
+constexpr int kRecMx2 = 24;    // int64 prefix of meansx^2                    (:406-407)
+constexpr int kRecMy2 = 26;    // int64 prefix of meansy^2                    (:408-409)
+constexpr int kRecDisp = 28;   // float Blelloch-order prefix of valid*d      (:385,455)
+constexpr int kRecValid = 29;  // float prefix of valid                       (:384,453)
+constexpr int kRecGround = 30; // float Blelloch-order prefix of ground_lut   (:437-446,460)
+constexpr int kRecSky = 31;    // float Blelloch-order prefix of sky_lut      (:424-433,461)
+
+// ---- per-frame static transition record S[vB] (pairwise only), 12 floats ----
+constexpr int kStatWords = 12;
+// ---- per-column dynamic row info Q[vB] (pairwise only), 12 floats ----
+constexpr int kDynWords = 12;
+
+// Parameters shared by all kernels (subset of StixelParameters, types.h:145-184).
+struct KParams {
+  int rows;          // H
+  int cols;          // W (input image)
+  int realcols;      // C = (W - width_margin) / column_step  (Stixels.cu:44)
+  int column_step;
+  int width_margin;
+  int max_dis;       // D
+  int hs2;           // rows_power2_segmentation
+  int n_classes;     // 19
+  int n_channels;    // 21
+  int median_join;
+  int size_filter;
+  int min_pts;
+  float eps_cluster;
+  float invalid_disparity;
+  float max_disf;
+  float rows_log, max_dis_log;
+  float pnexists_given_sky_log, normalization_sky, inv_sigma2_sky, puniform_sky, nopnexists_given_sky_log;
+  float pnexists_given_ground_log, puniform, nopnexists_given_ground_log;
+  float pord, epsilon, pgrav, pblg;
+  float prior_weight, disparity_weight, segmentation_weight, instance_weight;
+  // derived strides
+  int rec_rows;      // H + 1 records per column
+  int lut_stride;    // floats per fn row of the object LUT (>= H, multiple of 32)
+};
+
+// ---- pinned float ops (all .ftz through -ftz=true) ----
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fadd_rn(a, -b); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+// MUFU.RCP / MUFU.LG2, what fast-math division and __logf compile to.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// FMNMX: returns the non-NaN operand, like fminf.
+__device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }
+// NegFastLogDiv(a, b) = -__logf(a) + __logf(b)  (StixelsKernels.cu:35-38):
+//   t = FMUL(lg2 a, ln2); FFMA(lg2 b, ln2, -t)
+__device__ __forceinline__ float neg_log_div(float a, float b) {
+  const float t = fmul(lg2_approx(a), kLn2);
+  return ffma(lg2_approx(b), kLn2, -t);
+}
+// `x < 0 ? 0 : x` as compiled: FSETP.GEU + FSEL (NaN is kept).
+__device__ __forceinline__ float clamp_neg(float x) { return (x < 0.0f) ? 0.0f : x; }
+
+__device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
+
+}  // namespace isx
+

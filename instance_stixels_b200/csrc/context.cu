@@ -1,0 +1,720 @@
+// C ABI of the library (include/instance_stixels_b200.h): object lifetime,
+// configuration, device memory, streams and the per-batch kernel sequence.
+// Host orchestration of the reference: Stixels::Initialize / Compute /
+// ClusterInstances / GetInstanceStixels (InstanceStixels/src/Stixels.cu:43-283,
+// 449-681, 744-776).
+//
+// Differences in mechanism (not in results): batches of independent frames go
+// through every kernel in one launch; frames are processed in chunks so that a
+// chunk's H2D copy, the previous chunk's kernels and the one before's D2H copy
+// overlap on three streams; there is no per-frame cudaMalloc, handle
+// construction or device-wide synchronisation.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "host_model.h"
+#include "kernels.h"
+
+namespace isx {
+
+static thread_local std::string g_last_error;
+
+static int fail(isx_context *ctx, int code, const std::string &msg);
+
+struct RoadKey {
+  int vhor;
+  float tilt, height, alpha;
+  bool operator<(const RoadKey &o) const {
+    if (vhor != o.vhor) return vhor < o.vhor;
+    if (tilt != o.tilt) return tilt < o.tilt;
+    if (height != o.height) return height < o.height;
+    return alpha < o.alpha;
+  }
+};
+
+}  // namespace isx
+
+struct isx_context {
+  int device = 0;
+  bool configured_parts[8] = {false, false, false, false, false, false, false, false};
+  bool initialized = false;
+  isx::HostModel model;
+  isx::KParams kp{};
+  int max_batch = 0, chunk = 0;
+  std::string last_error;
+
+  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_chunk_done = nullptr;
+
+  // device memory
+  std::vector<void *> allocations;
+  float *d_in_disp[2] = {nullptr, nullptr};       // staging for host batches: [chunk][H][W]
+  int32_t *d_in_seg[2] = {nullptr, nullptr};      // [chunk][seg_elems]
+  float *d_single_disp = nullptr;                 // SetDisparityImage target (d_disparity_big)
+  int32_t *d_single_seg = nullptr;                // SetSegmentation target
+  isx::BatchBuffers buf;                          // intermediates sized `chunk`, results sized `max_batch`
+  isx_section *d_sections_all = nullptr;          // [max_batch][C][200]
+  int *d_nsections_all = nullptr;                 // [max_batch][C]
+  isx_instance *d_inst_all = nullptr;             // [max_batch][inst_cap]
+  int *d_inst_count_all = nullptr;                // [max_batch]
+  int inst_cap = 0;
+  float *d_export_cost = nullptr;
+  int *d_export_index = nullptr;
+
+  // pinned host staging
+  float *h_ground = nullptr;                      // [2][chunk][3][H]
+  int *h_vhor = nullptr;                          // [2][chunk]
+  isx_instance *h_inst = nullptr;                 // [max_batch][inst_cap]
+  int *h_inst_count = nullptr;                    // [max_batch]
+  int *h_error = nullptr;
+
+  std::map<isx::RoadKey, std::vector<float>> road_cache;
+  isx_road single_road{0, 0.f, 0.f, 0.f};
+  bool single_has_road = false;
+  int last_batch = 0;          // frames of the last batch (results valid for these)
+  int last_chunk_first = 0;    // first frame whose intermediates are still in `buf`
+  int last_chunk_n = 0;
+  bool last_pairwise = false;
+  std::vector<isx_road> last_roads;
+};
+
+namespace isx {
+
+static int fail(isx_context *ctx, int code, const std::string &msg) {
+  g_last_error = msg;
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+int fail_cuda(cudaError_t e, const char *expr, const char *file, int line) {
+  char buf[512];
+  std::snprintf(buf, sizeof buf, "%s returned %s(%d) at %s:%d", expr, cudaGetErrorString(e), (int)e, file, line);
+  g_last_error = buf;
+  return ISX_ERR_CUDA;
+}
+
+#define ISX_TRY(ctx, expr)                                            \
+  do {                                                                \
+    cudaError_t _e = (expr);                                          \
+    if (_e != cudaSuccess) {                                          \
+      int _c = ::isx::fail_cuda(_e, #expr, __FILE__, __LINE__);       \
+      (ctx)->last_error = ::isx::g_last_error;                        \
+      return _c;                                                      \
+    }                                                                 \
+  } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(isx_context *c, T **p, size_t count) {
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+  if (e == cudaSuccess) {
+    c->allocations.push_back(q);
+    *p = static_cast<T *>(q);
+  }
+  return e;
+}
+
+static size_t seg_elems(const isx_context *c) {
+  return (size_t)c->model.rows_power2_seg * c->model.realcols * c->model.n_channels;
+}
+
+static void fill_kparams(isx_context *c) {
+  const HostModel &m = c->model;
+  KParams &k = c->kp;
+  k.rows = m.rows;
+  k.cols = m.cols;
+  k.realcols = m.realcols;
+  k.column_step = m.column_step;
+  k.width_margin = m.width_margin;
+  k.max_dis = m.max_dis;
+  k.hs2 = m.rows_power2_seg;
+  k.n_classes = m.n_classes;
+  k.n_channels = m.n_channels;
+  k.median_join = m.median_join ? 1 : 0;
+  k.size_filter = m.size_filter;
+  k.min_pts = m.min_pts;
+  k.eps_cluster = m.eps;
+  k.invalid_disparity = m.invalid_disparity;
+  k.max_disf = m.max_disf;
+  k.rows_log = m.rows_log;
+  k.max_dis_log = m.max_dis_log;
+  k.pnexists_given_sky_log = m.pnexists_given_sky_log;
+  k.normalization_sky = m.normalization_sky;
+  k.inv_sigma2_sky = m.inv_sigma2_sky;
+  k.puniform_sky = m.puniform_sky;
+  k.nopnexists_given_sky_log = m.nopnexists_given_sky_log;
+  k.pnexists_given_ground_log = m.pnexists_given_ground_log;
+  k.puniform = m.puniform;
+  k.nopnexists_given_ground_log = m.nopnexists_given_ground_log;
+  k.pord = m.pord;
+  k.epsilon = m.epsilon;
+  k.pgrav = m.pgrav;
+  k.pblg = m.pblg;
+  k.prior_weight = m.prior_weight;
+  k.disparity_weight = m.disparity_weight;
+  k.segmentation_weight = m.segmentation_weight;
+  k.instance_weight = m.instance_weight;
+  k.rec_rows = m.rows + 1;
+  k.lut_stride = (m.rows + 31) & ~31;
+}
+
+// Compacts the grouping result of every frame into isx_instance records
+// ordered by (class, column, index).
+__global__ void pack_instances_kernel(const int *__restrict__ cand_count, const int2 *__restrict__ cand_idx,
+                                      const int *__restrict__ cand_label, isx_instance *__restrict__ out,
+                                      int *__restrict__ out_count, int inst_cap, KParams p) {
+  const int f = blockIdx.x;
+  const size_t cap = (size_t)p.realcols * kMaxSections;
+  int base = 0;
+  for (int k = 0; k < kInstanceClasses; k++) {
+    const int n = cand_count[f * kInstanceClasses + k];
+    const size_t src = ((size_t)f * kInstanceClasses + k) * cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int dst = base + i;
+      if (dst < inst_cap) {
+        isx_instance r;
+        const int2 ci = cand_idx[src + i];
+        r.column = ci.x;
+        r.index = ci.y;
+        r.label = cand_label[src + i];
+        r.semantic_class = kFirstInstanceClass + k;
+        out[(size_t)f * inst_cap + dst] = r;
+      }
+    }
+    base += n;
+  }
+  if (threadIdx.x == 0) out_count[f] = base;
+}
+
+static const float *road_tables(isx_context *c, const isx_road &r) {
+  RoadKey key{r.vhor, r.camera_tilt, r.camera_height, r.alpha_ground};
+  auto it = c->road_cache.find(key);
+  if (it == c->road_cache.end()) {
+    if (c->road_cache.size() > 64) c->road_cache.clear();
+    std::vector<float> t((size_t)3 * c->model.rows);
+    c->model.ground_tables(r, t.data());
+    it = c->road_cache.emplace(key, std::move(t)).first;
+  }
+  return it->second.data();
+}
+
+// Enqueue the kernel sequence for `n` frames whose inputs are at d_disp/d_seg.
+// `slot` selects the pinned ground-table staging half; results land at frame
+// offset `first` of the per-batch result arrays.
+static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const float *d_disp,
+                         const int32_t *d_seg, const isx_road *roads, int slot) {
+  const KParams &kp = c->kp;
+  const int H = kp.rows, C = kp.realcols;
+  float *hg = c->h_ground + (size_t)slot * c->chunk * 3 * H;
+  int *hv = c->h_vhor + (size_t)slot * c->chunk;
+  for (int i = 0; i < n; i++) {
+    std::memcpy(hg + (size_t)i * 3 * H, road_tables(c, roads[i]), sizeof(float) * 3 * H);
+    hv[i] = H - roads[i].vhor - 1;  // Stixels.cu:377
+  }
+  cudaStream_t s = c->s_compute;
+  ISX_TRY(c, cudaMemcpyAsync(c->buf.ground, hg, sizeof(float) * 3 * H * n, cudaMemcpyHostToDevice, s));
+  ISX_TRY(c, cudaMemcpyAsync(c->buf.vhor, hv, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  BatchBuffers b = c->buf;
+  b.disparity = d_disp;
+  b.segmentation = d_seg;
+  b.sections = c->d_sections_all + (size_t)first * C * kMaxSections;
+  b.n_sections = c->d_nsections_all + (size_t)first * C;
+  launch_join_columns(kp, b, n, s);
+  if (pairwise) launch_frame_tables(kp, b, n, s);
+  launch_column_tables(kp, b, n, s);
+  launch_dp(kp, b, n, pairwise, s);
+  launch_emit(kp, b, n, pairwise, s);
+  launch_grouping(kp, b, n, s);
+  pack_instances_kernel<<<n, 256, 0, s>>>(b.cand_count, b.cand_idx, b.cand_label,
+                                          c->d_inst_all + (size_t)first * c->inst_cap,
+                                          c->d_inst_count_all + first, c->inst_cap, kp);
+  g_launch_count++;
+  ISX_TRY(c, cudaGetLastError());
+  c->last_chunk_first = first;
+  c->last_chunk_n = n;
+  c->last_pairwise = pairwise;
+  return ISX_OK;
+}
+
+static int check_ready(isx_context *c) {
+  if (!c) return fail(nullptr, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  if (!c->initialized) return fail(c, ISX_ERR_NOT_INITIALIZED, "Initialize() has not been called");
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return fail(c, ISX_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  return ISX_OK;
+}
+
+}  // namespace isx
+
+using namespace isx;
+
+extern "C" {
+
+int isx_abi_version(void) { return ISX_ABI_VERSION; }
+uint64_t isx_kernel_launch_count(void) { return g_launch_count; }
+const char *isx_last_error(isx_handle h) { return h ? h->last_error.c_str() : g_last_error.c_str(); }
+
+void isx_config_init(isx_config *c) {
+  // default member initialisers of StixelConfig (types.h:30-141)
+  c->rows = -1; c->cols = -1; c->max_dis = -1; c->invalid_disparity = -1.0f;
+  c->eps = -1; c->min_pts = -1; c->size_filter = -1;
+  c->n_semantic_classes = -1; c->n_offset_channels = -1;
+  c->prior_weight = -1; c->segmentation_weight = -1; c->instance_weight = -1; c->disparity_weight = -1;
+  c->pairwise = 0; c->column_step = -1;
+  c->focal = -1; c->baseline = -1; c->camera_center_x = -1; c->camera_center_y = -1;
+  c->sigma_disparity_object = 1.0f; c->sigma_disparity_ground = 2.0f; c->sigma_sky = 0.1f;
+  c->pout = 0.15f; c->pout_sky = 0.4f; c->pord = 0.2f; c->pgrav = 0.1f; c->pblg = 0.04f;
+  c->pground_given_nexist = 0.28; c->pobject_given_nexist = 0.44; c->psky_given_nexist = 0.28;
+  c->pnexist_dis = 0.25f;
+  c->pground = 1.0f / 3.0f; c->pobject = 1.0f / 3.0f; c->psky = 1.0f / 3.0f;
+  c->width_margin = 0;
+  c->sigma_camera_tilt = 0.05f; c->sigma_camera_height = 0.05f;
+  c->median_join = 0; c->epsilon = 3.0f; c->range_objects_z = 10.20f;
+  c->road_vdisparity_threshold = 0.2f;
+}
+
+int isx_create(isx_handle *out, int device) {
+  if (!out) return fail(nullptr, ISX_ERR_INVALID_ARGUMENT, "null out pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, ISX_ERR_CUDA,
+                std::string("no CUDA device: the stixel path has no CPU fallback (") + cudaGetErrorString(e) + ")");
+  if (device < 0 || device >= count) return fail(nullptr, ISX_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+  isx_context *c = new isx_context();
+  c->device = device;
+  *out = c;
+  return ISX_OK;
+}
+
+int isx_destroy(isx_handle h) {
+  if (!h) return ISX_OK;
+  if (h->initialized) isx_finish(h);
+  delete h;
+  return ISX_OK;
+}
+
+int isx_set_config(isx_handle h, const isx_config *cfg) {
+  if (!h || !cfg) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  const std::string err = validate_config(*cfg);
+  if (!err.empty()) return fail(h, ISX_ERR_INVALID_ARGUMENT, err);
+  h->model.apply(*cfg);
+  return ISX_OK;
+}
+
+int isx_set_disparity_parameters(isx_handle h, int rows, int cols, int max_dis, float invalid_disparity,
+                                 float sigma_disparity_object, float sigma_disparity_ground, float sigma_sky) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  HostModel &m = h->model;
+  m.rows = rows; m.cols = cols; m.max_dis = max_dis; m.invalid_disparity = invalid_disparity;
+  m.sigma_disparity_object = sigma_disparity_object; m.sigma_disparity_ground = sigma_disparity_ground;
+  m.sigma_sky = sigma_sky;
+  return ISX_OK;
+}
+int isx_set_segmentation_parameters(isx_handle h, int classes, int instance_channels) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  h->model.n_classes = classes;
+  h->model.n_channels = classes + instance_channels;
+  return ISX_OK;
+}
+int isx_set_clustering_parameters(isx_handle h, float eps, int min_pts, int size_filter) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  h->model.eps = eps; h->model.min_pts = min_pts; h->model.size_filter = size_filter;
+  if (h->initialized) {  // the reference writes these straight into m_params (Stixels.cu:395-400)
+    h->kp.eps_cluster = eps; h->kp.min_pts = min_pts; h->kp.size_filter = size_filter;
+  }
+  return ISX_OK;
+}
+int isx_set_weight_parameters(isx_handle h, float prior_weight, float disparity_weight, float segmentation_weight,
+                              float instance_weight) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  HostModel &m = h->model;
+  m.prior_weight = prior_weight; m.disparity_weight = disparity_weight; m.segmentation_weight = segmentation_weight;
+  m.instance_weight = 0.0;
+  if (segmentation_weight > 1e-5) {
+    m.instance_weight = instance_weight / segmentation_weight;
+    if (instance_weight < 1e-8) m.instance_weight = 0.0;
+  }
+  return ISX_OK;
+}
+int isx_set_probabilities(isx_handle h, float pout, float pout_sky, float pground_given_nexist,
+                          float pobject_given_nexist, float psky_given_nexist, float pnexist_dis, float pground,
+                          float pobject, float psky, float pord, float pgrav, float pblg) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  HostModel &m = h->model;
+  m.pout = pout; m.pout_sky = pout_sky;
+  m.pnexists_given_ground = (pground_given_nexist * pnexist_dis) / pground;
+  m.pnexists_given_object = (pobject_given_nexist * pnexist_dis) / pobject;
+  m.pnexists_given_sky = (psky_given_nexist * pnexist_dis) / psky;
+  m.pord = pord; m.pgrav = pgrav; m.pblg = pblg;
+  return ISX_OK;
+}
+int isx_set_camera_parameters(isx_handle h, float focal, float baseline, float sigma_camera_tilt,
+                              float sigma_camera_height, float camera_center_x, float camera_center_y) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  HostModel &m = h->model;
+  m.focal = focal; m.baseline = baseline;
+  m.sigma_camera_tilt = sigma_camera_tilt * (3.1416f) / 180.0f;
+  m.sigma_camera_height = sigma_camera_height;
+  m.camera_center_x = camera_center_x; m.camera_center_y = camera_center_y;
+  return ISX_OK;
+}
+int isx_set_model_parameters(isx_handle h, int column_step, int median_join, float epsilon, float range_objects_z,
+                             int width_margin) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  HostModel &m = h->model;
+  m.column_step = column_step; m.median_join = median_join != 0; m.epsilon = epsilon;
+  m.range_objects_z = range_objects_z; m.width_margin = width_margin;
+  return ISX_OK;
+}
+
+int isx_initialize(isx_handle h, int max_batch) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  if (h->initialized) return fail(h, ISX_ERR_INVALID_ARGUMENT, "already initialized: call Finish() first");
+  if (max_batch < 1) return fail(h, ISX_ERR_INVALID_ARGUMENT, "max_batch must be >= 1");
+  HostModel &m = h->model;
+  if (m.rows <= 0 || m.cols <= 0 || m.max_dis <= 0 || m.column_step <= 0)
+    return fail(h, ISX_ERR_INVALID_ARGUMENT, "configuration is not set");
+  if (m.rows > 1024)  // same limit as the reference's one-thread-per-row block (apps/run_cityscapes.cu:129-134)
+    return fail(h, ISX_ERR_UNSUPPORTED, "rows > 1024 is not supported");
+  if (m.max_dis > 256) return fail(h, ISX_ERR_UNSUPPORTED, "max_dis > 256 is not supported");
+  if (m.n_classes != 19 || m.n_channels != 21)
+    return fail(h, ISX_ERR_UNSUPPORTED, "the Cityscapes layout (19 classes + 2 offsets) is hard-wired like Cityscapes.h");
+  if (m.column_step > 16) return fail(h, ISX_ERR_UNSUPPORTED, "column_step > 16 is not supported");
+  ISX_TRY(h, cudaSetDevice(h->device));
+  m.derive();
+  fill_kparams(h);
+  const KParams &kp = h->kp;
+  const size_t H = kp.rows, W = kp.cols, C = kp.realcols, D = kp.max_dis;
+  if (C == 0) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no stixel columns");
+  h->max_batch = max_batch;
+  int chunk = 16;
+  if (const char *e = std::getenv("ISX_CHUNK")) chunk = std::atoi(e) > 0 ? std::atoi(e) : chunk;
+  h->chunk = chunk < max_batch ? chunk : max_batch;
+  const size_t ch = h->chunk, MB = max_batch;
+  const size_t cap = C * kMaxSections;
+  h->inst_cap = (int)(cap * kInstanceClasses < 16384 ? cap * kInstanceClasses : 16384);
+
+  ISX_TRY(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+  ISX_TRY(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+  ISX_TRY(h, cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_in_ready[i], cudaEventDisableTiming));
+    ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_in_free[i], cudaEventDisableTiming));
+  }
+  ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_chunk_done, cudaEventDisableTiming));
+
+  BatchBuffers &b = h->buf;
+  for (int i = 0; i < 2; i++) {
+    ISX_TRY(h, dev_alloc(h, &h->d_in_disp[i], ch * H * W));
+    ISX_TRY(h, dev_alloc(h, &h->d_in_seg[i], ch * seg_elems(h)));
+  }
+  ISX_TRY(h, dev_alloc(h, &h->d_single_disp, H * W));
+  ISX_TRY(h, dev_alloc(h, &h->d_single_seg, seg_elems(h)));
+  ISX_TRY(h, dev_alloc(h, &b.ground, ch * 3 * H));
+  ISX_TRY(h, dev_alloc(h, &b.vhor, ch));
+  ISX_TRY(h, dev_alloc(h, &b.stat, ch * H * kStatWords));
+  ISX_TRY(h, dev_alloc(h, &b.joined, ch * C * H));
+  ISX_TRY(h, dev_alloc(h, &b.records, ch * C * (H + 1) * kRecWords));
+  ISX_TRY(h, dev_alloc(h, &b.object_lut, ch * C * D * (size_t)kp.lut_stride));
+  ISX_TRY(h, dev_alloc(h, &b.dyn, ch * C * H * kDynWords));
+  ISX_TRY(h, dev_alloc(h, &b.dp, ch * C * H));
+  ISX_TRY(h, dev_alloc(h, &b.cand_count, ch * kInstanceClasses));
+  ISX_TRY(h, dev_alloc(h, &b.cand_offset, ch * (C + 1) * kInstanceClasses));
+  ISX_TRY(h, dev_alloc(h, &b.cand_xy, ch * kInstanceClasses * cap));
+  ISX_TRY(h, dev_alloc(h, &b.cand_idx, ch * kInstanceClasses * cap));
+  ISX_TRY(h, dev_alloc(h, &b.cand_core, ch * kInstanceClasses * cap));
+  ISX_TRY(h, dev_alloc(h, &b.cand_label, ch * kInstanceClasses * cap));
+  ISX_TRY(h, dev_alloc(h, &b.cand_scratch, ch * kInstanceClasses * cap));
+  ISX_TRY(h, dev_alloc(h, &b.error_flag, 1));
+  ISX_TRY(h, cudaMemset(b.error_flag, 0, sizeof(int)));
+  ISX_TRY(h, cudaMemset(b.dyn, 0, ch * C * H * kDynWords * sizeof(float)));
+  ISX_TRY(h, dev_alloc(h, &h->d_sections_all, MB * C * kMaxSections));
+  ISX_TRY(h, dev_alloc(h, &h->d_nsections_all, MB * C));
+  ISX_TRY(h, dev_alloc(h, &h->d_inst_all, MB * (size_t)h->inst_cap));
+  ISX_TRY(h, dev_alloc(h, &h->d_inst_count_all, MB));
+  ISX_TRY(h, dev_alloc(h, &h->d_export_cost, C * H * 3));
+  ISX_TRY(h, dev_alloc(h, &h->d_export_index, C * H * 3));
+
+  float *d_tmp = nullptr;
+  ISX_TRY(h, dev_alloc(h, &d_tmp, D * D));
+  ISX_TRY(h, cudaMemcpy(d_tmp, m.obj_cost_lut.data(), sizeof(float) * D * D, cudaMemcpyHostToDevice));
+  b.obj_cost_lut = d_tmp;
+  ISX_TRY(h, dev_alloc(h, &d_tmp, D));
+  ISX_TRY(h, cudaMemcpy(d_tmp, m.object_disparity_range.data(), sizeof(float) * D, cudaMemcpyHostToDevice));
+  b.object_disparity_range = d_tmp;
+  ISX_TRY(h, dev_alloc(h, &d_tmp, H + 1));
+  ISX_TRY(h, cudaMemcpy(d_tmp, m.inverse_height.data(), sizeof(float) * (H + 1), cudaMemcpyHostToDevice));
+  b.inverse_height = d_tmp;
+
+  ISX_TRY(h, cudaMallocHost(&h->h_ground, sizeof(float) * 2 * ch * 3 * H));
+  ISX_TRY(h, cudaMallocHost(&h->h_vhor, sizeof(int) * 2 * ch));
+  ISX_TRY(h, cudaMallocHost(&h->h_inst, sizeof(isx_instance) * MB * h->inst_cap));
+  ISX_TRY(h, cudaMallocHost(&h->h_inst_count, sizeof(int) * MB));
+  ISX_TRY(h, cudaMallocHost(&h->h_error, sizeof(int)));
+  h->road_cache.clear();
+  h->initialized = true;
+  h->last_batch = 0;
+  return ISX_OK;
+}
+
+int isx_finish(isx_handle h) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  if (!h->initialized) return ISX_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void *p : h->allocations) cudaFree(p);
+  h->allocations.clear();
+  cudaFreeHost(h->h_ground);
+  cudaFreeHost(h->h_vhor);
+  cudaFreeHost(h->h_inst);
+  cudaFreeHost(h->h_inst_count);
+  cudaFreeHost(h->h_error);
+  for (int i = 0; i < 2; i++) {
+    cudaEventDestroy(h->ev_in_ready[i]);
+    cudaEventDestroy(h->ev_in_free[i]);
+  }
+  cudaEventDestroy(h->ev_chunk_done);
+  cudaStreamDestroy(h->s_compute);
+  cudaStreamDestroy(h->s_h2d);
+  cudaStreamDestroy(h->s_d2h);
+  h->buf = BatchBuffers();
+  h->initialized = false;
+  return ISX_OK;
+}
+
+int isx_is_initialized(isx_handle h) { return h && h->initialized; }
+int isx_real_cols(isx_handle h) { return h ? (h->initialized ? h->kp.realcols : 0) : 0; }
+int isx_max_sections(isx_handle h) { (void)h; return kMaxSections; }
+size_t isx_segmentation_elems(isx_handle h) { return (h && h->initialized) ? seg_elems(h) : 0; }
+
+int isx_set_disparity_image(isx_handle h, const float *host, size_t n) {
+  if (int rc = check_ready(h)) return rc;
+  if (!host || n != (size_t)h->kp.rows * h->kp.cols)
+    return fail(h, ISX_ERR_INVALID_ARGUMENT, "disparity image must hold rows*cols floats");
+  ISX_TRY(h, cudaMemcpyAsync(h->d_single_disp, host, n * sizeof(float), cudaMemcpyHostToDevice, h->s_compute));
+  return ISX_OK;
+}
+
+float *isx_input_disparity_device(isx_handle h) { return (h && h->initialized) ? h->d_single_disp : nullptr; }
+
+int isx_set_segmentation(isx_handle h, const int32_t *host, size_t n) {
+  if (int rc = check_ready(h)) return rc;
+  if (!host || n != seg_elems(h))
+    return fail(h, ISX_ERR_INVALID_ARGUMENT, "segmentation must hold realcols*channels*rows_power2_segmentation ints");
+  ISX_TRY(h, cudaMemcpyAsync(h->d_single_seg, host, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_compute));
+  return ISX_OK;
+}
+
+int isx_set_road_parameters(isx_handle h, int vhor, float camera_tilt, float camera_height, float alpha_ground) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  h->single_road = isx_road{vhor, camera_tilt, camera_height, alpha_ground};
+  h->single_has_road = true;
+  return ISX_OK;
+}
+
+static int fetch_results(isx_handle h, int n, isx_section *sections, isx_instance *instances, int instances_capacity,
+                         int32_t *instance_offsets, cudaStream_t s) {
+  const size_t C = h->kp.realcols;
+  if (sections)
+    ISX_TRY(h, cudaMemcpyAsync(sections, h->d_sections_all, sizeof(isx_section) * n * C * kMaxSections,
+                               cudaMemcpyDeviceToHost, s));
+  ISX_TRY(h, cudaMemcpyAsync(h->h_inst_count, h->d_inst_count_all, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  ISX_TRY(h, cudaMemcpyAsync(h->h_error, h->buf.error_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (instances || instance_offsets)
+    ISX_TRY(h, cudaMemcpyAsync(h->h_inst, h->d_inst_all, sizeof(isx_instance) * n * (size_t)h->inst_cap,
+                               cudaMemcpyDeviceToHost, s));
+  ISX_TRY(h, cudaStreamSynchronize(s));
+  if (*h->h_error) return fail(h, ISX_ERR_CAPACITY, "a column produced >= 200 stixels (MAX_STIXELS_PER_COLUMN)");
+  if (instances || instance_offsets) {
+    int total = 0;
+    for (int f = 0; f < n; f++) {
+      if (instance_offsets) instance_offsets[f] = total;
+      const int cnt = h->h_inst_count[f] < h->inst_cap ? h->h_inst_count[f] : h->inst_cap;
+      if (h->h_inst_count[f] > h->inst_cap)
+        return fail(h, ISX_ERR_CAPACITY, "more instance stixels in one frame than the packed result can hold");
+      if (instances) {
+        const int room = instances_capacity - total;
+        const int take = cnt < room ? cnt : (room > 0 ? room : 0);
+        std::memcpy(instances + total, h->h_inst + (size_t)f * h->inst_cap, sizeof(isx_instance) * take);
+      }
+      total += cnt;
+    }
+    if (instance_offsets) instance_offsets[n] = total;
+  }
+  return ISX_OK;
+}
+
+int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_meta *meta,
+                const int32_t *d_segmentation_local) {
+  if (int rc = check_ready(h)) return rc;
+  if (!h->single_has_road) return fail(h, ISX_ERR_INVALID_ARGUMENT, "SetRoadParameters has not been called");
+  const int32_t *seg = d_segmentation_local ? d_segmentation_local : h->d_single_seg;
+  if (int rc = enqueue_chunk(h, pairwise != 0, 0, 1, h->d_single_disp, seg, &h->single_road, 0)) return rc;
+  h->last_batch = 1;
+  h->last_roads.assign(1, h->single_road);
+  if (int rc = fetch_results(h, 1, sections, nullptr, 0, nullptr, h->s_compute)) return rc;
+  if (meta) {
+    meta->rows = h->kp.rows; meta->cols = h->kp.cols; meta->realcols = h->kp.realcols;
+    meta->max_sections = kMaxSections; meta->max_dis = h->kp.max_dis; meta->column_step = h->kp.column_step;
+    meta->semantic_classes = h->kp.n_classes; meta->alpha_ground = h->single_road.alpha_ground;
+    meta->vhor = h->kp.rows - h->single_road.vhor - 1;
+  }
+  return ISX_OK;
+}
+
+int isx_cluster_instances(isx_handle h) { return check_ready(h); }
+
+int isx_get_instance_stixels(isx_handle h, isx_instance *out, int capacity, int *n) {
+  if (int rc = check_ready(h)) return rc;
+  if (h->last_batch < 1) return fail(h, ISX_ERR_INVALID_ARGUMENT, "Compute has not been called");
+  int32_t offs[2] = {0, 0};
+  if (int rc = fetch_results(h, 1, nullptr, out, out ? capacity : 0, offs, h->s_compute)) return rc;
+  if (n) *n = offs[1];
+  return ISX_OK;
+}
+
+int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_disparity,
+                             const int32_t *d_segmentation, const isx_road *roads) {
+  if (int rc = check_ready(h)) return rc;
+  if (n < 1 || n > h->max_batch) return fail(h, ISX_ERR_CAPACITY, "batch size exceeds isx_initialize(max_batch)");
+  if (!d_disparity || !d_segmentation || !roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  const size_t hw = (size_t)h->kp.rows * h->kp.cols, se = seg_elems(h);
+  int slot = 0;
+  for (int first = 0; first < n; first += h->chunk) {
+    const int cn = (n - first) < h->chunk ? (n - first) : h->chunk;
+    // the pinned ground staging half must not be rewritten while its copy is in flight
+    ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[slot]));
+    if (int rc = enqueue_chunk(h, pairwise != 0, first, cn, d_disparity + first * hw, d_segmentation + first * se,
+                               roads + first, slot))
+      return rc;
+    ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_compute));
+    slot ^= 1;
+  }
+  h->last_batch = n;
+  h->last_roads.assign(roads, roads + n);
+  return ISX_OK;
+}
+
+int isx_synchronize(isx_handle h) {
+  if (int rc = check_ready(h)) return rc;
+  ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
+  return ISX_OK;
+}
+
+int isx_fetch_batch_results(isx_handle h, int n, isx_section *sections, isx_instance *instances,
+                            int instances_capacity, int32_t *instance_offsets) {
+  if (int rc = check_ready(h)) return rc;
+  if (n < 1 || n > h->last_batch) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no results for that many frames");
+  return fetch_results(h, n, sections, instances, instances_capacity, instance_offsets, h->s_compute);
+}
+
+int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
+                           const isx_road *roads, isx_section *sections, isx_instance *instances,
+                           int instances_capacity, int32_t *instance_offsets) {
+  if (int rc = check_ready(h)) return rc;
+  if (n < 1 || n > h->max_batch) return fail(h, ISX_ERR_CAPACITY, "batch size exceeds isx_initialize(max_batch)");
+  if (!disparity || !segmentation || !roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  const size_t hw = (size_t)h->kp.rows * h->kp.cols, se = seg_elems(h);
+  const size_t C = h->kp.realcols;
+  int slot = 0;
+  for (int first = 0; first < n; first += h->chunk) {
+    const int cn = (n - first) < h->chunk ? (n - first) : h->chunk;
+    // H2D of this chunk on the copy stream, once the kernels that last read this slot are done
+    ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_in_free[slot], 0));
+    ISX_TRY(h, cudaMemcpyAsync(h->d_in_disp[slot], disparity + first * hw, sizeof(float) * hw * cn,
+                               cudaMemcpyHostToDevice, h->s_h2d));
+    ISX_TRY(h, cudaMemcpyAsync(h->d_in_seg[slot], segmentation + first * se, sizeof(int32_t) * se * cn,
+                               cudaMemcpyHostToDevice, h->s_h2d));
+    ISX_TRY(h, cudaEventRecord(h->ev_in_ready[slot], h->s_h2d));
+    ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[slot]));  // pinned ground staging of this slot is reusable
+    ISX_TRY(h, cudaStreamWaitEvent(h->s_compute, h->ev_in_ready[slot], 0));
+    if (int rc = enqueue_chunk(h, pairwise != 0, first, cn, h->d_in_disp[slot], h->d_in_seg[slot], roads + first,
+                               slot))
+      return rc;
+    ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_compute));
+    // D2H of this chunk's sections overlaps the next chunk's kernels
+    if (sections) {
+      ISX_TRY(h, cudaStreamWaitEvent(h->s_d2h, h->ev_in_free[slot], 0));
+      ISX_TRY(h, cudaMemcpyAsync(sections + (size_t)first * C * kMaxSections,
+                                 h->d_sections_all + (size_t)first * C * kMaxSections,
+                                 sizeof(isx_section) * cn * C * kMaxSections, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    slot ^= 1;
+  }
+  h->last_batch = n;
+  h->last_roads.assign(roads, roads + n);
+  if (int rc = fetch_results(h, n, nullptr, instances, instances_capacity, instance_offsets, h->s_compute)) return rc;
+  ISX_TRY(h, cudaStreamSynchronize(h->s_d2h));
+  return ISX_OK;
+}
+
+uint64_t isx_stream(isx_handle h) { return (h && h->initialized) ? (uint64_t)(uintptr_t)h->s_compute : 0; }
+
+size_t isx_tensor_elems(isx_handle h, int tensor) {
+  if (!h || !h->initialized) return 0;
+  const size_t H = h->kp.rows, C = h->kp.realcols, D = h->kp.max_dis;
+  switch (tensor) {
+    case ISX_T_JOINED_DISPARITY: return C * H;
+    case ISX_T_OBJECT_LUT: return C * D * (H + 1);
+    case ISX_T_DISPARITY_PS:
+    case ISX_T_VALID_PS:
+    case ISX_T_GROUND_PS:
+    case ISX_T_SKY_PS: return C * (H + 1);
+    case ISX_T_COST_TABLE:
+    case ISX_T_INDEX_TABLE: return C * H * 3;
+    case ISX_T_GROUND_TABLES: return 3 * H;
+    case ISX_T_OBJ_COST_LUT: return D * D;
+    case ISX_T_OBJECT_DISPARITY_RANGE: return D;
+    default: return 0;
+  }
+}
+
+int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t bytes) {
+  if (int rc = check_ready(h)) return rc;
+  const size_t need = isx_tensor_elems(h, tensor) * 4;
+  if (need == 0 || !host || bytes < need) return fail(h, ISX_ERR_INVALID_ARGUMENT, "bad tensor id or buffer too small");
+  const int local = frame - h->last_chunk_first;
+  if (local < 0 || local >= h->last_chunk_n)
+    return fail(h, ISX_ERR_INVALID_ARGUMENT, "intermediates are only kept for the last chunk of the last batch");
+  ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
+  const KParams &kp = h->kp;
+  const size_t H = kp.rows, C = kp.realcols, D = kp.max_dis;
+  const BatchBuffers &b = h->buf;
+  if (tensor == ISX_T_GROUND_TABLES) {
+    ISX_TRY(h, cudaMemcpy(host, b.ground + (size_t)local * 3 * H, need, cudaMemcpyDeviceToHost));
+  } else if (tensor == ISX_T_OBJ_COST_LUT) {
+    ISX_TRY(h, cudaMemcpy(host, b.obj_cost_lut, need, cudaMemcpyDeviceToHost));
+  } else if (tensor == ISX_T_OBJECT_DISPARITY_RANGE) {
+    ISX_TRY(h, cudaMemcpy(host, b.object_disparity_range, need, cudaMemcpyDeviceToHost));
+  } else if (tensor == ISX_T_JOINED_DISPARITY) {
+    ISX_TRY(h, cudaMemcpy(host, b.joined + (size_t)local * C * H, need, cudaMemcpyDeviceToHost));
+  } else if (tensor == ISX_T_OBJECT_LUT) {
+    // device rows hold LUT[fn][1..H]; the reference layout has a leading 0 (StixelsKernels.cu:283-285)
+    float *dst = static_cast<float *>(host);
+    for (size_t r = 0; r < C * D; r++) dst[r * (H + 1)] = 0.0f;
+    ISX_TRY(h, cudaMemcpy2D(dst + 1, (H + 1) * 4, b.object_lut + (size_t)local * C * D * kp.lut_stride,
+                            (size_t)kp.lut_stride * 4, H * 4, C * D, cudaMemcpyDeviceToHost));
+  } else if (tensor >= ISX_T_DISPARITY_PS && tensor <= ISX_T_SKY_PS) {
+    const int word = tensor == ISX_T_DISPARITY_PS ? kRecDisp
+                     : tensor == ISX_T_VALID_PS   ? kRecValid
+                     : tensor == ISX_T_GROUND_PS  ? kRecGround
+                                                  : kRecSky;
+    ISX_TRY(h, cudaMemcpy2D(host, 4, b.records + (size_t)local * C * (H + 1) * kRecWords + word, kRecWords * 4, 4,
+                            C * (H + 1), cudaMemcpyDeviceToHost));
+  } else {
+    launch_export_tables(kp, b, local, h->last_pairwise, h->d_export_cost, h->d_export_index, h->s_compute);
+    ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
+    ISX_TRY(h, cudaMemcpy(host, tensor == ISX_T_COST_TABLE ? (void *)h->d_export_cost : (void *)h->d_export_index,
+                          need, cudaMemcpyDeviceToHost));
+  }
+  return ISX_OK;
+}
+
+}  // extern "C"

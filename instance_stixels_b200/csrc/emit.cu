@@ -1,0 +1,329 @@
+// Backtracking and stixel emission on the device, plus deterministic
+// collection of the instance-grouping candidates.
+// Replaces the thread-0 tail of StixelsKernel (InstanceStixels/src/
+// StixelsKernels.cu:843-955).
+//
+// The DP keeps (cost, argmin vB) per row and slot; the predecessor TYPE the
+// reference stores in index_table is re-derived here from the final row costs
+// with the same float operations (dp_common.cuh), only for the handful of
+// cells on the optimal path.  The reference appends candidates with a global
+// atomicAdd (:926-941), i.e. in nondeterministic order; here they are
+// compacted in (class, column, index-from-top) order.
+#include "dp_common.cuh"
+#include "kernels.h"
+
+namespace isx {
+
+namespace {
+
+struct Rec {
+  uint32_t w[kRecWords];
+};
+
+__device__ __forceinline__ Rec load_rec(const uint4 *rec, int v) {
+  Rec r;
+  const uint4 *s = rec + (size_t)v * (kRecWords / 4);
+#pragma unroll
+  for (int k = 0; k < kRecWords / 4; k++) {
+    const uint4 t = __ldg(s + k);
+    r.w[4 * k] = t.x; r.w[4 * k + 1] = t.y; r.w[4 * k + 2] = t.z; r.w[4 * k + 3] = t.w;
+  }
+  return r;
+}
+
+__device__ __forceinline__ long long rec_i64(const Rec &r, int w) {
+  return (long long)(((unsigned long long)r.w[w + 1] << 32) | r.w[w]);
+}
+
+__device__ __forceinline__ int seg_sum(const Rec &hi, const Rec &lo, int c) { return (int)(hi.w[c] - lo.w[c]); }
+
+// GetObjectSegmentationClass (Cityscapes.h:85-111): classes 2..18 without sky,
+// strict '>' so the lowest class wins ties; costs as floats like the reference.
+__device__ int object_class(const Rec &hi, const Rec &lo, float ic, float nic) {
+  float best = inf_f();
+  int cls = 2;
+  for (int c = 2; c < 19; c++) {
+    if (c == kSkyClass) continue;
+    float cost = fadd(0.0f, c < kSkyClass ? nic : ic);
+    cost = fadd(cost, (float)seg_sum(hi, lo, c));
+    if (best > cost) {
+      best = cost;
+      cls = c;
+    }
+  }
+  return cls;
+}
+
+// Priors that decide the predecessor type of the segment (vB..vT) of `type`.
+template <bool PAIRWISE>
+__device__ int predecessor_type(int type, int vB, float fn_clamped, const float4 *dp_col, const uint4 *rec,
+                                const float *S, const float *Q, int vhor,
+                                const float *__restrict__ object_disparity_range, const KParams &p) {
+  const int pv = vB - 1;
+  const float4 prev = dp_col[pv];
+  const bool ground_side = pv < vhor;
+  const float inf = inf_f();
+  const float cg = ground_side ? prev.x : inf, cs = ground_side ? inf : prev.x, co = prev.y;
+  if constexpr (!PAIRWISE) {
+    // unary: raw previous costs pick the type (:694-697, 723-727, 782-787, 828-835)
+    if (type != OBJECT) return prev_type_gs(cg, co);
+    return prev_type_obj(cg, co, cs);
+  } else {
+    const float pm = Q[(size_t)vB * kDynWords + 11];
+    RowPriors rp;
+    const RowInfo q = make_row_info(S + (size_t)vB * kStatWords, ground_side, cg, co, cs, pm,
+                                    object_disparity_range, p, &rp);
+    if (type != OBJECT) return prev_type_gs(rp.g1, rp.g2);
+    float p1, p2, p3;
+    object_priors(q, ground_side, fn_clamped, p.epsilon, p1, p2, p3);
+    // the reference compares the actual three priors; p1/p3 are +inf on the
+    // side where C[p][GROUND] / C[p][SKY] are +inf
+    return prev_type_obj(p1, p2, p3);
+  }
+}
+
+template <bool PAIRWISE>
+__global__ void __launch_bounds__(128)
+backtrack_kernel(const uint4 *__restrict__ records, const float4 *__restrict__ dp, const float *__restrict__ stat,
+                 const float *__restrict__ dyn, const int *__restrict__ vhor_arr,
+                 const float *__restrict__ object_disparity_range, isx_section *__restrict__ sections,
+                 int *__restrict__ n_sections, int *error_flag, int ncolumns, KParams p) {
+  const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gcol >= ncolumns) return;
+  const int H = p.rows, C = p.realcols;
+  const int f = gcol / C;
+  const int vhor = vhor_arr[f];
+  const bool has_invalid = p.invalid_disparity >= 0.0f;
+  const uint4 *rec = records + (size_t)gcol * p.rec_rows * (kRecWords / 4);
+  const float4 *dp_col = dp + (size_t)gcol * H;
+  const float *S = stat + (size_t)f * H * kStatWords;
+  const float *Q = dyn + (size_t)gcol * H * kDynWords;
+  isx_section *out = sections + (size_t)gcol * kMaxSections;
+  const float inf = inf_f();
+
+  int vT = H - 1;
+  // top row: OBJECT is the fallback type (:846-861)
+  int type = OBJECT;
+  {
+    const float4 top = dp_col[vT];
+    const float last_ground = vT < vhor ? top.x : inf, last_sky = vT < vhor ? inf : top.x, last_object = top.y;
+    if (last_ground < last_object) type = GROUND;
+    if (last_sky < fmin_(last_ground, last_object)) type = SKY;
+  }
+  int i = 0;
+  while (true) {
+    const float4 row = dp_col[vT];
+    const int vB = (type == OBJECT) ? __float_as_int(row.w) : __float_as_int(row.z);
+    const float cost = (type == OBJECT) ? row.y : row.x;
+    const Rec hi = load_rec(rec, vT + 1), lo = load_rec(rec, vB);
+    const int n = vT + 1 - vB;
+
+    isx_section sec;
+    sec.vT = vT;
+    sec.vB = vB;
+    sec.type = type;
+    // ComputeMean without the clamp (:872-875)
+    float mean;
+    {
+      const float sd = fsub(__uint_as_float(hi.w[kRecDisp]), __uint_as_float(lo.w[kRecDisp]));
+      if (has_invalid) {
+        const float vd = fsub(__uint_as_float(hi.w[kRecValid]), __uint_as_float(lo.w[kRecValid]));
+        mean = (vd != 0.0f) ? fmul(sd, rcp_approx(vd)) : 0.0f;
+      } else {
+        mean = fmul(sd, rcp_approx((float)n));
+      }
+    }
+    sec.disparity = mean;
+    sec.cost = fmin_(cost, 10000.0f);
+    const float rn = rcp_approx((float)n);
+    const float fmx = __ll2float_rn(rec_i64(hi, kRecMx) - rec_i64(lo, kRecMx));
+    const float fmy = __ll2float_rn(rec_i64(hi, kRecMy) - rec_i64(lo, kRecMy));
+    sec.instance_meanx = fmul(fmx, rn);
+    sec.instance_meany = fmul(fmy, rn);
+
+    if (type == GROUND) {
+      // GetGroundSegmentationClass (Cityscapes.h:52-58)
+      sec.semantic_class = ((float)seg_sum(hi, lo, 0) < (float)seg_sum(hi, lo, 1)) ? 0 : 1;
+    } else if (type == SKY || sec.disparity < 1.0f) {
+      sec.type = SKY;  // far objects become sky (:894-902)
+      sec.semantic_class = kSkyClass;
+    } else {
+      const float fmx2 = __ll2float_rn(rec_i64(hi, kRecMx2) - rec_i64(lo, kRecMx2));
+      const float fmy2 = __ll2float_rn(rec_i64(hi, kRecMy2) - rec_i64(lo, kRecMy2));
+      const float var = ffma(-fmul(fmy, fmy), rn, fadd(fmy2, ffma(-fmul(fmx, fmx), rn, fmx2)));
+      const float ic = fmul(var, p.instance_weight);
+      const float nic = fmul((float)seg_sum(hi, lo, kRecOff), p.instance_weight);
+      sec.semantic_class = object_class(hi, lo, ic, nic);
+    }
+    out[i] = sec;
+    i++;
+    if (vB == 0) break;
+    if (i >= kMaxSections - 1) {  // reference: assert(i < max_sections) (:950)
+      atomicExch(error_flag, 1);
+      break;
+    }
+    type = predecessor_type<PAIRWISE>(type, vB, clamp_neg(mean), dp_col, rec, S, Q, vhor, object_disparity_range, p);
+    vT = vB - 1;
+  }
+  isx_section term;
+  term.type = -1;
+  term.vB = term.vT = 0;
+  term.disparity = term.cost = term.instance_meanx = term.instance_meany = 0.0f;
+  term.semantic_class = 0;
+  out[i] = term;
+  n_sections[gcol] = i;
+}
+
+// One CTA per frame: count instance stixels per (column, class), scan over
+// columns, then write the candidates in (class, column, index) order.
+__global__ void __launch_bounds__(256)
+collect_candidates_kernel(const isx_section *__restrict__ sections, const int *__restrict__ n_sections,
+                          int *__restrict__ cand_count, int *__restrict__ cand_offset, float2 *__restrict__ cand_xy,
+                          int2 *__restrict__ cand_idx, uint8_t *__restrict__ cand_core, KParams p) {
+  __shared__ int warp_tot[8][kInstanceClasses];
+  __shared__ int running[kInstanceClasses];
+  const int f = blockIdx.x, C = p.realcols;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const isx_section *fs = sections + (size_t)f * C * kMaxSections;
+  const int *ns = n_sections + (size_t)f * C;
+  int *off = cand_offset + (size_t)f * (C + 1) * kInstanceClasses;
+  const size_t cap = (size_t)C * kMaxSections;
+  if (tid < kInstanceClasses) running[tid] = 0;
+  __syncthreads();
+  for (int base = 0; base < C; base += 256) {
+    const int col = base + tid;
+    int cnt[kInstanceClasses];
+#pragma unroll
+    for (int k = 0; k < kInstanceClasses; k++) cnt[k] = 0;
+    if (col < C) {
+      const int n = ns[col];
+      for (int j = 0; j < n; j++) {
+        const isx_section s = fs[(size_t)col * kMaxSections + j];
+        if (s.type == OBJECT && s.semantic_class >= kFirstInstanceClass) cnt[s.semantic_class - kFirstInstanceClass]++;
+      }
+    }
+    int excl[kInstanceClasses];
+#pragma unroll
+    for (int k = 0; k < kInstanceClasses; k++) {
+      int incl = cnt[k];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      excl[k] = incl - cnt[k];
+      if (lane == 31) warp_tot[warp][k] = incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kInstanceClasses; k++) {
+      int before = running[k];
+      for (int w = 0; w < warp; w++) before += warp_tot[w][k];
+      excl[k] += before;
+    }
+    if (col < C) {
+#pragma unroll
+      for (int k = 0; k < kInstanceClasses; k++) off[(size_t)col * kInstanceClasses + k] = excl[k];
+      const int n = ns[col];
+      for (int j = 0; j < n; j++) {
+        const isx_section s = fs[(size_t)col * kMaxSections + j];
+        if (s.type == OBJECT && s.semantic_class >= kFirstInstanceClass) {
+          const int k = s.semantic_class - kFirstInstanceClass;
+          const size_t dst = ((size_t)f * kInstanceClasses + k) * cap + excl[k]++;
+          cand_xy[dst] = make_float2(s.instance_meanx, s.instance_meany);
+          cand_idx[dst] = make_int2(col, j);
+          cand_core[dst] = (s.vT + 1 - s.vB) >= p.size_filter;  // core candidate = size filter (:940-941)
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < kInstanceClasses) {
+      int t = running[tid];
+      for (int w = 0; w < 8; w++) t += warp_tot[w][tid];
+      running[tid] = t;
+    }
+    __syncthreads();
+  }
+  if (tid < kInstanceClasses) {
+    cand_count[f * kInstanceClasses + tid] = running[tid];
+    off[(size_t)C * kInstanceClasses + tid] = running[tid];
+  }
+}
+
+// cost_table / index_table in the reference's layout (parity tests only).
+template <bool PAIRWISE>
+__global__ void export_tables_kernel(const uint4 *__restrict__ records, const float4 *__restrict__ dp,
+                                     const float *__restrict__ stat, const float *__restrict__ dyn,
+                                     const int *__restrict__ vhor_arr,
+                                     const float *__restrict__ object_disparity_range, int frame,
+                                     float *__restrict__ cost_table, int *__restrict__ index_table, KParams p) {
+  const int H = p.rows, C = p.realcols;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * H) return;
+  const int col = idx / H, vT = idx - col * H;
+  const int gcol = frame * C + col;
+  const int vhor = vhor_arr[frame];
+  const bool has_invalid = p.invalid_disparity >= 0.0f;
+  const uint4 *rec = records + (size_t)gcol * p.rec_rows * (kRecWords / 4);
+  const float4 *dp_col = dp + (size_t)gcol * H;
+  const float *S = stat + (size_t)frame * H * kStatWords;
+  const float *Q = dyn + (size_t)gcol * H * kDynWords;
+  const float4 row = dp_col[vT];
+  const float inf = inf_f();
+  float *ct = cost_table + ((size_t)col * H + vT) * 3;
+  int *it = index_table + ((size_t)col * H + vT) * 3;
+  const int gs_type = vT < vhor ? GROUND : SKY;
+  ct[GROUND] = gs_type == GROUND ? row.x : inf;
+  ct[SKY] = gs_type == SKY ? row.x : inf;
+  ct[OBJECT] = row.y;
+  it[GROUND] = it[SKY] = it[OBJECT] = -1;
+  for (int t = 0; t < 2; t++) {
+    const int type = t == 0 ? gs_type : OBJECT;
+    const float c = t == 0 ? row.x : row.y;
+    const int vB = __float_as_int(t == 0 ? row.z : row.w);
+    if (!(c < inf) && !(type == OBJECT && vB == 0)) continue;
+    if (vB == 0) {
+      it[type] = type == GROUND ? GROUND : OBJECT;  // (:564, 592)
+      continue;
+    }
+    const Rec hi = load_rec(rec, vT + 1), lo = load_rec(rec, vB);
+    const float fn = segment_mean(__uint_as_float(hi.w[kRecDisp]), __uint_as_float(lo.w[kRecDisp]),
+                                  __uint_as_float(hi.w[kRecValid]), __uint_as_float(lo.w[kRecValid]),
+                                  vT + 1 - vB, has_invalid);
+    it[type] = vB * 3 + predecessor_type<PAIRWISE>(type, vB, fn, dp_col, rec, S, Q, vhor, object_disparity_range, p);
+  }
+}
+
+}  // namespace
+
+void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s) {
+  const int ncolumns = nframes * p.realcols;
+  const int grid = (ncolumns + 127) / 128;
+  const uint4 *rec = reinterpret_cast<const uint4 *>(b.records);
+  if (pairwise)
+    backtrack_kernel<true><<<grid, 128, 0, s>>>(rec, b.dp, b.stat, b.dyn, b.vhor, b.object_disparity_range,
+                                                b.sections, b.n_sections, b.error_flag, ncolumns, p);
+  else
+    backtrack_kernel<false><<<grid, 128, 0, s>>>(rec, b.dp, b.stat, b.dyn, b.vhor, b.object_disparity_range,
+                                                 b.sections, b.n_sections, b.error_flag, ncolumns, p);
+  collect_candidates_kernel<<<nframes, 256, 0, s>>>(b.sections, b.n_sections, b.cand_count, b.cand_offset, b.cand_xy,
+                                                     b.cand_idx, b.cand_core, p);
+  g_launch_count += 2;
+}
+
+void launch_export_tables(const KParams &p, const BatchBuffers &b, int frame, bool pairwise, float *cost_table,
+                          int *index_table, cudaStream_t s) {
+  const int n = p.realcols * p.rows;
+  const uint4 *rec = reinterpret_cast<const uint4 *>(b.records);
+  if (pairwise)
+    export_tables_kernel<true><<<(n + 127) / 128, 128, 0, s>>>(rec, b.dp, b.stat, b.dyn, b.vhor,
+                                                               b.object_disparity_range, frame, cost_table,
+                                                               index_table, p);
+  else
+    export_tables_kernel<false><<<(n + 127) / 128, 128, 0, s>>>(rec, b.dp, b.stat, b.dyn, b.vhor,
+                                                                b.object_disparity_range, frame, cost_table,
+                                                                index_table, p);
+  g_launch_count++;
+}
+
+}  // namespace isx

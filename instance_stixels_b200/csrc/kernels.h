@@ -1,0 +1,57 @@
+// Launchers of the sm_100a kernels (one translation unit per stage).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/instance_stixels_b200.h"
+#include "common.cuh"
+
+namespace isx {
+
+// Device buffers of one batch (B frames).  Layouts are documented in DESIGN.md.
+struct BatchBuffers {
+  // inputs
+  const float *disparity = nullptr;    // [B][H][W]
+  const int32_t *segmentation = nullptr;  // [B][C][21][Hs2]
+  // per-frame road tables
+  float *ground = nullptr;             // [B][3][H]: ground_function | normalization | inv_sigma2
+  int *vhor = nullptr;                 // [B] flipped horizon row
+  float *stat = nullptr;               // [B][H][kStatWords] static transition records (pairwise)
+  // intermediates
+  float *joined = nullptr;             // [B][C][H]
+  uint32_t *records = nullptr;         // [B][C][H+1][32 words]
+  float *object_lut = nullptr;         // [B][C][D][lut_stride]
+  float *dyn = nullptr;                // [B][C][H][kDynWords] dynamic row info (pairwise)
+  float4 *dp = nullptr;                // [B][C][H]: {cost_gs, cost_obj, as_float(vB_gs), as_float(vB_obj)}
+  // model tables (device copies of HostModel vectors)
+  const float *obj_cost_lut = nullptr;       // [D][D]
+  const float *object_disparity_range = nullptr;  // [D]
+  const float *inverse_height = nullptr;     // [H+1]
+  // outputs
+  isx_section *sections = nullptr;     // [B][C][200]
+  int *n_sections = nullptr;           // [B][C] stixels per column
+  // instance candidates, per frame and instance class, column-major stable order
+  int *cand_count = nullptr;           // [B][8]
+  int *cand_offset = nullptr;          // [B][C+1][8] exclusive prefix over columns (per class)
+  float2 *cand_xy = nullptr;           // [B][8][C*200]
+  int2 *cand_idx = nullptr;            // [B][8][C*200] (column, index)
+  uint8_t *cand_core = nullptr;        // [B][8][C*200] size filter
+  int *cand_label = nullptr;           // [B][8][C*200]
+  int *cand_scratch = nullptr;         // [B][8][C*200] component representatives
+  int *error_flag = nullptr;           // [1] sticky: column overflowed 200 stixels etc.
+};
+
+void launch_join_columns(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
+void launch_frame_tables(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
+void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
+void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s);
+void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s);
+void launch_grouping(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
+// reference-format views for the parity tests
+void launch_export_tables(const KParams &p, const BatchBuffers &b, int frame, bool pairwise, float *cost_table,
+                          int *index_table, cudaStream_t s);
+
+extern unsigned long long g_launch_count;
+int set_kernel_attributes();
+
+}  // namespace isx

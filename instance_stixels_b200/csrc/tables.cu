@@ -1,0 +1,339 @@
+// Per-column cost tables ("table build").
+//
+//   frame_tables_kernel  : per frame, the vB-only parts of the pairwise
+//                          transition priors (StixelsKernels.cu:40-42, 98-144,
+//                          173-187) -- they depend on the road model only.
+//   column_tables_kernel : per (frame, column): per-row data costs
+//                          (:371-446), the prefix sums the reference computes
+//                          with in-kernel Blelloch scans (:452-469,
+//                          StixelsKernels.h:73-103) and the object-cost LUT of
+//                          ComputeObjectLUT (:236-296, 959-978).
+//
+// Float prefix sums are order-sensitive; both scan orders of the reference are
+// reproduced exactly (see blelloch_prefix_warp / object_lut_rows below).
+#include "kernels.h"
+
+namespace isx {
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// Static transition record S[vB], vB in [1, H):   (p = vB - 1)
+//  0 pc      = ln(H - vB)                       GetPriorCost            (:40-42)
+//  1 t1_hi   = max(gf[p],0) + eps               ObjectFromGround cases  (:120-144)
+//  2 t1_lo   = max(gf[p],0) - eps
+//  3 tr1_hi  4 tr1_mid  5 tr1_lo                its three finite values
+//  6 sky_fg  = gf[p] < 1 ? pc : inf             SkyFromGround           (:98-106)
+//  7 oo_base = pc + (p < vhor ? -ln .7 : ln 2)  ObjectFromObject prefix (:151-152)
+//  8 tr3     = pc + ln(D - eps)                 ObjectFromSky           (:173-183)
+//  9 g_prev  = -ln .3 + pc                      GetPriorCostGround      (:185-187)
+// 10 sky_fo  = ln 2 + pc                        SkyFromObject           (:88-96)
+// ---------------------------------------------------------------------------
+__global__ void frame_tables_kernel(const float *__restrict__ ground, const int *__restrict__ vhor_arr,
+                                    float *__restrict__ stat, KParams p) {
+  const int f = blockIdx.y;
+  const int vB = blockIdx.x * blockDim.x + threadIdx.x;
+  const int H = p.rows;
+  if (vB >= H) return;
+  float *S = stat + ((size_t)f * H + vB) * kStatWords;
+  if (vB == 0) {
+    for (int i = 0; i < kStatWords; i++) S[i] = 0.0f;
+    return;
+  }
+  const float *gf = ground + (size_t)f * 3 * H;
+  const int vhor = vhor_arr[f];
+  const int pv = vB - 1;
+  const float eps = p.epsilon;
+
+  // FFMA(lg2(H-vB), ln2, -0): the -__logf(1.0f) term folds to -0.
+  const float pc = ffma(lg2_approx((float)(H - vB)), kLn2, -0.0f);
+  const float fnp = clamp_neg(gf[pv]);
+  const float t1_hi = fadd(fnp, eps);
+  const float t1_lo = fsub(fnp, eps);
+  const float og_base = fadd(pc, kNegLog07);
+  const float tr1_hi = fadd(neg_log_div(p.pgrav, fsub(fadd(-fnp, p.max_disf), eps)), og_base);
+  const float tr1_mid = fadd(neg_log_div(fsub(fadd(-p.pgrav, 1.0f), p.pblg), fadd(eps, eps)), og_base);
+  const float tr1_lo = fadd(neg_log_div(p.pblg, t1_lo), og_base);
+  const float sky_fg = (gf[pv] < 1.0f) ? pc : inf_f();
+  const float oo_base = fadd(pc, (pv < vhor) ? kNegLog07 : kLn2);
+  const float tr3 = fadd(pc, ffma(lg2_approx(fsub(p.max_disf, eps)), kLn2, -0.0f));
+  const float g_prev = ffma(-kLn2, kLg2_03, pc);
+  const float sky_fo = ffma(kLn2, 1.0f, pc);
+  S[0] = pc;  S[1] = t1_hi;  S[2] = t1_lo;  S[3] = tr1_hi;  S[4] = tr1_mid;  S[5] = tr1_lo;
+  S[6] = sky_fg;  S[7] = oo_base;  S[8] = tr3;  S[9] = g_prev;  S[10] = sky_fo;  S[11] = 0.0f;
+}
+
+// ---------------------------------------------------------------------------
+// Blelloch-order exclusive prefix sum of e[0..H) (H <= 1024), one warp.
+//
+// The reference scans in place with the classic work-efficient tree
+// (StixelsKernels.h:73-103): block sums are pairwise trees U(.), and ps[i]
+// folds, from the most to the least significant set bit of i,
+//      prefix = prefix + U(aligned block that bit selects).
+// A butterfly (shfl_xor) reproduces U(.) of every aligned block; the value a
+// lane receives at level b while its bit b is set is exactly the U(left
+// sibling) the down-sweep adds.  Levels 0-4 live inside a 32-row chunk,
+// levels 5-9 across the (<= 32) chunk totals.
+// ---------------------------------------------------------------------------
+__device__ void blelloch_prefix_warp(const float *e, int H, float *ps) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int nchunks = (H + 31) >> 5;
+  float total_k = 0.0f;  // lane k: U(chunk k)
+  for (int k = 0; k < nchunks; k++) {
+    const int v = (k << 5) + lane;
+    float x = v < H ? e[v] : 0.0f;
+#pragma unroll
+    for (int b = 0; b < 5; b++) x = fadd(x, __shfl_xor_sync(full, x, 1 << b));
+    if (lane == k) total_k = x;
+  }
+  float y = total_k, left[5];
+#pragma unroll
+  for (int b = 0; b < 5; b++) {
+    const float o = __shfl_xor_sync(full, y, 1 << b);
+    left[b] = o;
+    y = fadd(y, o);
+  }
+  float hi = 0.0f;  // lane k: prefix of chunk k's first row
+#pragma unroll
+  for (int b = 4; b >= 0; b--)
+    if ((lane >> b) & 1) hi = fadd(hi, left[b]);
+  const int kmax = H >> 5;  // chunk index of row H itself
+  for (int k = 0; k <= kmax; k++) {
+    const int v = (k << 5) + lane;
+    float x = v < H ? e[v] : 0.0f;
+    float lo[5];
+#pragma unroll
+    for (int b = 0; b < 5; b++) {
+      const float o = __shfl_xor_sync(full, x, 1 << b);
+      lo[b] = o;
+      x = fadd(x, o);
+    }
+    // k == 32 only for H == 1024, lane 0: the root total.
+    float pre = (k < 32) ? __shfl_sync(full, hi, k & 31) : y;
+#pragma unroll
+    for (int b = 4; b >= 0; b--)
+      if ((lane >> b) & 1) pre = fadd(pre, lo[b]);
+    if (v <= H) ps[v] = pre;
+  }
+}
+
+// Exact integer exclusive prefix sums (any order is bit-identical).
+template <typename T>
+__device__ void exact_prefix_warp(const T *e, int n, T *ps) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  T carry = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    T x = i < n ? e[i] : (T)0;
+    T incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const T o = __shfl_up_sync(full, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (i < n) ps[i] = carry + incl - x;
+    carry += __shfl_sync(full, incl, 31);
+  }
+  if (lane == 0) ps[n] = carry;
+}
+
+// One fn row of the object LUT in the reference's summation order
+// (warp_prefix_sum / ComputePrefixSumWarp2, StixelsKernels.cu:236-296):
+// 32-row chunks, the running total joins lane 0 BEFORE the Kogge-Stone scan.
+// out[v] = LUT[fn][v+1]; LUT[fn][0] = 0 is implicit.
+__device__ __forceinline__ void object_lut_row(const float *__restrict__ cost_row, const uint8_t *dis, int H,
+                                               float *__restrict__ out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  float add = 0.0f;
+  for (int i = 0; i < H; i += 32) {
+    const int v = i + lane;
+    float c = __ldg(cost_row + (v < H ? dis[v] : 0));
+    if (lane == 0) c = fadd(c, add);
+#pragma unroll
+    for (int j = 1; j < 32; j <<= 1) {
+      const float n = __shfl_up_sync(full, c, j);
+      if (lane >= j) c = fadd(c, n);
+    }
+    if (v < H) out[v] = c;
+    add = __shfl_sync(full, c, 31);
+  }
+}
+
+constexpr int kTabThreads = 256;
+
+// Dynamic shared memory carve-up (bytes), Hp = H + 1 rounded up to 4.
+struct TabSmem {
+  int Hp, nq;
+  size_t off_e[4], off_ps[4], off_segps, off_seg, off_i64e, off_i64ps, off_dis, total;
+  __host__ __device__ TabSmem(int H, int hs2) {
+    Hp = (H + 1 + 3) & ~3;
+    nq = H / 8 + 1;  // prefix entries per 1/8-res channel (index v>>3 for v <= H)
+    size_t o = 0;
+    for (int i = 0; i < 4; i++) { off_e[i] = o; o += (size_t)Hp * 4; }
+    for (int i = 0; i < 4; i++) { off_ps[i] = o; o += (size_t)Hp * 4; }
+    off_i64e = o; o += (size_t)Hp * 8 * 4;
+    off_i64ps = o; o += (size_t)Hp * 8 * 4;
+    off_seg = o; o += (size_t)21 * (nq + 1) * 4;
+    off_segps = o; o += (size_t)21 * (nq + 1) * 4;
+    off_dis = o; o += (size_t)Hp;
+    total = (o + 15) & ~(size_t)15;
+    (void)hs2;
+  }
+};
+
+__global__ void __launch_bounds__(kTabThreads)
+column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict__ segmentation,
+                     const float *__restrict__ ground, const int *__restrict__ vhor_arr,
+                     const float *__restrict__ obj_cost_lut, uint32_t *__restrict__ records,
+                     float *__restrict__ object_lut, KParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int H = p.rows, C = p.realcols, D = p.max_dis;
+  const int col = blockIdx.x, f = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TabSmem L(H, p.hs2);
+  float *e_disp = reinterpret_cast<float *>(smem + L.off_e[0]);
+  float *e_valid = reinterpret_cast<float *>(smem + L.off_e[1]);
+  float *e_ground = reinterpret_cast<float *>(smem + L.off_e[2]);
+  float *e_sky = reinterpret_cast<float *>(smem + L.off_e[3]);
+  float *ps_f[4];
+  for (int i = 0; i < 4; i++) ps_f[i] = reinterpret_cast<float *>(smem + L.off_ps[i]);
+  long long *e_i64 = reinterpret_cast<long long *>(smem + L.off_i64e);    // [4][Hp]
+  long long *ps_i64 = reinterpret_cast<long long *>(smem + L.off_i64ps);  // [4][Hp]
+  int *seg_s = reinterpret_cast<int *>(smem + L.off_seg);                 // [21][nq+1]
+  int *seg_ps = reinterpret_cast<int *>(smem + L.off_segps);              // [21][nq+1]
+  uint8_t *dis_s = smem + L.off_dis;
+  const int nq = L.nq, segld = nq + 1;
+
+  const float *d_col = joined + ((size_t)f * C + col) * H;
+  const int32_t *seg_col = segmentation + ((size_t)f * C + col) * p.n_channels * p.hs2;
+  const float *gf = ground + (size_t)f * 3 * H;
+  const float *norm_g = gf + H, *inv_g = gf + 2 * H;
+  const int vhor = vhor_arr[f];
+  const float invalid = p.invalid_disparity;
+  const int K = p.n_classes;  // 19; channel K = y offsets, K+1 = x offsets
+
+  // ---- 1/8-resolution channels (squared offsets like :411-416) ----
+  for (int i = tid; i < 21 * nq; i += kTabThreads) {
+    const int c = i / nq, q = i - c * nq;
+    int v = 0;
+    if (c < p.n_channels && q < p.hs2) v = seg_col[(size_t)c * p.hs2 + q];
+    if (c >= K) v = v * v;
+    seg_s[c * segld + q] = v;
+  }
+  // ---- per-row terms (:371-446) ----
+  for (int v = tid; v < H; v += kTabThreads) {
+    const float d = d_col[v];
+    if (invalid >= 0.0f) {
+      const int va = d != invalid;
+      e_valid[v] = (float)va;
+      e_disp[v] = fmul((float)va, d);
+    } else {
+      e_valid[v] = 1.0f;  // unused by the reference in this mode (ComputeMean divides by the height)
+      e_disp[v] = d;
+    }
+    // sky_lut: GetDataCostSky (:201-215), zero below the horizon (:424-433)
+    float sky = 0.0f;
+    if (v >= vhor) {
+      sky = p.pnexists_given_sky_log;
+      if (d != invalid) {
+        const float g = ffma(fmul(d, d), p.inv_sigma2_sky, p.normalization_sky);
+        sky = fadd(fmin_(g, p.puniform_sky), p.nopnexists_given_sky_log);
+      }
+    }
+    e_sky[v] = sky;
+    // ground_lut: GetDataCostGround (:217-234), +inf at/above the horizon (:437-446)
+    float grd = inf_f();
+    if (v < vhor) {
+      grd = p.pnexists_given_ground_log;
+      if (d != invalid) {
+        const float diff = fsub(d, gf[v]);
+        const float g = ffma(fmul(diff, diff), inv_g[v], norm_g[v]);
+        grd = fadd(fmin_(g, p.puniform), p.nopnexists_given_ground_log);
+      }
+    }
+    e_ground[v] = grd;
+    // instance means (:400-409): C++ double arithmetic truncated toward zero
+    const int q = v / kDownsample;
+    const int off_y = (q < p.hs2 && K < p.n_channels) ? seg_col[(size_t)K * p.hs2 + q] : 0;
+    const int off_x = (q < p.hs2 && K + 1 < p.n_channels) ? seg_col[(size_t)(K + 1) * p.hs2 + q] : 0;
+    const long long mx = (long long)((p.column_step * col + 0.5 * (p.column_step - 1.0)) + off_x + 0.5);
+    const long long my = (long long)(v - off_y + 0.5);
+    e_i64[0 * L.Hp + v] = mx;
+    e_i64[1 * L.Hp + v] = my;
+    e_i64[2 * L.Hp + v] = mx * mx;
+    e_i64[3 * L.Hp + v] = my * my;
+    int di = (int)d;  // (int) d as LUT index (:246-248)
+    di = di < 0 ? 0 : (di >= D ? D - 1 : di);
+    dis_s[v] = (uint8_t)di;
+  }
+  __syncthreads();
+
+  // ---- prefix sums: warps 0-3 float (Blelloch order), 4-7 int64, all: 1/8-res ints ----
+  if (warp < 4) {
+    const float *src = warp == 0 ? e_disp : warp == 1 ? e_valid : warp == 2 ? e_ground : e_sky;
+    blelloch_prefix_warp(src, H, ps_f[warp]);
+  } else {
+    exact_prefix_warp<long long>(e_i64 + (warp - 4) * L.Hp, H, ps_i64 + (warp - 4) * L.Hp);
+  }
+  for (int c = warp; c < 21; c += kTabThreads / 32) exact_prefix_warp<int>(seg_s + c * segld, nq, seg_ps + c * segld);
+  __syncthreads();
+
+  // ---- assemble the 128-byte records R[v], v in [0, H] ----
+  uint32_t *rec_col = records + ((size_t)f * C + col) * (size_t)p.rec_rows * kRecWords;
+  for (int v = tid; v <= H; v += kTabThreads) {
+    uint32_t w[kRecWords];
+    const int q = v >> 3, r = v & 7;
+#pragma unroll
+    for (int c = 0; c < 19; c++)  // P_c(v) = 8*ps[q] + seg[q]*r  (Cityscapes.h:28-42)
+      w[kRecSeg + c] = (uint32_t)(seg_ps[c * segld + q] * kDownsample + seg_s[c * segld + q] * r);
+    w[kRecOff] = (uint32_t)((seg_ps[19 * segld + q] + seg_ps[20 * segld + q]) * kDownsample +
+                            (seg_s[19 * segld + q] + seg_s[20 * segld + q]) * r);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const long long s = ps_i64[k * L.Hp + v];
+      w[kRecMx + 2 * k] = (uint32_t)(unsigned long long)s;
+      w[kRecMx + 2 * k + 1] = (uint32_t)((unsigned long long)s >> 32);
+    }
+    w[kRecDisp] = __float_as_uint(ps_f[0][v]);
+    w[kRecValid] = __float_as_uint(ps_f[1][v]);
+    w[kRecGround] = __float_as_uint(ps_f[2][v]);
+    w[kRecSky] = __float_as_uint(ps_f[3][v]);
+    uint4 *dst = reinterpret_cast<uint4 *>(rec_col + (size_t)v * kRecWords);
+#pragma unroll
+    for (int k = 0; k < kRecWords / 4; k++) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+  }
+
+  // ---- object LUT rows, fn = warp, warp+8, ... ----
+  float *lut_col = object_lut + ((size_t)f * C + col) * (size_t)D * p.lut_stride;
+  for (int fn = warp; fn < D; fn += kTabThreads / 32)
+    object_lut_row(obj_cost_lut + (size_t)fn * D, dis_s, H, lut_col + (size_t)fn * p.lut_stride);
+  (void)lane;
+}
+
+}  // namespace
+
+void launch_frame_tables(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s) {
+  dim3 grid((p.rows + 255) / 256, nframes);
+  frame_tables_kernel<<<grid, 256, 0, s>>>(b.ground, b.vhor, b.stat, p);
+  g_launch_count++;
+}
+
+static size_t tab_smem_bytes(const KParams &p) { return TabSmem(p.rows, p.hs2).total; }
+
+void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s) {
+  dim3 grid(p.realcols, nframes);
+  const size_t smem = tab_smem_bytes(p);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(column_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.obj_cost_lut,
+                                                        b.records, b.object_lut, p);
+  g_launch_count++;
+}
+
+}  // namespace isx
