@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the stixel hot path (BASELINE.json metric: stixel frames/sec @1024x2048).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload unary_b64|pairwise_b64|pairwise_w4_b64]
+  python bench.py --impl reference ...      # the reference's own implementation, same workload
+
+A "step" is one pass of the whole path (column join -> tables -> DP -> backtracking -> instance
+grouping) over one batch of 64 synthetic Cityscapes-shaped frames per GPU.  Frames are independent,
+so N GPUs run N shards with no collective in the data path (weak scaling).
+
+  value : frames/s with inputs already resident in HBM (isx_compute_batch_device), timed with CUDA
+          events on the stream the kernels are launched on, max over ranks.
+  e2e   : the same batch through the host-buffer entry point (isx_compute_batch_host): pinned host
+          inputs -> H2D -> kernels -> D2H of all Sections + instance records, every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: unary model, batch of 64 frames on 1 B200
+    "unary_b64": dict(mode="unary", step=8, batch=64),
+    # configs[2]: pairwise model + instance grouping, batch 64
+    "pairwise_b64": dict(mode="pairwise", step=8, batch=64),
+    # configs[3]: pairwise at stixel width 4
+    "pairwise_w4_b64": dict(mode="pairwise", step=4, batch=64),
+}
+ROWS, COLS = 1024, 2048
+OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), sm_max_mhz=d.get("sm_max_mhz", 1965.0), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=float(self.rows[0][1]),
+                    reasons=reasons, samples=len(self.rows))
+
+
+def cpu_baseline(wl, nframes=1):
+    """The oracle port on the host cores, bounded sample of the same workload."""
+    from instance_stixels_b200 import synth
+    from oracle import cpubind
+    pre = synth.preset(wl["mode"], ROWS, COLS, wl["step"])
+    cfg = cpubind.default_config(**pre)
+    lib = cpubind.load()
+    cores = lib.orc_max_threads()
+    frames = [synth.make_frame(i, rows=ROWS, cols=COLS, column_step=wl["step"]) for i in range(nframes)]
+    t0 = time.perf_counter()
+    for fr in frames:
+        cpubind.compute_frame(cfg, wl["mode"] == "pairwise", fr.disparity, fr.segmentation, fr.road)
+    dt = time.perf_counter() - t0
+    return dict(value=nframes / dt, unit="frames/s", cores=cores, kind="port",
+                sample=f"{nframes} frame(s) of the workload, oracle/stixels_cpu.cpp, OpenMP over columns")
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's own implementation of the path.  The reference has no CPU
+    path (all stages are __global__ kernels): its implementation IS the CUDA build, compiled
+    unmodified for sm_100a into oracle/_ref and driven one frame per Compute() like
+    apps/run_cityscapes.cu:346-431.  Falls back to the CPU port when oracle/_ref cannot be used."""
+    if rank != 0:
+        return
+    from instance_stixels_b200 import api, synth
+    from oracle import refbind
+    pairwise = wl["mode"] == "pairwise"
+    sample = min(wl["batch"], 16)
+    line = dict(impl="reference", metric="stixel frames/sec @1024x2048", unit="frames/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=args.workload, rows=ROWS, cols=COLS, column_step=wl["step"],
+                            mode=wl["mode"], frames_per_step=sample))
+    try:
+        import torch
+        if not (refbind.available() and torch.cuda.is_available()):
+            raise RuntimeError("oracle/_ref or CUDA device not available")
+        disp, seg, roads = synth.make_batch(sample, rows=ROWS, cols=COLS, column_step=wl["step"])
+        ref = refbind.RefStixels(api.StixelConfig(**synth.preset(wl["mode"], ROWS, COLS, wl["step"])))
+        for _ in range(max(args.warmup, 1)):
+            ref.time_frames(pairwise, disp[:2], seg[:2], roads[0])
+        t = 0.0
+        for _ in range(args.steps):
+            t += ref.time_frames(pairwise, disp, seg, roads[0])
+        ref.close()
+        fps = sample * args.steps / t
+        line.update(value=fps, ms_per_step=1e3 * t / args.steps,
+                    cpu_baseline=dict(value=fps, unit="frames/s", cores=0, kind="reference",
+                                      sample=f"{sample} frames/step through the reference CUDA build "
+                                             "(oracle/_ref, sm_100a) on GPU 0, one frame per Compute()"))
+    except Exception as e:  # no GPU / no _ref: time the CPU port instead
+        cb = cpu_baseline(wl, 1)
+        line.update(value=cb["value"], ms_per_step=1e3 / cb["value"], cpu_baseline=cb, note=f"reference CUDA build unusable: {e!r}")
+    line["e2e"] = dict(value=line["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="unary_b64", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the latency / other-workload extras")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from instance_stixels_b200 import api, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the stixel path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B = wl["batch"]
+    pairwise = wl["mode"] == "pairwise"
+    pre = synth.preset(wl["mode"], ROWS, COLS, wl["step"])
+    st = api.make_stixels(pre, max_batch=B, device=local)
+    C_ = st.GetRealCols()
+
+    # synthetic frames: every rank gets its own shard of the stream (frame ids rank*B ...)
+    disp, seg, roads = synth.make_batch(B, start=rank * B, rows=ROWS, cols=COLS, column_step=wl["step"])
+    h_disp = torch.from_numpy(disp).pin_memory()
+    h_seg = torch.from_numpy(seg).pin_memory()
+    d_disp = h_disp.cuda(non_blocking=True)
+    d_seg = h_seg.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(st.stream(), device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        st.ComputeBatchDevice(pairwise, B, d_disp.data_ptr(), d_seg.data_ptr(), roads)
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    st.Synchronize()
+    st.set_profiling(True)
+    st.stage_times(reset=True)
+    launches0 = st._lib.isx_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            device_step()
+        e1.record(stream)
+        st.Synchronize()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = st._lib.isx_kernel_launch_count() - launches0
+    stages = st.stage_times(reset=True)
+    st.set_profiling(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- e2e: host buffers through the public batch API, copies inside the timed region ----
+    sections_host = torch.empty((B, C_, 200, 32), dtype=torch.uint8).pin_memory()
+    sec_np = sections_host.numpy().view(api.L.SECTION_DTYPE).reshape(B, C_, 200)
+
+    def host_step():
+        return st.ComputeBatch(pairwise, h_disp.numpy(), h_seg.numpy(), roads, sections_out=sec_np)
+
+    for _ in range(2):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_inst = 0
+    for _ in range(args.steps):
+        _, inst, _ = host_step()
+        n_inst = len(inst)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_s = float(t2.item())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        H = ROWS
+        cells_per_frame = C_ * H * (H + 1) // 2
+        dp_ms, dp_launches = stages["dp"]
+        chunk = st.chunk_frames()
+        ops_per_launch = cells_per_frame * chunk * OPS_PER_CELL[wl["mode"]]
+        dp_avg_s = dp_ms * 1e-3 / max(dp_launches, 1)
+        achieved = ops_per_launch / dp_avg_s / 1e12
+        peak = 148 * 128 * peaks["sm_max_mhz"] * 1e6 / 1e12
+        # table build (join + column tables): algorithmic HBM bytes per frame
+        seg_bytes = C_ * 21 * (H // 8) * 4
+        tab_bytes = (H * COLS * 4 + seg_bytes) * chunk
+        tab_ms = stages["join"][0] + stages["column_tables"][0]
+        tab_launches = max(stages["join"][1], 1)
+        line = dict(
+            metric="stixel frames/sec @1024x2048", value=world * B * args.steps / (ms_max * 1e-3), unit="frames/s",
+            n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_max / args.steps,
+            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+            config=dict(workload=args.workload, rows=ROWS, cols=COLS, column_step=wl["step"], mode=wl["mode"],
+                        frames_per_step_per_gpu=B, chunk_frames=chunk,
+                        l2="inputs (890 MB/step) and tables (>2 GB/chunk) exceed the 126 MB L2"),
+            e2e=dict(value=world * B * args.steps / e2e_s, unit="frames/s",
+                     h2d_bytes_per_step=int(h_disp.numel() * 4 + h_seg.numel() * 4),
+                     d2h_bytes_per_step=int(sections_host.numel() + n_inst * 16 + B * 4)),
+            gpu_launches=int(launches),
+            clocks=clk.summary(),
+            roofline=dict(bound="alu", kernel="dp_kernel", achieved=achieved, peak=peak, unit="Tlane-op/s",
+                          frac=achieved / peak, traffic=None,
+                          note=f"{OPS_PER_CELL[wl['mode']]} lane-ops per DP cell x {cells_per_frame} cells/frame x "
+                               f"{chunk} frames per launch / {dp_avg_s * 1e3:.2f} ms avg launch (CUDA events, "
+                               f"{dp_launches} launches); peak = 148 SM x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz "
+                               f"({peaks['source']})"),
+            roofline_tables=dict(bound="hbm", kernel="join_columns+column_tables",
+                                 achieved=tab_bytes / (tab_ms * 1e-3 / tab_launches) / 1e9,
+                                 peak=peaks["hbm_gbs"], unit="GB/s",
+                                 frac=tab_bytes / (tab_ms * 1e-3 / tab_launches) / 1e9 / peaks["hbm_gbs"],
+                                 traffic=None),
+            stage_ms_per_step={k: v[0] / args.steps for k, v in stages.items()},
+        )
+        if not args.no_extra and world == 1:
+            # p50 latency of one frame through the reference call sequence (host in -> host out)
+            lat = []
+            fr = synth.make_frame(0, rows=ROWS, cols=COLS, column_step=wl["step"])
+            for i in range(25):
+                t0 = time.perf_counter()
+                st.SetDisparityImage(fr.disparity)
+                st.SetSegmentation(fr.segmentation)
+                st.SetRoadParameters(**fr.road)
+                st.Compute(pairwise)
+                st.GetInstanceStixels()
+                lat.append(1e3 * (time.perf_counter() - t0))
+            lat = sorted(lat[3:])
+            line["latency_ms_batch1"] = dict(p50=lat[len(lat) // 2], p99=lat[-1])
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(wl, 1)
+        print(json.dumps(line), flush=True)
+    st.Finish()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

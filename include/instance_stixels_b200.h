@@ -238,6 +238,16 @@ typedef enum isx_tensor {
   ISX_T_OBJ_COST_LUT = 9,     /* float [max_dis][max_dis] (Stixels.cu:122-129) */
   ISX_T_OBJECT_DISPARITY_RANGE = 10 /* float [max_dis] (Stixels.cu:111-115) */
 } isx_tensor;
+/* Per-stage device time, measured with CUDA events on the handle's stream
+ * around the launches of every enqueued chunk while profiling is enabled.
+ * Stages: 0 column join | 1 frame tables (pairwise) | 2 column tables + object
+ * LUT | 3 DP | 4 backtracking + candidate collection | 5 grouping + packing.
+ * isx_get_stage_times synchronises, accumulates into ms[0..n_stages) /
+ * chunks[] (number of timed launches per stage) and optionally resets. */
+int isx_set_profiling(isx_handle h, int enable);
+int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, int reset);
+/* Frames per kernel launch (batches are cut into chunks of this many frames). */
+int isx_chunk_frames(isx_handle h);
 size_t isx_tensor_elems(isx_handle h, int tensor);
 int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t bytes);
 

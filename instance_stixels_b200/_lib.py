@@ -24,7 +24,8 @@ EXPORTS = [
     "isx_set_disparity_image", "isx_input_disparity_device", "isx_set_segmentation",
     "isx_set_road_parameters", "isx_compute", "isx_cluster_instances", "isx_get_instance_stixels",
     "isx_compute_batch_host", "isx_compute_batch_device", "isx_synchronize", "isx_fetch_batch_results",
-    "isx_stream", "isx_tensor_elems", "isx_read_tensor",
+    "isx_stream", "isx_tensor_elems", "isx_read_tensor", "isx_set_profiling", "isx_get_stage_times",
+    "isx_chunk_frames",
 ]
 
 
@@ -118,6 +119,9 @@ def _declare(lib):
     lib.isx_tensor_elems.argtypes = [H, i]
     lib.isx_tensor_elems.restype = C.c_size_t
     lib.isx_read_tensor.argtypes = [H, i, i, C.c_void_p, C.c_size_t]
+    lib.isx_set_profiling.argtypes = [H, i]
+    lib.isx_get_stage_times.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_long), i, i]
+    lib.isx_chunk_frames.argtypes = [H]
 
 
 def load():

@@ -209,6 +209,21 @@ class Stixels:
             cap if want_instances else 0, offs.ctypes.data if want_instances else None))
         return sections, inst[:offs[n]], offs
 
+    STAGES = ("join", "frame_tables", "column_tables", "dp", "backtrack", "grouping")
+
+    def set_profiling(self, enable: bool):
+        self._check(self._lib.isx_set_profiling(self._h, int(enable)))
+
+    def stage_times(self, reset: bool = True) -> dict:
+        """{stage: (total_ms, launches)} measured with CUDA events on the library's stream."""
+        ms = (C.c_double * 6)()
+        ch = (C.c_long * 6)()
+        self._check(self._lib.isx_get_stage_times(self._h, ms, ch, 6, int(reset)))
+        return {n: (ms[i], ch[i]) for i, n in enumerate(self.STAGES)}
+
+    def chunk_frames(self) -> int:
+        return self._lib.isx_chunk_frames(self._h)
+
     def stream(self) -> int:
         return self._lib.isx_stream(self._h)
 

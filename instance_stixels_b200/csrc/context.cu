@@ -82,6 +82,13 @@ struct isx_context {
   int last_chunk_n = 0;
   bool last_pairwise = false;
   std::vector<isx_road> last_roads;
+
+  // optional per-stage CUDA-event timing (isx_set_profiling)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;   // kStages+1 events per enqueued chunk
+  size_t prof_used = 0;
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long stage_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace isx {
@@ -225,16 +232,34 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
   b.segmentation = d_seg;
   b.sections = c->d_sections_all + (size_t)first * C * kMaxSections;
   b.n_sections = c->d_nsections_all + (size_t)first * C;
+  // stage boundaries: 0 join | 1 frame tables | 2 column tables | 3 dp | 4 backtrack+collect | 5 grouping+pack
+  auto mark = [&](int i) {
+    if (!c->profiling) return;
+    if (c->prof_used >= c->prof_events.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      c->prof_events.push_back(e);
+    }
+    cudaEventRecord(c->prof_events[c->prof_used++], s);
+    (void)i;
+  };
+  mark(0);
   launch_join_columns(kp, b, n, s);
+  mark(1);
   if (pairwise) launch_frame_tables(kp, b, n, s);
+  mark(2);
   launch_column_tables(kp, b, n, s);
+  mark(3);
   launch_dp(kp, b, n, pairwise, s);
+  mark(4);
   launch_emit(kp, b, n, pairwise, s);
+  mark(5);
   launch_grouping(kp, b, n, s);
   pack_instances_kernel<<<n, 256, 0, s>>>(b.cand_count, b.cand_idx, b.cand_label,
                                           c->d_inst_all + (size_t)first * c->inst_cap,
                                           c->d_inst_count_all + first, c->inst_cap, kp);
   g_launch_count++;
+  mark(6);
   ISX_TRY(c, cudaGetLastError());
   c->last_chunk_first = first;
   c->last_chunk_n = n;
@@ -716,5 +741,36 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
   }
   return ISX_OK;
 }
+
+int isx_set_profiling(isx_handle h, int enable) {
+  if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
+  h->profiling = enable != 0;
+  return ISX_OK;
+}
+
+int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, int reset) {
+  if (int rc = check_ready(h)) return rc;
+  ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
+  const int per = 7;
+  for (size_t base = 0; base + per <= h->prof_used; base += per) {
+    for (int i = 0; i < 6; i++) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, h->prof_events[base + i], h->prof_events[base + i + 1]) == cudaSuccess) {
+        h->stage_ms[i] += t;
+        h->stage_launches[i]++;
+      }
+    }
+  }
+  h->prof_used = 0;
+  for (int i = 0; i < n_stages && i < 6; i++) {
+    if (ms) ms[i] = h->stage_ms[i];
+    if (chunks) chunks[i] = h->stage_launches[i];
+  }
+  if (reset)
+    for (int i = 0; i < 8; i++) { h->stage_ms[i] = 0; h->stage_launches[i] = 0; }
+  return ISX_OK;
+}
+
+int isx_chunk_frames(isx_handle h) { return (h && h->initialized) ? h->chunk : 0; }
 
 }  // extern "C"

@@ -1,0 +1,225 @@
+"""Parity of the CUDA product (through the C ABI) on a B200:
+  * bit-for-bit against the reference CUDA build oracle/_ref on identical seeded inputs,
+  * against the committed golden vectors (outputs of the reference itself),
+  * against the CPU oracle (column-exact, floats within 1e-4 relative),
+  * at BASELINE.json's full size through size-independent properties.
+Bar: stixel boundaries / types / classes / instance partitions identical; DP costs and stixel
+disparities bit-identical to the reference build (tolerance stated where the CPU oracle is the
+checker: 1e-4 relative, the north-star tolerance)."""
+import numpy as np
+import pytest
+
+import parity
+from instance_stixels_b200 import _lib as L, api, synth
+from oracle import cpubind, refbind
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # name, mode, rows, cols, step, frame, invalid_disparity, median
+    ("small_unary", "unary", 256, 512, 8, 0, 0.0, False),
+    ("small_pairwise", "pairwise", 256, 512, 8, 1, 0.0, False),
+    ("small_pairwise_w4", "pairwise", 256, 512, 4, 2, 0.0, False),
+    ("ragged_pairwise", "pairwise", 200, 328, 8, 3, 0.0, False),   # rows % 32 != 0, 41 columns
+    ("ragged_unary_noinvalid", "unary", 200, 328, 8, 4, -1.0, False),
+    ("median_pairwise", "pairwise", 128, 256, 8, 5, 0.0, True),
+    ("tiny_rows", "pairwise", 40, 64, 8, 6, 0.0, False),           # a single partial tile + one full
+    ("crop_reference_size", "pairwise", 784, 1792, 8, 0, 0.0, False),  # the reference's own test size
+]
+
+
+def _preset(mode, rows, cols, step, invalid, median):
+    pre = synth.preset(mode, rows, cols, step)
+    pre["invalid_disparity"] = invalid
+    pre["median_join"] = median
+    return pre
+
+
+def _run_ours(pre, pairwise, fr, max_batch=1):
+    st = api.make_stixels(pre, max_batch=max_batch)
+    st.SetDisparityImage(fr.disparity)
+    st.SetSegmentation(fr.segmentation)
+    st.SetRoadParameters(**fr.road)
+    data = st.Compute(pairwise)
+    inst = st.instance_records()
+    return st, data, inst
+
+
+@pytest.mark.skipif(not refbind.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_bit_exact_against_reference_cuda_build(case):
+    name, mode, rows, cols, step, frame, invalid, median = case
+    pairwise = mode == "pairwise"
+    pre = _preset(mode, rows, cols, step, invalid, median)
+    fr = synth.make_frame(frame, rows=rows, cols=cols, column_step=step)
+    ref = refbind.RefStixels(api.StixelConfig(**pre))
+    rsec, rinst, rmeta = ref.compute(pairwise, fr.disparity, fr.segmentation, fr.road)
+    st, data, inst = _run_ours(pre, pairwise, fr)
+    # host tables and stage tensors (integer/byte/index work and these float tables: bit-exact)
+    lut, odr, _ = ref.init_tables()
+    assert np.array_equal(st.read_tensor(L.T_OBJ_COST_LUT).view(np.int32), lut.ravel().view(np.int32))
+    assert np.array_equal(st.read_tensor(L.T_OBJECT_DISPARITY_RANGE).view(np.int32), odr.view(np.int32))
+    assert np.array_equal(st.read_tensor(L.T_GROUND_TABLES).view(np.int32),
+                          np.concatenate(ref.ground_tables()).view(np.int32))
+    assert np.array_equal(st.read_tensor(L.T_JOINED_DISPARITY).view(np.int32),
+                          ref.read_tensor(L.T_JOINED_DISPARITY).view(np.int32))
+    assert np.array_equal(st.read_tensor(L.T_OBJECT_LUT).view(np.int32),
+                          ref.read_tensor(L.T_OBJECT_LUT).view(np.int32))
+    ref.close()
+    r = parity.compare_sections(data.sections, rsec)
+    assert r["exact"] == 1.0, r          # boundaries, types, classes on every column
+    assert r["close"] == 1.0 and r["bitwise"] >= 0.995, r   # costs / disparities / instance means
+    ri = parity.compare_instances(inst, rinst)
+    assert ri["same_keys"] and ri["same_partition"], ri   # instance ids up to label permutation
+    for n, _ in L.FrameMeta._fields_:
+        assert getattr(rmeta, n) == getattr(data, n), n
+    st.Finish()
+
+
+def test_against_golden_vectors(golden_files):
+    for path in golden_files:
+        z = np.load(path)
+        mode = str(z["mode"])
+        rows, cols, step, frame = int(z["rows"]), int(z["cols"]), int(z["step"]), int(z["frame"])
+        pre = _preset(mode, rows, cols, step, float(z["invalid"]), False)
+        fr = synth.make_frame(frame, rows=rows, cols=cols, column_step=step)
+        st, data, inst = _run_ours(pre, mode == "pairwise", fr)
+        ref = np.zeros((cols // step, 200), dtype=L.SECTION_DTYPE)
+        ref["type"] = -1
+        ref[:, :z["sections"].shape[1]] = z["sections"]
+        r = parity.compare_sections(data.sections, ref)
+        assert r["exact"] == 1.0 and r["bitwise"] == 1.0, (path, r)
+        assert parity.compare_instances(inst, z["instances"])["same_partition"], path
+        st.Finish()
+
+
+@pytest.mark.parametrize("mode", ["unary", "pairwise"])
+def test_against_cpu_oracle_with_tables(mode):
+    rows, cols = 160, 256
+    pairwise = mode == "pairwise"
+    pre = _preset(mode, rows, cols, 8, 0.0, False)
+    fr = synth.make_frame(11, rows=rows, cols=cols)
+    st, data, inst = _run_ours(pre, pairwise, fr)
+    osec, oinst, ex = cpubind.compute_frame(cpubind.default_config(**pre), pairwise, fr.disparity,
+                                            fr.segmentation, fr.road, tables=True)
+    r = parity.compare_sections(data.sections, osec, rtol=1e-4)
+    assert r["exact"] >= 0.99 and r["close"] >= 0.99, r
+    C_ = cols // 8
+    cost = st.read_tensor(L.T_COST_TABLE).reshape(C_, rows, 3)
+    index = st.read_tensor(L.T_INDEX_TABLE).reshape(C_, rows, 3)
+    fin = np.isfinite(ex["cost_table"])
+    assert np.array_equal(fin, np.isfinite(cost))
+    rel = np.abs(cost[fin] - ex["cost_table"][fin]) / np.maximum(np.abs(ex["cost_table"][fin]), 1e-6)
+    assert np.quantile(rel, 0.999) <= 1e-4    # DP costs: 1e-4 relative (north star)
+    same = (index == ex["index_table"])[fin]
+    assert same.mean() >= 0.99                # back-pointers (argmin vB and predecessor type)
+    j = st.read_tensor(L.T_JOINED_DISPARITY).reshape(C_, rows)
+    assert np.allclose(j, ex["joined"], rtol=1e-6, atol=0)
+    lut = st.read_tensor(L.T_OBJECT_LUT).reshape(C_, -1, rows + 1)
+    assert np.array_equal(lut.view(np.int32), ex["object_lut"].view(np.int32))  # pure fp32 adds: bit-exact
+    st.Finish()
+
+
+def test_batch_equals_single_frame_and_is_deterministic():
+    rows, cols, n = 256, 512, 5
+    pre = _preset("pairwise", rows, cols, 8, 0.0, False)
+    disp, seg, roads = synth.make_batch(n, start=20, rows=rows, cols=cols)
+    roads[2] = dict(roads[2], vhor=roads[2]["vhor"] + 9, camera_tilt=0.01)   # per-frame road parameters
+    st = api.make_stixels(pre, max_batch=8)
+    sec1, inst1, offs1 = st.ComputeBatch(True, disp, seg, roads)
+    sec2, inst2, offs2 = st.ComputeBatch(True, disp, seg, roads)
+    assert np.array_equal(sec1.view(np.uint8), sec2.view(np.uint8))
+    assert np.array_equal(inst1.view(np.uint8), inst2.view(np.uint8)) and np.array_equal(offs1, offs2)
+    for f in range(n):
+        st.SetDisparityImage(disp[f])
+        st.SetSegmentation(seg[f])
+        st.SetRoadParameters(**roads[f])
+        data = st.Compute(True)
+        assert np.array_equal(data.sections.view(np.uint8), sec1[f].view(np.uint8)), f
+        assert np.array_equal(st.instance_records().view(np.uint8), inst1[offs1[f]:offs1[f + 1]].view(np.uint8))
+    st.Finish()
+    # chunked execution (ISX_CHUNK) does not change results
+    import os
+    os.environ["ISX_CHUNK"] = "2"
+    try:
+        st2 = api.make_stixels(pre, max_batch=8)
+        sec3, inst3, offs3 = st2.ComputeBatch(True, disp, seg, roads)
+        st2.Finish()
+    finally:
+        del os.environ["ISX_CHUNK"]
+    assert np.array_equal(sec1.view(np.uint8), sec3.view(np.uint8)) and np.array_equal(offs1, offs3)
+
+
+def test_device_resident_entry_point_matches_host_entry_point():
+    import torch
+    rows, cols, n = 128, 256, 3
+    pre = _preset("unary", rows, cols, 8, 0.0, False)
+    disp, seg, roads = synth.make_batch(n, start=3, rows=rows, cols=cols)
+    st = api.make_stixels(pre, max_batch=4)
+    sec_h, inst_h, offs_h = st.ComputeBatch(False, disp, seg, roads)
+    d_disp, d_seg = torch.from_numpy(disp).cuda(), torch.from_numpy(seg).cuda()
+    before = seg.copy()
+    st.ComputeBatchDevice(False, n, d_disp.data_ptr(), d_seg.data_ptr(), roads)
+    st.Synchronize()
+    sec_d, inst_d, offs_d = st.FetchBatchResults(n)
+    assert np.array_equal(sec_h.view(np.uint8), sec_d.view(np.uint8))
+    assert np.array_equal(inst_h.view(np.uint8), inst_d.view(np.uint8))
+    # unlike the reference (StixelsKernels.cu:411-416, 462-469) the borrowed tensor is not modified
+    assert np.array_equal(d_seg.cpu().numpy(), before)
+    st.Finish()
+
+
+def test_edge_inputs():
+    rows, cols = 64, 64
+    pre = _preset("pairwise", rows, cols, 8, 0.0, False)
+    fr = synth.make_frame(1, rows=rows, cols=cols)
+    cfg = cpubind.default_config(**pre)
+    st = api.make_stixels(pre)
+    for disp, seg in ((np.zeros_like(fr.disparity), fr.segmentation),          # every pixel invalid
+                      (fr.disparity, np.zeros_like(fr.segmentation)),          # empty CNN output
+                      (np.full_like(fr.disparity, 127.5), fr.segmentation)):   # maximum disparity everywhere
+        st.SetDisparityImage(disp)
+        st.SetSegmentation(seg)
+        st.SetRoadParameters(**fr.road)
+        data = st.Compute(True)
+        osec, oinst, _ = cpubind.compute_frame(cfg, True, disp, seg, fr.road)
+        r = parity.compare_sections(data.sections, osec, rtol=1e-4)
+        assert r["exact"] == 1.0 and r["close"] == 1.0, r
+        assert parity.compare_instances(st.instance_records(), oinst)["same_partition"]
+    st.Finish()
+
+
+@pytest.mark.parametrize("mode,step", [("unary", 8), ("pairwise", 8), ("pairwise", 4)])
+def test_full_size_properties(mode, step):
+    """BASELINE.json sizes (1024x2048): every column is tiled bottom to top without gaps or overlaps,
+    stixel costs are the table minima, frames of a batch do not interact, and the result equals the
+    reference CUDA build when it is available."""
+    rows, cols, n = 1024, 2048, 3
+    pairwise = mode == "pairwise"
+    pre = _preset(mode, rows, cols, step, 0.0, False)
+    disp, seg, roads = synth.make_batch(n, start=100, rows=rows, cols=cols, column_step=step)
+    st = api.make_stixels(pre, max_batch=4)
+    sec, inst, offs = st.ComputeBatch(pairwise, disp, seg, roads)
+    for f in range(n):
+        ln = parity.column_lengths(sec[f])
+        assert ln.min() >= 1 and ln.max() < 199
+        idx = np.arange(sec.shape[1])
+        assert np.all(sec[f]["vT"][idx, 0] == rows - 1)
+        assert np.all(sec[f]["vB"][idx, ln - 1] == 0)
+        for c in range(0, sec.shape[1], 7):
+            s = sec[f][c, :ln[c]]
+            assert np.all(s["vB"][:-1] == s["vT"][1:] + 1) and np.all(s["vT"] >= s["vB"])
+            assert np.all((s["type"] >= 0) & (s["type"] <= 2)) and np.all(np.isfinite(s["cost"]))
+            assert np.all((s["semantic_class"] >= 0) & (s["semantic_class"] < 19))
+    # permuting the frames of the batch permutes the results (no cross-frame state)
+    perm = [2, 0, 1]
+    sec_p, inst_p, offs_p = st.ComputeBatch(pairwise, disp[perm], seg[perm], [roads[i] for i in perm])
+    for k, f in enumerate(perm):
+        assert np.array_equal(sec_p[k].view(np.uint8), sec[f].view(np.uint8))
+    if refbind.available():
+        ref = refbind.RefStixels(api.StixelConfig(**pre))
+        rsec, rinst, _ = ref.compute(pairwise, disp[0], seg[0], roads[0])
+        ref.close()
+        r = parity.compare_sections(sec[0], rsec)
+        assert r["exact"] >= 0.999 and r["close"] >= 0.999, r
+        assert parity.compare_instances(inst[offs[0]:offs[1]], rinst)["same_keys"]
+    st.Finish()
