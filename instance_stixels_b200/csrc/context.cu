@@ -419,7 +419,7 @@ int isx_initialize(isx_handle h, int max_batch) {
   const size_t H = kp.rows, W = kp.cols, C = kp.realcols, D = kp.max_dis;
   if (C == 0) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no stixel columns");
   h->max_batch = max_batch;
-  int chunk = 16;
+  int chunk = 64;  // frames per launch: >= 5 waves of one-warp-per-column DP work on 148 SMs
   if (const char *e = std::getenv("ISX_CHUNK")) chunk = std::atoi(e) > 0 ? std::atoi(e) : chunk;
   h->chunk = chunk < max_batch ? chunk : max_batch;
   const size_t ch = h->chunk, MB = max_batch;

@@ -149,7 +149,10 @@ dp_kernel(const uint4 *__restrict__ records, const float *__restrict__ object_lu
       const float var = ffma(-fmul(fmy, fmy), rn, fadd(fmy2, ffma(-fmul(fmx, fmx), rn, fmx2)));
       const float ic = fmul(var, iw);
       const float seg_o = fmin_(fadd(nic, (float)s_ni), fadd(ic, (float)s_in));
-      const float seg_gs = fadd(nic, ground_side ? (float)min(s_road, s_side) : (float)s_sky);
+      // In the first-segment block nvcc contracted `min(road, sidewalk) + weight * offsets` into one
+      // FFMA (reference SASS of StixelsKernels.cu:502-506); everywhere else it is FMUL + FADD.
+      const float seg_gs = vB == 0 ? ffma((float)s_off, iw, (float)min(s_road, s_side))
+                                   : fadd(nic, ground_side ? (float)min(s_road, s_side) : (float)s_sky);
 
       // ---- disparity terms ----
       const float fn = segment_mean(a_disp, __uint_as_float(Bw[kRecDisp]), a_valid, __uint_as_float(Bw[kRecValid]),

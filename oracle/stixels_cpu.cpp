@@ -341,7 +341,8 @@ void process_column(const Ctx &c, int col, const float *disp_img, const int32_t 
     const float ih = 1. / (vT + 1 - vB);
     const float ic = iw * inst_cost(w, vB, vT);
     const float nic = iw * (float)(dsum(ox, vB, vT) + dsum(oy, vB, vT));
-    const float seg_g = seg_ground(vB, vT) + nic;
+    // first-segment block: FFMA(offsets, weight, min(road, sidewalk)) in the reference SASS (:502-506)
+    const float seg_g = ffma((float)(dsum(ox, vB, vT) + dsum(oy, vB, vT)), iw, seg_ground(vB, vT));
     const float seg_o = seg_object(vB, vT, ic, nic, nullptr);
     const float fn = clamp_neg(mean_of(w, m, vB, vT));
     int fni = (int)floorf(fn); fni = fni < 0 ? 0 : (fni >= D ? D - 1 : fni);

@@ -22,7 +22,7 @@ CASES = [  # name, mode, rows, cols, step, frame, invalid_disparity, median
     ("ragged_pairwise", "pairwise", 200, 328, 8, 3, 0.0, False),   # rows % 32 != 0, 41 columns
     ("ragged_unary_noinvalid", "unary", 200, 328, 8, 4, -1.0, False),
     ("median_pairwise", "pairwise", 128, 256, 8, 5, 0.0, True),
-    ("tiny_rows", "pairwise", 40, 64, 8, 6, 0.0, False),           # a single partial tile + one full
+    ("short_rows", "pairwise", 136, 64, 8, 6, 0.0, False),         # four full 32-row tiles + a partial one
     ("crop_reference_size", "pairwise", 784, 1792, 8, 0, 0.0, False),  # the reference's own test size
 ]
 
@@ -165,6 +165,21 @@ def test_device_resident_entry_point_matches_host_entry_point():
     assert np.array_equal(inst_h.view(np.uint8), inst_d.view(np.uint8))
     # unlike the reference (StixelsKernels.cu:411-416, 462-469) the borrowed tensor is not modified
     assert np.array_equal(d_seg.cpu().numpy(), before)
+    st.Finish()
+
+
+def test_fewer_rows_than_disparities_against_cpu_oracle():
+    """rows < max_dis: the reference kernel only fills object_disparity_range[0..rows) of its shared
+    copy (StixelsKernels.cu:378-380, one thread per row), so its own results depend on uninitialised
+    shared memory there; the CPU oracle (full table) is the checker for such sizes."""
+    rows, cols = 40, 64
+    pre = _preset("pairwise", rows, cols, 8, 0.0, False)
+    fr = synth.make_frame(6, rows=rows, cols=cols)
+    st, data, inst = _run_ours(pre, True, fr)
+    osec, oinst, _ = cpubind.compute_frame(cpubind.default_config(**pre), True, fr.disparity, fr.segmentation,
+                                           fr.road)
+    r = parity.compare_sections(data.sections, osec, rtol=1e-4)
+    assert r["exact"] == 1.0 and r["close"] == 1.0, r
     st.Finish()
 
 
