@@ -101,9 +101,11 @@ struct Model {
       const float z = (c.baseline * c.focal / pm) + c.range_objects_z;
       odr[i] = pm - (c.baseline * c.focal / z);
     }
+    // erff: the reference is host code compiled by nvcc, whose headers add a global erf(float)
+    // overload (= erff); plain g++ would pick ::erf(double) here and round differently.
     {  // PrecomputeSky :856-865
       const float s = c.sigma_sky;
-      const float a = 0.5f * (erf(max_disf / (s * sqrtf(2.0f))) - erf(0.0f));
+      const float a = 0.5f * (erff(max_disf / (s * sqrtf(2.0f))) - erff(0.0f));
       norm_sky = fast_log(a) - logf((1.0f - c.pout_sky) / (s * sqrtf(2.0f * kPi)));
       inv_s2_sky = 1.0f / (2.0f * s * s);
     }
@@ -112,7 +114,7 @@ struct Model {
       const float fn = (float)d;
       const float so = fn * fn * c.range_objects_z / (c.focal * c.baseline);
       const float s = sqrtf(c.sigma_disparity_object * c.sigma_disparity_object + so * so);
-      const float a = 0.5f * (erf((max_disf - fn) / (s * sqrtf(2.0f))) - erf((-fn) / (s * sqrtf(2.0f))));
+      const float a = 0.5f * (erff((max_disf - fn) / (s * sqrtf(2.0f))) - erff((-fn) / (s * sqrtf(2.0f))));
       norm_o[d] = fast_log(a) - fast_log((1.0f - c.pout) / (s * sqrtf(2.0f * kPi)));
       inv_o[d] = 1.0f / (2.0f * s * s);
     }
@@ -143,7 +145,7 @@ struct Model {
                              (r.camera_height * r.camera_height) +
                          sigma_tilt * sigma_tilt);
       const float s = sqrtf(cfg.sigma_disparity_ground * cfg.sigma_disparity_ground + s2r);
-      const float a = 0.5f * (erf((max_disf - fn) / (s * sqrtf(2.0f))) - erf((-fn) / (s * sqrtf(2.0f))));
+      const float a = 0.5f * (erff((max_disf - fn) / (s * sqrtf(2.0f))) - erff((-fn) / (s * sqrtf(2.0f))));
       norm[v] = fast_log(a) - fast_log((1.0f - cfg.pout) / (s * sqrtf(2.0f * kPi)));
       inv[v] = 1.0f / (2.0f * s * s);
     }
