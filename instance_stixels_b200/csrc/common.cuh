@@ -26,25 +26,40 @@ constexpr float kLn2 = 0.69314718246459960938f;        // 0x3f317218, fast-math 
 constexpr float kNegLog07 = 0.35667496919631958008f;   // -logf(0.7f) folded by nvcc (StixelsKernels.cu:124,151)
 constexpr float kLg2_03 = -1.7369655370712280273f;     // lg2(0.3f) folded by nvcc (StixelsKernels.cu:186)
 
-// ---- per-row record of the column tables (one 128-byte line per v in [0,H]) ----
-// Prefix sums over rows [0, v) of one stixel column; the DP reads R[vT+1]
-// ("A side", once per 32-row tile) and R[vB] ("B side", warp-uniform).
-constexpr int kRecWords = 32;
-constexpr int kRecSeg = 0;     // 19 words: full-resolution prefix of class c, exact int
+// ---- column tables: prefix sums over rows [0, v) of one stixel column ----
+// Stored word-major ("SoA"): records[column][word][v], v in [0, rec_stride), rec_stride = H + 1
+// rounded up to 32, so that both access patterns of the DP are coalesced 128-byte lines:
+//   * "A side": lane l reads word w of row vT + 1 = a + l + 1  (one line per word),
+//   * "B side": the 32 rows of a vB chunk are staged once per CTA into shared memory.
+constexpr int kRecWords = 30;
+constexpr int kRecSeg = 0;     // 19 words: full-resolution prefix of class c, exact int32
                                //   P_c(v) = 8*ps_c[v/8] + seg_c[v/8]*(v%8)   (Cityscapes.h:28-42)
-constexpr int kRecOff = 19;    // prefix of squared offsets x^2+y^2 (StixelsKernels.cu:62-70, 411-416)
-constexpr int kRecMx = 20;     // int64 prefix of instance_meansx (2 words)   (StixelsKernels.cu:401-403)
-constexpr int kRecMy = 22;     // int64 prefix of instance_meansy             (:404-405)
-constexpr int kRecMx2 = 24;    // int64 prefix of meansx^2                    (:406-407)
-constexpr int kRecMy2 = 26;    // int64 prefix of meansy^2                    (:408-409)
-constexpr int kRecDisp = 28;   // float Blelloch-order prefix of valid*d      (:385,455)
-constexpr int kRecValid = 29;  // float prefix of valid                       (:384,453)
-constexpr int kRecGround = 30; // float Blelloch-order prefix of ground_lut   (:437-446,460)
-constexpr int kRecSky = 31;    // float Blelloch-order prefix of sky_lut      (:424-433,461)
+constexpr int kRecOff = 19;    // int32 prefix of squared offsets x^2+y^2 (StixelsKernels.cu:62-70, 411-416)
+// The reference keeps the four instance-mean sums as int64 and converts the DIFFERENCE of two
+// prefixes to float (I2F.S64, round to nearest; :72-86, 611-616).  Here the prefixes are stored as
+// exactly representable floats so that the same value comes out of plain FADDs:
+//   sum(mx), sum(my): |P| < 2^24, float(P) exact, float(P_a) - float(P_b) exact == float(P_a - P_b);
+//   sum(mx^2), sum(my^2): P = hi * 4096 + lo, both parts exact floats; (hi_a - hi_b) and
+//   (lo_a - lo_b) are exact and their FADD rounds the exact difference once == I2F.S64(P_a - P_b).
+// column_tables_kernel checks the ranges (|P| < 2^24, P2 < 2^36) and raises the error flag otherwise.
+constexpr int kRecMx = 20;     // float(sum instance_meansx)                  (StixelsKernels.cu:401-403)
+constexpr int kRecMy = 21;     // float(sum instance_meansy)                  (:404-405)
+constexpr int kRecMx2Hi = 22;  // float((sum meansx^2 >> 12) << 12)           (:406-407)
+constexpr int kRecMx2Lo = 23;  // float(sum meansx^2 & 4095)
+constexpr int kRecMy2Hi = 24;  // same for meansy^2                           (:408-409)
+constexpr int kRecMy2Lo = 25;
+constexpr int kRecDisp = 26;   // float Blelloch-order prefix of valid*d      (:385,455)
+constexpr int kRecValid = 27;  // float prefix of valid                       (:384,453)
+constexpr int kRecGround = 28; // float Blelloch-order prefix of ground_lut   (:437-446,460)
+constexpr int kRecSky = 29;    // float Blelloch-order prefix of sky_lut      (:424-433,461)
+constexpr int kSqSplitBits = 12;
+// bits of the sticky device error flag
+constexpr int kErrSectionOverflow = 1;  // a column produced >= 200 stixels (StixelsKernels.cu:950 asserts)
+constexpr int kErrOffsetRange = 2;      // instance-offset sums outside the exact-float range above
 
 // ---- per-frame static transition record S[vB] (pairwise only), 12 floats ----
 constexpr int kStatWords = 12;
-// ---- per-column dynamic row info Q[vB] (pairwise only), 12 floats ----
+// ---- per-column dynamic row info Q[vB] (pairwise only), 12 floats, lives in shared memory ----
 constexpr int kDynWords = 12;
 
 // Parameters shared by all kernels (subset of StixelParameters, types.h:145-184).
@@ -70,7 +85,7 @@ struct KParams {
   float pord, epsilon, pgrav, pblg;
   float prior_weight, disparity_weight, segmentation_weight, instance_weight;
   // derived strides
-  int rec_rows;      // H + 1 records per column
+  int rec_stride;    // entries per (column, word) row of the records: H + 1 rounded up to 32
   int lut_stride;    // floats per fn row of the object LUT (>= H, multiple of 32)
 };
 

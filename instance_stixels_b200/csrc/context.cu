@@ -167,7 +167,7 @@ static void fill_kparams(isx_context *c) {
   k.disparity_weight = m.disparity_weight;
   k.segmentation_weight = m.segmentation_weight;
   k.instance_weight = m.instance_weight;
-  k.rec_rows = m.rows + 1;
+  k.rec_stride = (m.rows + 1 + 31) & ~31;
   k.lut_stride = (m.rows + 31) & ~31;
 }
 
@@ -446,9 +446,10 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &b.vhor, ch));
   ISX_TRY(h, dev_alloc(h, &b.stat, ch * H * kStatWords));
   ISX_TRY(h, dev_alloc(h, &b.joined, ch * C * H));
-  ISX_TRY(h, dev_alloc(h, &b.records, ch * C * (H + 1) * kRecWords));
+  ISX_TRY(h, dev_alloc(h, &b.records, ch * C * kRecWords * (size_t)kp.rec_stride));
+  ISX_TRY(h, cudaMemset(b.records, 0, ch * C * kRecWords * (size_t)kp.rec_stride * sizeof(uint32_t)));
   ISX_TRY(h, dev_alloc(h, &b.object_lut, ch * C * D * (size_t)kp.lut_stride));
-  ISX_TRY(h, dev_alloc(h, &b.dyn, ch * C * H * kDynWords));
+  ISX_TRY(h, dev_alloc(h, &b.pm, ch * C * H));
   ISX_TRY(h, dev_alloc(h, &b.dp, ch * C * H));
   ISX_TRY(h, dev_alloc(h, &b.cand_count, ch * kInstanceClasses));
   ISX_TRY(h, dev_alloc(h, &b.cand_offset, ch * (C + 1) * kInstanceClasses));
@@ -459,8 +460,10 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &b.cand_scratch, ch * kInstanceClasses * cap));
   ISX_TRY(h, dev_alloc(h, &b.error_flag, 1));
   ISX_TRY(h, cudaMemset(b.error_flag, 0, sizeof(int)));
-  ISX_TRY(h, cudaMemset(b.dyn, 0, ch * C * H * kDynWords * sizeof(float)));
+  ISX_TRY(h, cudaMemset(b.pm, 0, ch * C * H * sizeof(float)));
   ISX_TRY(h, dev_alloc(h, &h->d_sections_all, MB * C * kMaxSections));
+  // entries after a column's terminator are never written: start them from zero
+  ISX_TRY(h, cudaMemset(h->d_sections_all, 0, MB * C * kMaxSections * sizeof(isx_section)));
   ISX_TRY(h, dev_alloc(h, &h->d_nsections_all, MB * C));
   ISX_TRY(h, dev_alloc(h, &h->d_inst_all, MB * (size_t)h->inst_cap));
   ISX_TRY(h, dev_alloc(h, &h->d_inst_count_all, MB));
@@ -556,6 +559,9 @@ static int fetch_results(isx_handle h, int n, isx_section *sections, isx_instanc
     ISX_TRY(h, cudaMemcpyAsync(h->h_inst, h->d_inst_all, sizeof(isx_instance) * n * (size_t)h->inst_cap,
                                cudaMemcpyDeviceToHost, s));
   ISX_TRY(h, cudaStreamSynchronize(s));
+  if (*h->h_error & kErrOffsetRange)
+    return fail(h, ISX_ERR_UNSUPPORTED,
+                "instance offsets out of range: |sum of instance means| of a column must stay below 2^24");
   if (*h->h_error) return fail(h, ISX_ERR_CAPACITY, "a column produced >= 200 stixels (MAX_STIXELS_PER_COLUMN)");
   if (instances || instance_offsets) {
     int total = 0;
@@ -731,8 +737,10 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
                      : tensor == ISX_T_VALID_PS   ? kRecValid
                      : tensor == ISX_T_GROUND_PS  ? kRecGround
                                                   : kRecSky;
-    ISX_TRY(h, cudaMemcpy2D(host, 4, b.records + (size_t)local * C * (H + 1) * kRecWords + word, kRecWords * 4, 4,
-                            C * (H + 1), cudaMemcpyDeviceToHost));
+    // word-major records: [column][word][rec_stride] -> [column][H+1]
+    ISX_TRY(h, cudaMemcpy2D(host, (H + 1) * 4,
+                            b.records + ((size_t)local * C * kRecWords + word) * kp.rec_stride,
+                            (size_t)kRecWords * kp.rec_stride * 4, (H + 1) * 4, C, cudaMemcpyDeviceToHost));
   } else {
     launch_export_tables(kp, b, local, h->last_pairwise, h->d_export_cost, h->d_export_index, h->s_compute);
     ISX_TRY(h, cudaStreamSynchronize(h->s_compute));

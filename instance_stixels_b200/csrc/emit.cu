@@ -20,19 +20,22 @@ struct Rec {
   uint32_t w[kRecWords];
 };
 
-__device__ __forceinline__ Rec load_rec(const uint4 *rec, int v) {
+// rec = records of this column, word-major with row stride Hp (common.cuh)
+__device__ __forceinline__ Rec load_rec(const uint32_t *rec, int Hp, int v) {
   Rec r;
-  const uint4 *s = rec + (size_t)v * (kRecWords / 4);
 #pragma unroll
-  for (int k = 0; k < kRecWords / 4; k++) {
-    const uint4 t = __ldg(s + k);
-    r.w[4 * k] = t.x; r.w[4 * k + 1] = t.y; r.w[4 * k + 2] = t.z; r.w[4 * k + 3] = t.w;
-  }
+  for (int k = 0; k < kRecWords; k++) r.w[k] = __ldg(rec + (size_t)k * Hp + v);
   return r;
 }
 
-__device__ __forceinline__ long long rec_i64(const Rec &r, int w) {
-  return (long long)(((unsigned long long)r.w[w + 1] << 32) | r.w[w]);
+__device__ __forceinline__ float rec_f(const Rec &r, int w) { return __uint_as_float(r.w[w]); }
+// float(sum over the segment) of the instance means / their squares: the exact-float prefixes
+// reproduce the reference's I2F.S64 of the int64 difference (common.cuh).
+__device__ __forceinline__ float seg_mean_sum(const Rec &hi, const Rec &lo, int w) {
+  return fsub(rec_f(hi, w), rec_f(lo, w));
+}
+__device__ __forceinline__ float seg_sq_sum(const Rec &hi, const Rec &lo, int w_hi) {
+  return fadd(fsub(rec_f(hi, w_hi), rec_f(lo, w_hi)), fsub(rec_f(hi, w_hi + 1), rec_f(lo, w_hi + 1)));
 }
 
 __device__ __forceinline__ int seg_sum(const Rec &hi, const Rec &lo, int c) { return (int)(hi.w[c] - lo.w[c]); }
@@ -56,8 +59,8 @@ __device__ int object_class(const Rec &hi, const Rec &lo, float ic, float nic) {
 
 // Priors that decide the predecessor type of the segment (vB..vT) of `type`.
 template <bool PAIRWISE>
-__device__ int predecessor_type(int type, int vB, float fn_clamped, const float4 *dp_col, const uint4 *rec,
-                                const float *S, const float *Q, int vhor,
+__device__ int predecessor_type(int type, int vB, float fn_clamped, const float4 *dp_col, const float *S,
+                                const float *pm_col, int vhor,
                                 const float *__restrict__ object_disparity_range, const KParams &p) {
   const int pv = vB - 1;
   const float4 prev = dp_col[pv];
@@ -69,7 +72,7 @@ __device__ int predecessor_type(int type, int vB, float fn_clamped, const float4
     if (type != OBJECT) return prev_type_gs(cg, co);
     return prev_type_obj(cg, co, cs);
   } else {
-    const float pm = Q[(size_t)vB * kDynWords + 11];
+    const float pm = pm_col[vB];
     RowPriors rp;
     const RowInfo q = make_row_info(S + (size_t)vB * kStatWords, ground_side, cg, co, cs, pm,
                                     object_disparity_range, p, &rp);
@@ -84,8 +87,8 @@ __device__ int predecessor_type(int type, int vB, float fn_clamped, const float4
 
 template <bool PAIRWISE>
 __global__ void __launch_bounds__(128)
-backtrack_kernel(const uint4 *__restrict__ records, const float4 *__restrict__ dp, const float *__restrict__ stat,
-                 const float *__restrict__ dyn, const int *__restrict__ vhor_arr,
+backtrack_kernel(const uint32_t *__restrict__ records, const float4 *__restrict__ dp, const float *__restrict__ stat,
+                 const float *__restrict__ pm, const int *__restrict__ vhor_arr,
                  const float *__restrict__ object_disparity_range, isx_section *__restrict__ sections,
                  int *__restrict__ n_sections, int *error_flag, int ncolumns, KParams p) {
   const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,10 +97,11 @@ backtrack_kernel(const uint4 *__restrict__ records, const float4 *__restrict__ d
   const int f = gcol / C;
   const int vhor = vhor_arr[f];
   const bool has_invalid = p.invalid_disparity >= 0.0f;
-  const uint4 *rec = records + (size_t)gcol * p.rec_rows * (kRecWords / 4);
+  const int Hp = p.rec_stride;
+  const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
   const float4 *dp_col = dp + (size_t)gcol * H;
   const float *S = stat + (size_t)f * H * kStatWords;
-  const float *Q = dyn + (size_t)gcol * H * kDynWords;
+  const float *pm_col = pm + (size_t)gcol * H;
   isx_section *out = sections + (size_t)gcol * kMaxSections;
   const float inf = inf_f();
 
@@ -115,7 +119,7 @@ backtrack_kernel(const uint4 *__restrict__ records, const float4 *__restrict__ d
     const float4 row = dp_col[vT];
     const int vB = (type == OBJECT) ? __float_as_int(row.w) : __float_as_int(row.z);
     const float cost = (type == OBJECT) ? row.y : row.x;
-    const Rec hi = load_rec(rec, vT + 1), lo = load_rec(rec, vB);
+    const Rec hi = load_rec(rec, Hp, vT + 1), lo = load_rec(rec, Hp, vB);
     const int n = vT + 1 - vB;
 
     isx_section sec;
@@ -136,8 +140,8 @@ backtrack_kernel(const uint4 *__restrict__ records, const float4 *__restrict__ d
     sec.disparity = mean;
     sec.cost = fmin_(cost, 10000.0f);
     const float rn = rcp_approx((float)n);
-    const float fmx = __ll2float_rn(rec_i64(hi, kRecMx) - rec_i64(lo, kRecMx));
-    const float fmy = __ll2float_rn(rec_i64(hi, kRecMy) - rec_i64(lo, kRecMy));
+    const float fmx = seg_mean_sum(hi, lo, kRecMx);
+    const float fmy = seg_mean_sum(hi, lo, kRecMy);
     sec.instance_meanx = fmul(fmx, rn);
     sec.instance_meany = fmul(fmy, rn);
 
@@ -148,8 +152,8 @@ backtrack_kernel(const uint4 *__restrict__ records, const float4 *__restrict__ d
       sec.type = SKY;  // far objects become sky (:894-902)
       sec.semantic_class = kSkyClass;
     } else {
-      const float fmx2 = __ll2float_rn(rec_i64(hi, kRecMx2) - rec_i64(lo, kRecMx2));
-      const float fmy2 = __ll2float_rn(rec_i64(hi, kRecMy2) - rec_i64(lo, kRecMy2));
+      const float fmx2 = seg_sq_sum(hi, lo, kRecMx2Hi);
+      const float fmy2 = seg_sq_sum(hi, lo, kRecMy2Hi);
       const float var = ffma(-fmul(fmy, fmy), rn, fadd(fmy2, ffma(-fmul(fmx, fmx), rn, fmx2)));
       const float ic = fmul(var, p.instance_weight);
       const float nic = fmul((float)seg_sum(hi, lo, kRecOff), p.instance_weight);
@@ -159,10 +163,10 @@ backtrack_kernel(const uint4 *__restrict__ records, const float4 *__restrict__ d
     i++;
     if (vB == 0) break;
     if (i >= kMaxSections - 1) {  // reference: assert(i < max_sections) (:950)
-      atomicExch(error_flag, 1);
+      atomicOr(error_flag, kErrSectionOverflow);
       break;
     }
-    type = predecessor_type<PAIRWISE>(type, vB, clamp_neg(mean), dp_col, rec, S, Q, vhor, object_disparity_range, p);
+    type = predecessor_type<PAIRWISE>(type, vB, clamp_neg(mean), dp_col, S, pm_col, vhor, object_disparity_range, p);
     vT = vB - 1;
   }
   isx_section term;
@@ -252,8 +256,8 @@ collect_candidates_kernel(const isx_section *__restrict__ sections, const int *_
 
 // cost_table / index_table in the reference's layout (parity tests only).
 template <bool PAIRWISE>
-__global__ void export_tables_kernel(const uint4 *__restrict__ records, const float4 *__restrict__ dp,
-                                     const float *__restrict__ stat, const float *__restrict__ dyn,
+__global__ void export_tables_kernel(const uint32_t *__restrict__ records, const float4 *__restrict__ dp,
+                                     const float *__restrict__ stat, const float *__restrict__ pm,
                                      const int *__restrict__ vhor_arr,
                                      const float *__restrict__ object_disparity_range, int frame,
                                      float *__restrict__ cost_table, int *__restrict__ index_table, KParams p) {
@@ -264,10 +268,11 @@ __global__ void export_tables_kernel(const uint4 *__restrict__ records, const fl
   const int gcol = frame * C + col;
   const int vhor = vhor_arr[frame];
   const bool has_invalid = p.invalid_disparity >= 0.0f;
-  const uint4 *rec = records + (size_t)gcol * p.rec_rows * (kRecWords / 4);
+  const int Hp = p.rec_stride;
+  const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
   const float4 *dp_col = dp + (size_t)gcol * H;
   const float *S = stat + (size_t)frame * H * kStatWords;
-  const float *Q = dyn + (size_t)gcol * H * kDynWords;
+  const float *pm_col = pm + (size_t)gcol * H;
   const float4 row = dp_col[vT];
   const float inf = inf_f();
   float *ct = cost_table + ((size_t)col * H + vT) * 3;
@@ -286,11 +291,11 @@ __global__ void export_tables_kernel(const uint4 *__restrict__ records, const fl
       it[type] = type == GROUND ? GROUND : OBJECT;  // (:564, 592)
       continue;
     }
-    const Rec hi = load_rec(rec, vT + 1), lo = load_rec(rec, vB);
+    const Rec hi = load_rec(rec, Hp, vT + 1), lo = load_rec(rec, Hp, vB);
     const float fn = segment_mean(__uint_as_float(hi.w[kRecDisp]), __uint_as_float(lo.w[kRecDisp]),
                                   __uint_as_float(hi.w[kRecValid]), __uint_as_float(lo.w[kRecValid]),
                                   vT + 1 - vB, has_invalid);
-    it[type] = vB * 3 + predecessor_type<PAIRWISE>(type, vB, fn, dp_col, rec, S, Q, vhor, object_disparity_range, p);
+    it[type] = vB * 3 + predecessor_type<PAIRWISE>(type, vB, fn, dp_col, S, pm_col, vhor, object_disparity_range, p);
   }
 }
 
@@ -299,12 +304,12 @@ __global__ void export_tables_kernel(const uint4 *__restrict__ records, const fl
 void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s) {
   const int ncolumns = nframes * p.realcols;
   const int grid = (ncolumns + 127) / 128;
-  const uint4 *rec = reinterpret_cast<const uint4 *>(b.records);
+  const uint32_t *rec = b.records;
   if (pairwise)
-    backtrack_kernel<true><<<grid, 128, 0, s>>>(rec, b.dp, b.stat, b.dyn, b.vhor, b.object_disparity_range,
+    backtrack_kernel<true><<<grid, 128, 0, s>>>(rec, b.dp, b.stat, b.pm, b.vhor, b.object_disparity_range,
                                                 b.sections, b.n_sections, b.error_flag, ncolumns, p);
   else
-    backtrack_kernel<false><<<grid, 128, 0, s>>>(rec, b.dp, b.stat, b.dyn, b.vhor, b.object_disparity_range,
+    backtrack_kernel<false><<<grid, 128, 0, s>>>(rec, b.dp, b.stat, b.pm, b.vhor, b.object_disparity_range,
                                                  b.sections, b.n_sections, b.error_flag, ncolumns, p);
   collect_candidates_kernel<<<nframes, 256, 0, s>>>(b.sections, b.n_sections, b.cand_count, b.cand_offset, b.cand_xy,
                                                      b.cand_idx, b.cand_core, p);
@@ -314,13 +319,13 @@ void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pair
 void launch_export_tables(const KParams &p, const BatchBuffers &b, int frame, bool pairwise, float *cost_table,
                           int *index_table, cudaStream_t s) {
   const int n = p.realcols * p.rows;
-  const uint4 *rec = reinterpret_cast<const uint4 *>(b.records);
+  const uint32_t *rec = b.records;
   if (pairwise)
-    export_tables_kernel<true><<<(n + 127) / 128, 128, 0, s>>>(rec, b.dp, b.stat, b.dyn, b.vhor,
+    export_tables_kernel<true><<<(n + 127) / 128, 128, 0, s>>>(rec, b.dp, b.stat, b.pm, b.vhor,
                                                                b.object_disparity_range, frame, cost_table,
                                                                index_table, p);
   else
-    export_tables_kernel<false><<<(n + 127) / 128, 128, 0, s>>>(rec, b.dp, b.stat, b.dyn, b.vhor,
+    export_tables_kernel<false><<<(n + 127) / 128, 128, 0, s>>>(rec, b.dp, b.stat, b.pm, b.vhor,
                                                                 b.object_disparity_range, frame, cost_table,
                                                                 index_table, p);
   g_launch_count++;

@@ -19,9 +19,9 @@ struct BatchBuffers {
   float *stat = nullptr;               // [B][H][kStatWords] static transition records (pairwise)
   // intermediates
   float *joined = nullptr;             // [B][C][H]
-  uint32_t *records = nullptr;         // [B][C][H+1][32 words]
+  uint32_t *records = nullptr;         // [B][C][kRecWords][rec_stride], word-major (common.cuh)
   float *object_lut = nullptr;         // [B][C][D][lut_stride]
-  float *dyn = nullptr;                // [B][C][H][kDynWords] dynamic row info (pairwise)
+  float *pm = nullptr;                 // [B][C][H] previous_mean of row vB-1 (pairwise; backtracking re-derives priors)
   float4 *dp = nullptr;                // [B][C][H]: {cost_gs, cost_obj, as_float(vB_gs), as_float(vB_obj)}
   // model tables (device copies of HostModel vectors)
   const float *obj_cost_lut = nullptr;       // [D][D]

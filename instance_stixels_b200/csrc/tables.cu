@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kTabThreads)
 column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict__ segmentation,
                      const float *__restrict__ ground, const int *__restrict__ vhor_arr,
                      const float *__restrict__ obj_cost_lut, uint32_t *__restrict__ records,
-                     float *__restrict__ object_lut, KParams p) {
+                     float *__restrict__ object_lut, int *__restrict__ error_flag, KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = p.rows, C = p.realcols, D = p.max_dis;
   const int col = blockIdx.x, f = blockIdx.y;
@@ -281,30 +281,37 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   for (int c = warp; c < 21; c += kTabThreads / 32) exact_prefix_warp<int>(seg_s + c * segld, nq, seg_ps + c * segld);
   __syncthreads();
 
-  // ---- assemble the 128-byte records R[v], v in [0, H] ----
-  uint32_t *rec_col = records + ((size_t)f * C + col) * (size_t)p.rec_rows * kRecWords;
+  // ---- records[word][v], v in [0, H]: word-major, coalesced over v (layout: common.cuh) ----
+  uint32_t *rec_col = records + ((size_t)f * C + col) * (size_t)kRecWords * p.rec_stride;
+  bool out_of_range = false;
   for (int v = tid; v <= H; v += kTabThreads) {
-    uint32_t w[kRecWords];
     const int q = v >> 3, r = v & 7;
+    uint32_t *dst = rec_col + v;
 #pragma unroll
     for (int c = 0; c < 19; c++)  // P_c(v) = 8*ps[q] + seg[q]*r  (Cityscapes.h:28-42)
-      w[kRecSeg + c] = (uint32_t)(seg_ps[c * segld + q] * kDownsample + seg_s[c * segld + q] * r);
-    w[kRecOff] = (uint32_t)((seg_ps[19 * segld + q] + seg_ps[20 * segld + q]) * kDownsample +
-                            (seg_s[19 * segld + q] + seg_s[20 * segld + q]) * r);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const long long s = ps_i64[k * L.Hp + v];
-      w[kRecMx + 2 * k] = (uint32_t)(unsigned long long)s;
-      w[kRecMx + 2 * k + 1] = (uint32_t)((unsigned long long)s >> 32);
-    }
-    w[kRecDisp] = __float_as_uint(ps_f[0][v]);
-    w[kRecValid] = __float_as_uint(ps_f[1][v]);
-    w[kRecGround] = __float_as_uint(ps_f[2][v]);
-    w[kRecSky] = __float_as_uint(ps_f[3][v]);
-    uint4 *dst = reinterpret_cast<uint4 *>(rec_col + (size_t)v * kRecWords);
-#pragma unroll
-    for (int k = 0; k < kRecWords / 4; k++) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+      dst[(size_t)(kRecSeg + c) * p.rec_stride] =
+          (uint32_t)(seg_ps[c * segld + q] * kDownsample + seg_s[c * segld + q] * r);
+    dst[(size_t)kRecOff * p.rec_stride] =
+        (uint32_t)((seg_ps[19 * segld + q] + seg_ps[20 * segld + q]) * kDownsample +
+                   (seg_s[19 * segld + q] + seg_s[20 * segld + q]) * r);
+    // instance-mean sums as exactly representable floats (see common.cuh)
+    const long long smx = ps_i64[0 * L.Hp + v], smy = ps_i64[1 * L.Hp + v];
+    const long long smx2 = ps_i64[2 * L.Hp + v], smy2 = ps_i64[3 * L.Hp + v];
+    const long long lim1 = 1ll << 24, lim2 = 1ll << (24 + kSqSplitBits);
+    out_of_range |= smx <= -lim1 || smx >= lim1 || smy <= -lim1 || smy >= lim1 || smx2 >= lim2 || smy2 >= lim2;
+    const long long lomask = (1ll << kSqSplitBits) - 1;
+    dst[(size_t)kRecMx * p.rec_stride] = __float_as_uint((float)smx);
+    dst[(size_t)kRecMy * p.rec_stride] = __float_as_uint((float)smy);
+    dst[(size_t)kRecMx2Hi * p.rec_stride] = __float_as_uint((float)(smx2 & ~lomask));
+    dst[(size_t)kRecMx2Lo * p.rec_stride] = __float_as_uint((float)(smx2 & lomask));
+    dst[(size_t)kRecMy2Hi * p.rec_stride] = __float_as_uint((float)(smy2 & ~lomask));
+    dst[(size_t)kRecMy2Lo * p.rec_stride] = __float_as_uint((float)(smy2 & lomask));
+    dst[(size_t)kRecDisp * p.rec_stride] = __float_as_uint(ps_f[0][v]);
+    dst[(size_t)kRecValid * p.rec_stride] = __float_as_uint(ps_f[1][v]);
+    dst[(size_t)kRecGround * p.rec_stride] = __float_as_uint(ps_f[2][v]);
+    dst[(size_t)kRecSky * p.rec_stride] = __float_as_uint(ps_f[3][v]);
   }
+  if (out_of_range) atomicOr(error_flag, kErrOffsetRange);
 
   // ---- object LUT rows, fn = warp, warp+8, ... ----
   float *lut_col = object_lut + ((size_t)f * C + col) * (size_t)D * p.lut_stride;
@@ -332,7 +339,7 @@ void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, 
     configured = smem;
   }
   column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.obj_cost_lut,
-                                                        b.records, b.object_lut, p);
+                                                        b.records, b.object_lut, b.error_flag, p);
   g_launch_count++;
 }
 

@@ -61,6 +61,17 @@ def compare_sections(ours: np.ndarray, ref: np.ndarray, rtol: float = 1e-4) -> d
                 max_rel=max_rel, first_bad=first_bad, stixels_ours=int(n_o.sum()), stixels_ref=int(n_r.sum()))
 
 
+def same_used_sections(a: np.ndarray, b: np.ndarray) -> bool:
+    """Byte equality of the USED part of two [C][200] Section arrays: per column the stixels and the
+    type == -1 terminator.  Entries after the terminator are never written (like the reference's
+    d_stixels, StixelsKernels.cu:951-955) and hold whatever an earlier frame left there."""
+    na, nb = column_lengths(a), column_lengths(b)
+    if not np.array_equal(na, nb):
+        return False
+    used = np.arange(a.shape[1])[None, :] <= na[:, None]
+    return bool(np.array_equal(a[used].view(np.uint8), b[used].view(np.uint8)))
+
+
 def partition_of(instances: np.ndarray) -> dict:
     """{(class, label): frozenset of (column, index)} ignoring noise; plus the noise set under key None."""
     groups: dict = {}
