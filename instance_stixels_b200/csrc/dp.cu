@@ -43,8 +43,7 @@ constexpr int kQsRows = kChunk + 1;
 struct DpConsts {
   float pw, dw, sw, iw;
   float dm1f;          // max_dis - 1 as float (LUT row clamp)
-  unsigned lut_stride;
-  unsigned lut_koff;   // -(0x4B000000 * lut_stride): folds the float->index bias into one IMAD
+  unsigned lut_stride4;  // bytes per fn row of the object LUT
   bool has_invalid;
   float epsilon;
 };
@@ -56,7 +55,7 @@ __device__ __forceinline__ float f_(uint32_t u) { return __uint_as_float(u); }
 //   nf, n  : segment height as float / int,  rn = MUFU.RCP(nf)
 template <bool PAIRWISE, bool FIRST, bool GROUND, bool HAS_INVALID>
 __device__ __forceinline__ void dp_cell(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ brow,
-                                        const float *__restrict__ lut, unsigned ia, unsigned ib,
+                                        const char *pa, const char *pb,
                                         float nf, float ih, const RowInfo &q, float first_k_gs, float first_k_o,
                                         const DpConsts &c, float &cost_gs, float &cost_o) {
   uint32_t Bw[32];
@@ -105,13 +104,13 @@ __device__ __forceinline__ void dp_cell(const uint32_t (&A)[kRecWords], const ui
     mean = fmul(sd, rn);
   }
   const float fn = fmaxf(mean, 0.0f);  // == clamp_neg for every comparison below (mean is never NaN)
-  // floor(fn) as LUT row: add.rz of 2^23 leaves floor(fn) in the mantissa; the bias is folded
-  // into the row-offset multiply.
+  // floor(fn) as LUT row: add.rz of 2^23 leaves floor(fn) in the mantissa; pa / pb are the byte
+  // addresses of LUT[0][vT] / LUT[0][vB-1] minus 0x4B000000 rows, so one 32x32+64 multiply-add
+  // (IMAD.WIDE.U32) forms each address.
   const float fbias = __fadd_rz(fminf(fn, c.dm1f), 8388608.0f);
-  const unsigned off = (unsigned)__float_as_int(fbias) * c.lut_stride + c.lut_koff;
-  // 32-bit element indices from the column's LUT base: ia = vT, ib = vB - 1
-  const float lut_hi = __ldg(lut + (off + ia));
-  const float lut_lo = FIRST ? 0.0f : __ldg(lut + (off + ib));
+  const unsigned long long roff = (unsigned long long)(unsigned)__float_as_int(fbias) * c.lut_stride4;
+  const float lut_hi = __ldg(reinterpret_cast<const float *>(pa + roff));
+  const float lut_lo = FIRST ? 0.0f : __ldg(reinterpret_cast<const float *>(pb + roff));
   const float data_o = fsub(lut_hi, lut_lo);
   const float data_gs = GROUND ? fsub(f_(A[kRecGround]), f_(Bw[kRecGround])) : fsub(f_(A[kRecSky]), f_(Bw[kRecSky]));
 
@@ -156,7 +155,7 @@ __device__ __forceinline__ void store_row_info(float *qrow, const RowInfo &q) {
 //   DIAG: tile == chunk, lane l is live for k <= l only (vT >= vB).
 template <bool PAIRWISE, bool GROUND, bool DIAG, bool HAS_INVALID>
 __device__ __forceinline__ void dp_steps(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ bchunk,
-                                         const float *__restrict__ lut, unsigned ia, const float *__restrict__ ihs,
+                                         const char *lutb, const char *pa, const float *__restrict__ ihs,
                                          const float *__restrict__ qs, int vb0, int k0, int k1, int n0, int lane,
                                          const DpConsts &c, float &best_gs, float &best_o, int &vb_gs, int &vb_o) {
   RowInfo q{};
@@ -171,7 +170,7 @@ __device__ __forceinline__ void dp_steps(const uint32_t (&A)[kRecWords], const u
     if constexpr (PAIRWISE) q = load_row_info(qs + k * kDynWords);
     else ih = DIAG ? ihs[max(n0 - k, 1)] : *ihp;
     float cost_gs, cost_o;
-    dp_cell<PAIRWISE, false, GROUND, HAS_INVALID>(A, bchunk + k * kBStride, lut, ia, (unsigned)(vB - 1), nfc, ih, q,
+    dp_cell<PAIRWISE, false, GROUND, HAS_INVALID>(A, bchunk + k * kBStride, pa, lutb + 4 * (vB - 1), nfc, ih, q,
                                                   0.0f, 0.0f, c, cost_gs, cost_o);
     const bool live = !DIAG || lane >= k;
     if (live && cost_gs < best_gs) { best_gs = cost_gs; vb_gs = vB; }
@@ -219,13 +218,16 @@ dp_kernel(const uint32_t *__restrict__ records, const float *__restrict__ object
   DpConsts c;
   c.pw = p.prior_weight; c.dw = p.disparity_weight; c.sw = p.segmentation_weight; c.iw = p.instance_weight;
   c.dm1f = (float)(p.max_dis - 1);
-  c.lut_stride = (unsigned)p.lut_stride;
-  c.lut_koff = 0u - 0x4B000000u * (unsigned)p.lut_stride;
+  c.lut_stride4 = (unsigned)p.lut_stride * 4u;
   c.has_invalid = HAS_INVALID;
   c.epsilon = p.epsilon;
 
   const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
   const float *lut = object_lut + (size_t)gcol * p.max_dis * p.lut_stride;
+  // byte address of LUT[0][0] of this column minus the 2^23 bias rows (see dp_cell); opaque to the
+  // compiler so that it stays one materialised 64-bit base
+  const char *lutb = reinterpret_cast<const char *>(lut) - (unsigned long long)0x4B000000u * c.lut_stride4;
+  asm volatile("" : "+l"(lutb));
   const float *S = stat + (size_t)f * H * kStatWords;
   float *pm_col = pm_out + (size_t)gcol * H;
 
@@ -276,7 +278,7 @@ dp_kernel(const uint32_t *__restrict__ records, const float *__restrict__ object
 #pragma unroll
         for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
         const float a_disp = f_(A[kRecDisp]), a_valid = f_(A[kRecValid]);
-        const unsigned ia = (unsigned)vTc;
+        const char *pa = lutb + 4 * vTc;
         // start from the minima over the earlier chunks (lower vB: they keep winning ties)
         const float4 prev = best[vb0 + lane];
         float best_gs = prev.x, best_o = prev.y;
@@ -305,13 +307,13 @@ dp_kernel(const uint32_t *__restrict__ records, const float *__restrict__ object
           const uint32_t *brow = bchunk + k * kBStride;
           if (vB == 0) {
             const float first_k_o = fmul(fadd(fadd((vT <= vhor) ? kLn2 : 0.0f, p.rows_log), p.max_dis_log), c.pw);
-            dp_cell<true, true, true, HAS_INVALID>(A, brow, lut, ia, 0u, (float)n, 0.0f, q, first_k_gs, first_k_o, c,
+            dp_cell<true, true, true, HAS_INVALID>(A, brow, pa, lutb, (float)n, 0.0f, q, first_k_gs, first_k_o, c,
                                                    cost_gs, cost_o);
           } else if (k < kg) {
-            dp_cell<true, false, true, HAS_INVALID>(A, brow, lut, ia, (unsigned)(vB - 1), (float)n, 0.0f, q, 0.0f,
+            dp_cell<true, false, true, HAS_INVALID>(A, brow, pa, lutb + 4 * (vB - 1), (float)n, 0.0f, q, 0.0f,
                                                     0.0f, c, cost_gs, cost_o);
           } else {
-            dp_cell<true, false, false, HAS_INVALID>(A, brow, lut, ia, (unsigned)(vB - 1), (float)n, 0.0f, q, 0.0f,
+            dp_cell<true, false, false, HAS_INVALID>(A, brow, pa, lutb + 4 * (vB - 1), (float)n, 0.0f, q, 0.0f,
                                                      0.0f, c, cost_gs, cost_o);
           }
           const bool live = row_ok && lane >= k;
@@ -345,7 +347,7 @@ dp_kernel(const uint32_t *__restrict__ records, const float *__restrict__ object
       uint32_t A[kRecWords];
 #pragma unroll
       for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
-      const unsigned ia = (unsigned)vTc;
+      const char *pa = lutb + 4 * vTc;
       const float4 prev = best[t * kChunk + lane];
       float best_gs = prev.x, best_o = prev.y;
       int vb_gs = __float_as_int(prev.z), vb_o = __float_as_int(prev.w);
@@ -357,21 +359,21 @@ dp_kernel(const uint32_t *__restrict__ records, const float *__restrict__ object
         RowInfo q{};
         const float first_k_o =
             PAIRWISE ? fmul(fadd(fadd((vT <= vhor) ? kLn2 : 0.0f, p.rows_log), p.max_dis_log), c.pw) : 0.0f;
-        dp_cell<PAIRWISE, true, true, HAS_INVALID>(A, bchunk, lut, ia, 0u, (float)n0, PAIRWISE ? 0.0f : extra[n0], q,
+        dp_cell<PAIRWISE, true, true, HAS_INVALID>(A, bchunk, pa, lutb, (float)n0, PAIRWISE ? 0.0f : extra[n0], q,
                                                    first_k_gs, first_k_o, c, cost_gs, cost_o);
         if (cost_gs < best_gs) { best_gs = cost_gs; vb_gs = 0; }
         if (cost_o < best_o) { best_o = cost_o; vb_o = 0; }
         k0 = 1;
       }
       if (!PAIRWISE && t == j) {  // unary only: the diagonal unit needs the vT >= vB predicate
-        dp_steps<PAIRWISE, true, true, HAS_INVALID>(A, bchunk, lut, ia, extra, extra, vb0, k0, max(k0, kg), n0, lane,
+        dp_steps<PAIRWISE, true, true, HAS_INVALID>(A, bchunk, lutb, pa, extra, extra, vb0, k0, max(k0, kg), n0, lane,
                                                     c, best_gs, best_o, vb_gs, vb_o);
-        dp_steps<PAIRWISE, false, true, HAS_INVALID>(A, bchunk, lut, ia, extra, extra, vb0, max(k0, kg), nsteps, n0,
+        dp_steps<PAIRWISE, false, true, HAS_INVALID>(A, bchunk, lutb, pa, extra, extra, vb0, max(k0, kg), nsteps, n0,
                                                      lane, c, best_gs, best_o, vb_gs, vb_o);
       } else {
-        dp_steps<PAIRWISE, true, false, HAS_INVALID>(A, bchunk, lut, ia, extra, extra, vb0, k0, max(k0, kg), n0, lane,
+        dp_steps<PAIRWISE, true, false, HAS_INVALID>(A, bchunk, lutb, pa, extra, extra, vb0, k0, max(k0, kg), n0, lane,
                                                      c, best_gs, best_o, vb_gs, vb_o);
-        dp_steps<PAIRWISE, false, false, HAS_INVALID>(A, bchunk, lut, ia, extra, extra, vb0, max(k0, kg), nsteps, n0,
+        dp_steps<PAIRWISE, false, false, HAS_INVALID>(A, bchunk, lutb, pa, extra, extra, vb0, max(k0, kg), nsteps, n0,
                                                       lane, c, best_gs, best_o, vb_gs, vb_o);
       }
       best[t * kChunk + lane] = make_float4(best_gs, best_o, __int_as_float(vb_gs), __int_as_float(vb_o));

@@ -167,7 +167,7 @@ constexpr int kTabThreads = 256;
 // Dynamic shared memory carve-up (bytes), Hp = H + 1 rounded up to 4.
 struct TabSmem {
   int Hp, nq;
-  size_t off_e[4], off_ps[4], off_segps, off_seg, off_i64e, off_i64ps, off_dis, total;
+  size_t off_e[4], off_ps[4], off_segps, off_seg, off_i64e, off_i64ps, total;
   __host__ __device__ TabSmem(int H, int hs2) {
     Hp = (H + 1 + 3) & ~3;
     nq = H / 8 + 1;  // prefix entries per 1/8-res channel (index v>>3 for v <= H)
@@ -178,7 +178,6 @@ struct TabSmem {
     off_i64ps = o; o += (size_t)Hp * 8 * 4;
     off_seg = o; o += (size_t)21 * (nq + 1) * 4;
     off_segps = o; o += (size_t)21 * (nq + 1) * 4;
-    off_dis = o; o += (size_t)Hp;
     total = (o + 15) & ~(size_t)15;
     (void)hs2;
   }
@@ -187,10 +186,9 @@ struct TabSmem {
 __global__ void __launch_bounds__(kTabThreads)
 column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict__ segmentation,
                      const float *__restrict__ ground, const int *__restrict__ vhor_arr,
-                     const float *__restrict__ obj_cost_lut, uint32_t *__restrict__ records,
-                     float *__restrict__ object_lut, int *__restrict__ error_flag, KParams p) {
+                     uint32_t *__restrict__ records, int *__restrict__ error_flag, KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int H = p.rows, C = p.realcols, D = p.max_dis;
+  const int H = p.rows, C = p.realcols;
   const int col = blockIdx.x, f = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const TabSmem L(H, p.hs2);
@@ -204,7 +202,6 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   long long *ps_i64 = reinterpret_cast<long long *>(smem + L.off_i64ps);  // [4][Hp]
   int *seg_s = reinterpret_cast<int *>(smem + L.off_seg);                 // [21][nq+1]
   int *seg_ps = reinterpret_cast<int *>(smem + L.off_segps);              // [21][nq+1]
-  uint8_t *dis_s = smem + L.off_dis;
   const int nq = L.nq, segld = nq + 1;
 
   const float *d_col = joined + ((size_t)f * C + col) * H;
@@ -265,9 +262,6 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
     e_i64[1 * L.Hp + v] = my;
     e_i64[2 * L.Hp + v] = mx * mx;
     e_i64[3 * L.Hp + v] = my * my;
-    int di = (int)d;  // (int) d as LUT index (:246-248)
-    di = di < 0 ? 0 : (di >= D ? D - 1 : di);
-    dis_s[v] = (uint8_t)di;
   }
   __syncthreads();
 
@@ -312,12 +306,37 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
     dst[(size_t)kRecSky * p.rec_stride] = __float_as_uint(ps_f[3][v]);
   }
   if (out_of_range) atomicOr(error_flag, kErrOffsetRange);
-
-  // ---- object LUT rows, fn = warp, warp+8, ... ----
-  float *lut_col = object_lut + ((size_t)f * C + col) * (size_t)D * p.lut_stride;
-  for (int fn = warp; fn < D; fn += kTabThreads / 32)
-    object_lut_row(obj_cost_lut + (size_t)fn * D, dis_s, H, lut_col + (size_t)fn * p.lut_stride);
   (void)lane;
+}
+
+// ---------------------------------------------------------------------------
+// Object-cost LUT (ComputeObjectLUT, StixelsKernels.cu:959-978): one warp per
+// (column, fn) row.  The reference's summation order makes the 32-row chunks of
+// a row a serial chain of shuffles, so the kernel is built for occupancy: no
+// shared memory beyond the column's 1 KB of quantised disparities, 16 warps per
+// CTA, every warp an independent row; each chunk is stored as one 128-byte line.
+// ---------------------------------------------------------------------------
+constexpr int kLutWarps = 16;
+constexpr int kLutThreads = kLutWarps * 32;
+
+__global__ void __launch_bounds__(kLutThreads, 4)
+object_lut_kernel(const float *__restrict__ joined, const float *__restrict__ obj_cost_lut,
+                  float *__restrict__ object_lut, KParams p) {
+  __shared__ uint8_t dis_s[1024];
+  const int H = p.rows, C = p.realcols, D = p.max_dis;
+  const int col = blockIdx.x, f = blockIdx.z;
+  const int warp = threadIdx.x >> 5;
+  const float *d_col = joined + ((size_t)f * C + col) * H;
+  for (int v = threadIdx.x; v < H; v += kLutThreads) {
+    int di = (int)d_col[v];  // (int) d as LUT index (:246-248)
+    di = di < 0 ? 0 : (di >= D ? D - 1 : di);
+    dis_s[v] = (uint8_t)di;
+  }
+  __syncthreads();
+  const int fn = blockIdx.y * kLutWarps + warp;
+  if (fn >= D) return;
+  float *lut_col = object_lut + ((size_t)f * C + col) * (size_t)D * p.lut_stride;
+  object_lut_row(obj_cost_lut + (size_t)fn * D, dis_s, H, lut_col + (size_t)fn * p.lut_stride);
 }
 
 }  // namespace
@@ -338,9 +357,11 @@ void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, 
     cudaFuncSetAttribute(column_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.obj_cost_lut,
-                                                        b.records, b.object_lut, b.error_flag, p);
-  g_launch_count++;
+  column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.records,
+                                                        b.error_flag, p);
+  dim3 lgrid(p.realcols, (p.max_dis + kLutWarps - 1) / kLutWarps, nframes);
+  object_lut_kernel<<<lgrid, kLutThreads, 0, s>>>(b.joined, b.obj_cost_lut, b.object_lut, p);
+  g_launch_count += 2;
 }
 
 }  // namespace isx
