@@ -53,6 +53,9 @@ constexpr int kRecValid = 27;  // float prefix of valid                       (:
 constexpr int kRecGround = 28; // float Blelloch-order prefix of ground_lut   (:437-446,460)
 constexpr int kRecSky = 29;    // float Blelloch-order prefix of sky_lut      (:424-433,461)
 constexpr int kSqSplitBits = 12;
+// Second copy for the B side: records_b[column][v][32 words] (30 used), 128-byte rows, so that the 32
+// rows of a vB chunk are one contiguous 4 KB block for cp.async.bulk.
+constexpr int kRecBWords = 32;
 // bits of the sticky device error flag
 constexpr int kErrSectionOverflow = 1;  // a column produced >= 200 stixels (StixelsKernels.cu:950 asserts)
 constexpr int kErrOffsetRange = 2;      // instance-offset sums outside the exact-float range above

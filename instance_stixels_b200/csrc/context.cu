@@ -448,6 +448,8 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &b.joined, ch * C * H));
   ISX_TRY(h, dev_alloc(h, &b.records, ch * C * kRecWords * (size_t)kp.rec_stride));
   ISX_TRY(h, cudaMemset(b.records, 0, ch * C * kRecWords * (size_t)kp.rec_stride * sizeof(uint32_t)));
+  ISX_TRY(h, dev_alloc(h, &b.records_b, ch * C * kRecBWords * (size_t)kp.rec_stride));
+  ISX_TRY(h, cudaMemset(b.records_b, 0, ch * C * kRecBWords * (size_t)kp.rec_stride * sizeof(uint32_t)));
   ISX_TRY(h, dev_alloc(h, &b.object_lut, ch * C * D * (size_t)kp.lut_stride));
   ISX_TRY(h, dev_alloc(h, &b.pm, ch * C * H));
   ISX_TRY(h, dev_alloc(h, &b.dp, ch * C * H));

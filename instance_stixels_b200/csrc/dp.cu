@@ -4,21 +4,32 @@
 //
 // Mapping (B200): ONE CTA (8 warps) owns one (frame, column).  The column's rows
 // are cut into tiles of 32 top rows (lane l of a warp owns vT = a + l) and into
-// chunks of 32 candidate bottom rows vB.  The CTA walks the vB chunks in
-// lockstep: the chunk's 32 prefix records ("B side") are staged once in shared
-// memory, and every tile at or above the chunk is one unit of work for one
-// warp: it loads its own records R[vT+1] ("A side", coalesced word-major lines)
-// into registers, evaluates the 32 x 32 cells of the unit with the B side read
-// as 128-bit shared-memory broadcasts, and keeps the running (cost, vB) minimum
-// with the reference's strict-< rule (lowest vB wins ties).  Because all warps
-// of the CTA are inside the same vB chunk of the same column at the same time,
-// the object-LUT gathers of a step hit the same few L1 lines.
+// chunks of 32 candidate bottom rows vB.  A (tile, chunk) pair with tile >=
+// chunk is one unit of work: 32 x 32 DP cells.
 //
-// Pairwise mode adds the wavefront: the diagonal unit (tile == chunk) is
-// processed first by warp 0, which finalises row vB-1 before it evaluates vB,
-// exchanges it through warp shuffles and publishes the per-vB transition
-// scalars Q[vB] in shared memory for the off-diagonal units of the chunk.
-// No tensor cores (min-plus recurrence).
+//  * B side: the 32 prefix records of a chunk (4 KB, chunk-major copy of the
+//    column tables) travel global -> shared memory as ONE bulk async copy
+//    (cp.async.bulk, mbarrier complete_tx) into a ring of kStages slots; one
+//    elected lane is the producer, slots are recycled through empty barriers.
+//    Inside a unit the record of vB is read as 8 warp-uniform LDS.128.
+//  * A side: for a unit the warp loads its records R[vT+1] from the word-major
+//    copy (one coalesced line per word) into 30 registers; the running
+//    (cost, vB) minima of a tile live in shared memory between its units and
+//    are handed from the warp that did (tile, chunk-1) to the one doing
+//    (tile, chunk) through a per-tile mbarrier.  Strict '<' in ascending vB
+//    order reproduces the reference's tie rule (lowest vB wins).
+//  * Scheduling: units are handed out chunk-major from shared-memory counters
+//    (one atomicAdd per unit), lowest tile first, so the warps stay within a
+//    chunk or two of each other, nobody waits at a CTA-wide barrier, and in
+//    pairwise mode the units that the next diagonal needs are taken first.
+//
+// Pairwise mode adds the wavefront along the diagonal units (tile == chunk):
+// the warp that draws the diagonal unit j first evaluates the chain-independent part of its 32 x 32
+// cells in parallel (pass 1, parked in shared memory), then finalises row after
+// row (pass 2: row vB-1 -> transition scalars Q[vB] -> row vB) exchanging the
+// finished row through warp shuffles, and publishes Q[vB] of the chunk for the
+// off-diagonal units of the other warps through an mbarrier.
+// No tensor cores: the recurrence is min-plus, not a dense contraction.
 //
 // Because one of GROUND/SKY is +inf for every row (ground only exists below
 // the horizon, sky only at/above it) the cost table keeps two slots per row:
@@ -35,29 +46,63 @@ namespace {
 constexpr int kDpWarps = 8;
 constexpr int kDpThreads = kDpWarps * 32;
 constexpr int kChunk = 32;
-constexpr int kBStride = 36;  // words per staged B row: >= 32, rows stay 16-byte aligned
-constexpr int kStageWords = kRecWords * kChunk;
-constexpr int kStagePerThread = (kStageWords + kDpThreads - 1) / kDpThreads;
-constexpr int kQsRows = kChunk + 1;
+constexpr int kStages = 6;     // ring slots of 4 KB
+constexpr int kPrefetch = 3;   // chunks the producer runs ahead (< kStages)
+constexpr int kSlotWords = kChunk * kRecBWords;
+constexpr int kSlotBytes = kSlotWords * 4;
+constexpr int kSstWords = ((kChunk + 1) * kStatWords + 3) & ~3;  // staged static transition records of a chunk
+constexpr int kBaseWords = 5 * kChunk * 32;                      // parked CellBase of a diagonal unit
 
 struct DpConsts {
   float pw, dw, sw, iw;
-  float dm1f;          // max_dis - 1 as float (LUT row clamp)
+  float dm1f;            // max_dis - 1 as float (LUT row clamp)
   unsigned lut_stride4;  // bytes per fn row of the object LUT
-  bool has_invalid;
   float epsilon;
 };
 
 __device__ __forceinline__ float f_(uint32_t u) { return __uint_as_float(u); }
 
-// One DP cell per lane: segment (vB .. vT) of this lane's row vT.
-//   A      : R[vT+1] in registers,  brow: R[vB] in shared memory (warp-uniform address)
-//   nf, n  : segment height as float / int,  rn = MUFU.RCP(nf)
-template <bool PAIRWISE, bool FIRST, bool GROUND, bool HAS_INVALID>
-__device__ __forceinline__ void dp_cell(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ brow,
-                                        const char *pa, const char *pb,
-                                        float nf, float ih, const RowInfo &q, float first_k_gs, float first_k_o,
-                                        const DpConsts &c, float &cost_gs, float &cost_o) {
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- one DP cell per lane: segment (vB .. vT) of this lane's row vT ----
+// The chain-independent part: everything that does not need the costs of row vB - 1.
+struct CellBase {
+  float seg_gs, data_gs, seg_o, data_o, fn;
+};
+
+//   A : R[vT+1] in registers,  brow: R[vB] in shared memory (warp-uniform address)
+//   nf: segment height as float;  pa / pb: biased byte addresses of LUT[0][vT] / LUT[0][vB-1]
+template <bool FIRST, bool GROUND, bool HAS_INVALID>
+__device__ __forceinline__ CellBase cell_base(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ brow,
+                                              const char *pa, const char *pb, float nf, const DpConsts &c) {
   uint32_t Bw[32];
   {
     const uint4 *b4 = reinterpret_cast<const uint4 *>(brow);
@@ -88,10 +133,11 @@ __device__ __forceinline__ void dp_cell(const uint32_t (&A)[kRecWords], const ui
   const float fmy2 = fadd(fsub(f_(A[kRecMy2Hi]), f_(Bw[kRecMy2Hi])), fsub(f_(A[kRecMy2Lo]), f_(Bw[kRecMy2Lo])));
   const float var = ffma(-fmul(fmy, fmy), rn, fadd(fmy2, ffma(-fmul(fmx, fmx), rn, fmx2)));
   const float ic = fmul(var, c.iw);
-  const float seg_o = fmin_(fadd(nic, (float)s_ni), fadd(ic, (float)s_in));
+  CellBase b;
+  b.seg_o = fmin_(fadd(nic, (float)s_ni), fadd(ic, (float)s_in));
   // In the first-segment block nvcc contracted `min(road, sidewalk) + weight * offsets` into one
   // FFMA (reference SASS of StixelsKernels.cu:502-506); everywhere else it is FMUL + FADD.
-  const float seg_gs = FIRST ? ffma(f_off, c.iw, (float)s_gs) : fadd(nic, (float)s_gs);
+  b.seg_gs = FIRST ? ffma(f_off, c.iw, (float)s_gs) : fadd(nic, (float)s_gs);
 
   // ---- disparity terms: ComputeMean (:47-60) + clamp (:651-653) ----
   const float sd = fsub(f_(A[kRecDisp]), f_(Bw[kRecDisp]));
@@ -103,18 +149,23 @@ __device__ __forceinline__ void dp_cell(const uint32_t (&A)[kRecWords], const ui
   } else {
     mean = fmul(sd, rn);
   }
-  const float fn = fmaxf(mean, 0.0f);  // == clamp_neg for every comparison below (mean is never NaN)
+  b.fn = fmaxf(mean, 0.0f);  // == clamp_neg for every comparison downstream (mean is never NaN)
   // floor(fn) as LUT row: add.rz of 2^23 leaves floor(fn) in the mantissa; pa / pb are the byte
   // addresses of LUT[0][vT] / LUT[0][vB-1] minus 0x4B000000 rows, so one 32x32+64 multiply-add
   // (IMAD.WIDE.U32) forms each address.
-  const float fbias = __fadd_rz(fminf(fn, c.dm1f), 8388608.0f);
+  const float fbias = __fadd_rz(fminf(b.fn, c.dm1f), 8388608.0f);
   const unsigned long long roff = (unsigned long long)(unsigned)__float_as_int(fbias) * c.lut_stride4;
   const float lut_hi = __ldg(reinterpret_cast<const float *>(pa + roff));
   const float lut_lo = FIRST ? 0.0f : __ldg(reinterpret_cast<const float *>(pb + roff));
-  const float data_o = fsub(lut_hi, lut_lo);
-  const float data_gs = GROUND ? fsub(f_(A[kRecGround]), f_(Bw[kRecGround])) : fsub(f_(A[kRecSky]), f_(Bw[kRecSky]));
+  b.data_o = fsub(lut_hi, lut_lo);
+  b.data_gs = GROUND ? fsub(f_(A[kRecGround]), f_(Bw[kRecGround])) : fsub(f_(A[kRecSky]), f_(Bw[kRecSky]));
+  return b;
+}
 
-  // ---- combine (:548-560, 575-584, 700-720, 740-766, 788-824) ----
+// Prior + combine (:548-560, 575-584, 700-720, 740-766, 788-824).
+template <bool PAIRWISE, bool FIRST, bool GROUND>
+__device__ __forceinline__ void cell_finish(const CellBase &b, float ih, const RowInfo &q, float first_k_gs,
+                                            float first_k_o, const DpConsts &c, float &cost_gs, float &cost_o) {
   if constexpr (PAIRWISE) {
     float k_gs, k_o;
     if constexpr (FIRST) {
@@ -122,15 +173,15 @@ __device__ __forceinline__ void dp_cell(const uint32_t (&A)[kRecWords], const ui
       k_o = first_k_o;
     } else {
       float p1, p2, p3;
-      object_priors(q, GROUND, fn, c.epsilon, p1, p2, p3);
+      object_priors(q, GROUND, b.fn, c.epsilon, p1, p2, p3);
       k_gs = q.gs_k;
       k_o = fmul(fmin_(p3, fmin_(p1, p2)), c.pw);
     }
-    cost_gs = ffma(seg_gs, c.sw, ffma(data_gs, c.dw, k_gs));
-    cost_o = ffma(seg_o, c.sw, ffma(data_o, c.dw, k_o));
+    cost_gs = ffma(b.seg_gs, c.sw, ffma(b.data_gs, c.dw, k_gs));
+    cost_o = ffma(b.seg_o, c.sw, ffma(b.data_o, c.dw, k_o));
   } else {
-    cost_gs = ffma(seg_gs, c.sw, ffma(ih, c.pw, fmul(data_gs, c.dw)));
-    cost_o = ffma(seg_o, c.sw, ffma(ih, c.pw, fmul(data_o, c.dw)));
+    cost_gs = ffma(b.seg_gs, c.sw, ffma(ih, c.pw, fmul(b.data_gs, c.dw)));
+    cost_o = ffma(b.seg_o, c.sw, ffma(ih, c.pw, fmul(b.data_o, c.dw)));
   }
 }
 
@@ -151,15 +202,20 @@ __device__ __forceinline__ void store_row_info(float *qrow, const RowInfo &q) {
   qd[2] = make_float4(q.p2_mid, q.t2_hi, q.t2_lo, q.pm);
 }
 
+struct Best {
+  float gs, o;
+  int vb_gs, vb_o;
+};
+
 // Steps [k0, k1) of one unit; the whole range lies on one side of the horizon.
-//   DIAG: tile == chunk, lane l is live for k <= l only (vT >= vB).
+//   DIAG (unary only): tile == chunk, lane l is live for k <= l only (vT >= vB).
 template <bool PAIRWISE, bool GROUND, bool DIAG, bool HAS_INVALID>
 __device__ __forceinline__ void dp_steps(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ bchunk,
                                          const char *lutb, const char *pa, const float *__restrict__ ihs,
                                          const float *__restrict__ qs, int vb0, int k0, int k1, int n0, int lane,
-                                         const DpConsts &c, float &best_gs, float &best_o, int &vb_gs, int &vb_o) {
+                                         const DpConsts &c, Best &best) {
   RowInfo q{};
-  float nf = (float)(n0 - k0);       // segment height vT + 1 - vB, kept as a float counter
+  float nf = (float)(n0 - k0);  // segment height vT + 1 - vB, kept as a float counter
   const float *ihp = ihs + (n0 - k0);
 #pragma unroll 2
   for (int k = k0; k < k1; k++) {
@@ -169,178 +225,277 @@ __device__ __forceinline__ void dp_steps(const uint32_t (&A)[kRecWords], const u
     float ih = 0.0f;
     if constexpr (PAIRWISE) q = load_row_info(qs + k * kDynWords);
     else ih = DIAG ? ihs[max(n0 - k, 1)] : *ihp;
+    const CellBase b =
+        cell_base<false, GROUND, HAS_INVALID>(A, bchunk + k * kRecBWords, pa, lutb + 4 * (vB - 1), nfc, c);
     float cost_gs, cost_o;
-    dp_cell<PAIRWISE, false, GROUND, HAS_INVALID>(A, bchunk + k * kBStride, pa, lutb + 4 * (vB - 1), nfc, ih, q,
-                                                  0.0f, 0.0f, c, cost_gs, cost_o);
+    cell_finish<PAIRWISE, false, GROUND>(b, ih, q, 0.0f, 0.0f, c, cost_gs, cost_o);
     const bool live = !DIAG || lane >= k;
-    if (live && cost_gs < best_gs) { best_gs = cost_gs; vb_gs = vB; }
-    if (live && cost_o < best_o) { best_o = cost_o; vb_o = vB; }
+    if (live && cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = vB; }
+    if (live && cost_o < best.o) { best.o = cost_o; best.vb_o = vB; }
     nf = fadd(nf, -1.0f);
     ihp--;
   }
 }
 
-// previous_mean of the best object segment ending at row pv (:674-685) and the row info of vB = pv + 1.
-__device__ __forceinline__ RowInfo finish_row(const uint32_t *__restrict__ rec, int Hp, const float *__restrict__ S,
-                                              int vB, int vhor, float c_gs, float c_o, int o_vb, float hi_d,
-                                              float hi_v, const float *__restrict__ object_disparity_range,
-                                              const KParams &p, bool has_invalid) {
-  const bool ground_side = vB - 1 < vhor;
-  const float lo_d = f_(__ldg(rec + (size_t)kRecDisp * Hp + o_vb));
-  const float lo_v = f_(__ldg(rec + (size_t)kRecValid * Hp + o_vb));
-  const float pm = segment_mean(hi_d, lo_d, hi_v, lo_v, vB - o_vb, has_invalid);
-  const float inf = inf_f();
-  RowPriors rp;
-  return make_row_info(S + (size_t)vB * kStatWords, ground_side, ground_side ? c_gs : inf, c_o,
-                       ground_side ? inf : c_gs, pm, object_disparity_range, p, &rp);
-}
+// Shared-memory carve-up (bytes).
+struct DpLayout {
+  int nt;
+  size_t off_ring, off_bars, off_cnt, off_best, off_ih, off_qs, off_qnext, off_sst, off_dps, off_vps, off_odr, off_base, total;
+  __host__ __device__ DpLayout(int H, int Hp, int D, bool pairwise) {
+    nt = (H + kChunk - 1) / kChunk;
+    size_t o = 0;
+    off_ring = o; o += (size_t)kStages * kSlotBytes;
+    off_bars = o; o += (size_t)2 * kStages * 8;            // full[kStages] | qfull[kStages]
+    off_cnt = o; o += (size_t)3 * nt * 4;                  // per chunk: units handed out | finished; per tile: chunks done
+    o = (o + 15) & ~(size_t)15;
+    off_best = o; o += (size_t)nt * kChunk * 16;
+    off_ih = off_qs = off_qnext = off_sst = off_dps = off_vps = off_odr = off_base = o;
+    if (!pairwise) {
+      off_ih = o; o += (size_t)(H + 1) * 4;
+    } else {
+      off_qs = o; o += (size_t)kStages * kChunk * kDynWords * 4;
+      off_qnext = o; o += (size_t)2 * kDynWords * 4;
+      off_sst = o; o += (size_t)2 * kSstWords * 4;           // double-buffered: consecutive diagonals overlap
+      off_dps = o; o += (size_t)Hp * 4;
+      off_vps = o; o += (size_t)Hp * 4;
+      off_odr = o; o += (size_t)((D + 3) & ~3) * 4;
+      off_base = o; o += (size_t)2 * kBaseWords * 4;         // double-buffered like sst
+    }
+    total = (o + 15) & ~(size_t)15;
+  }
+};
 
 template <bool PAIRWISE, bool HAS_INVALID>
 __global__ void __launch_bounds__(kDpThreads, 2)
-dp_kernel(const uint32_t *__restrict__ records, const float *__restrict__ object_lut, const float *__restrict__ stat,
-          float *__restrict__ pm_out, const int *__restrict__ vhor_arr,
-          const float *__restrict__ object_disparity_range, const float *__restrict__ inverse_height,
-          float4 *__restrict__ dp_out, KParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const unsigned full = 0xffffffffu;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
+          const float *__restrict__ object_lut, const float *__restrict__ stat, float *__restrict__ pm_out,
+          const int *__restrict__ vhor_arr, const float *__restrict__ object_disparity_range,
+          const float *__restrict__ inverse_height, float4 *__restrict__ dp_out, KParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const unsigned full_mask = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int gcol = blockIdx.x;  // frame * C + column
   const int H = p.rows, C = p.realcols, Hp = p.rec_stride;
   const int f = gcol / C;
   const int vhor = vhor_arr[f];
-  const int nchunks = (H + kChunk - 1) / kChunk;
   const float inf = inf_f();
+  const DpLayout L(H, Hp, p.max_dis, PAIRWISE);
+  const int nt = L.nt;
 
-  uint32_t *brec = reinterpret_cast<uint32_t *>(smem_raw);                       // [2][32][kBStride]
-  float4 *best = reinterpret_cast<float4 *>(smem_raw + 2 * kChunk * kBStride * 4);  // [32 * nchunks]
-  float *extra = reinterpret_cast<float *>(best + kChunk * nchunks);             // unary: ih[H+1]; pairwise: qs[33][12]
+  uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + L.off_ring);
+  uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem_raw + L.off_bars);
+  uint64_t *bar_q = bar_full + kStages;
+  int *cnt_out = reinterpret_cast<int *>(smem_raw + L.off_cnt);  // [nt] units handed out, per chunk
+  int *cnt_fin = cnt_out + nt;                                    // [nt] units finished, per chunk
+  int *tile_done = cnt_fin + nt;                                  // [nt] chunks finished, per tile
+  float4 *best_s = reinterpret_cast<float4 *>(smem_raw + L.off_best);
+  float *ihs = reinterpret_cast<float *>(smem_raw + L.off_ih);
+  float *qs = reinterpret_cast<float *>(smem_raw + L.off_qs);
+  float *qnext = reinterpret_cast<float *>(smem_raw + L.off_qnext);
+  float *sst = reinterpret_cast<float *>(smem_raw + L.off_sst);
+  float *dps = reinterpret_cast<float *>(smem_raw + L.off_dps);
+  float *vps = reinterpret_cast<float *>(smem_raw + L.off_vps);
+  float *odr = reinterpret_cast<float *>(smem_raw + L.off_odr);
+  float *base_s = reinterpret_cast<float *>(smem_raw + L.off_base);
 
   DpConsts c;
   c.pw = p.prior_weight; c.dw = p.disparity_weight; c.sw = p.segmentation_weight; c.iw = p.instance_weight;
   c.dm1f = (float)(p.max_dis - 1);
   c.lut_stride4 = (unsigned)p.lut_stride * 4u;
-  c.has_invalid = HAS_INVALID;
   c.epsilon = p.epsilon;
 
   const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
+  const uint32_t *recb = records_b + (size_t)gcol * Hp * kRecBWords;
   const float *lut = object_lut + (size_t)gcol * p.max_dis * p.lut_stride;
-  // byte address of LUT[0][0] of this column minus the 2^23 bias rows (see dp_cell); opaque to the
+  // byte address of LUT[0][0] of this column minus the 2^23 bias rows (see cell_base); opaque to the
   // compiler so that it stays one materialised 64-bit base
   const char *lutb = reinterpret_cast<const char *>(lut) - (unsigned long long)0x4B000000u * c.lut_stride4;
   asm volatile("" : "+l"(lutb));
   const float *S = stat + (size_t)f * H * kStatWords;
   float *pm_col = pm_out + (size_t)gcol * H;
+  float4 *out = dp_out + (size_t)gcol * H;
 
-  for (int i = tid; i < kChunk * nchunks; i += kDpThreads) best[i] = make_float4(inf, inf, 0.0f, 0.0f);
-  if constexpr (!PAIRWISE)
-    for (int i = tid; i <= H; i += kDpThreads) extra[i] = __ldg(inverse_height + i);
+  // ---- one-time setup ----
+  if (tid == 0) {
+    for (int s = 0; s < kStages; s++) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_q[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < nt * kChunk; i += kDpThreads) best_s[i] = make_float4(inf, inf, 0.0f, 0.0f);
+  for (int i = tid; i < 3 * nt; i += kDpThreads) cnt_out[i] = 0;
+  if constexpr (!PAIRWISE) {
+    for (int i = tid; i <= H; i += kDpThreads) ihs[i] = __ldg(inverse_height + i);
+  } else {
+    for (int i = tid; i <= H; i += kDpThreads) {
+      dps[i] = f_(__ldg(rec + (size_t)kRecDisp * Hp + i));
+      vps[i] = f_(__ldg(rec + (size_t)kRecValid * Hp + i));
+    }
+    for (int i = tid; i < p.max_dis; i += kDpThreads) odr[i] = __ldg(object_disparity_range + i);
+  }
+  __syncthreads();
+
+  // ---- producer: chunk ch -> ring slot ch % kStages (one elected lane).  The slot is free once
+  //      every unit of the chunk that used it before has finished. ----
+  auto produce = [&](int ch) {
+    if (ch >= nt) return;
+    const int s = ch % kStages;
+    if (ch >= kStages) {
+      const int old = ch - kStages;
+      while (*reinterpret_cast<volatile int *>(cnt_fin + old) < nt - old) __nanosleep(64);
+      __threadfence_block();
+    }
+    mbar_arrive_expect_tx(&bar_full[s], kSlotBytes);
+    bulk_g2s(ring + (size_t)s * kSlotWords, recb + (size_t)ch * kSlotWords, kSlotBytes, &bar_full[s]);
+  };
+  if (tid == 0)
+    for (int ch = 0; ch < kPrefetch; ch++) produce(ch);
 
   // first-segment priors (:189-199)
   const float first_k_gs = fmul(ffma(1.0f, kLn2, p.rows_log), c.pw);
 
-  // B-side staging: word-major global lines -> row-major shared rows, one chunk ahead in registers
-  uint32_t pre[kStagePerThread];
-  auto load_stage = [&](int j) {
-#pragma unroll
-    for (int i = 0; i < kStagePerThread; i++) {
-      const int e = tid + i * kDpThreads;
-      if (e < kStageWords) pre[i] = __ldg(rec + (size_t)(e >> 5) * Hp + j * kChunk + (e & 31));
+  int jcur = 0;  // chunk this warp currently draws units from (warp-uniform, only grows)
+  while (true) {
+    // ---- draw the next unit: chunk-major, lowest tile first ----
+    int idx = 0;
+    if (lane == 0) {
+      while (jcur < nt) {
+        idx = atomicAdd(&cnt_out[jcur], 1);
+        if (jcur + idx < nt) break;
+        jcur++;
+      }
     }
-  };
-  auto store_stage = [&](int buf) {
-    uint32_t *dst = brec + buf * kChunk * kBStride;
-#pragma unroll
-    for (int i = 0; i < kStagePerThread; i++) {
-      const int e = tid + i * kDpThreads;
-      if (e < kStageWords) dst[(e & 31) * kBStride + (e >> 5)] = pre[i];
-    }
-  };
-  load_stage(0);
-
-  for (int j = 0; j < nchunks; j++) {
-    store_stage(j & 1);
-    __syncthreads();
-    if (j + 1 < nchunks) load_stage(j + 1);
-    const uint32_t *bchunk = brec + (j & 1) * kChunk * kBStride;
+    jcur = __shfl_sync(full_mask, jcur, 0);
+    idx = __shfl_sync(full_mask, idx, 0);
+    if (jcur >= nt) break;
+    const int j = jcur, t = j + idx;
+    if (idx == 0 && lane == 0) produce(j + kPrefetch);  // the first unit of a chunk keeps the ring filled
+    __syncwarp();
+    const int slot = j % kStages;
+    const unsigned parity = (unsigned)(j / kStages) & 1u;
+    mbar_wait(&bar_full[slot], parity);
+    const uint32_t *bchunk = ring + (size_t)slot * kSlotWords;
     const int vb0 = j * kChunk;
     const int nsteps = min(kChunk, H - vb0);
     // steps with vB <= vhor are on the ground side (predecessor row vB-1 below the horizon)
     const int kg = max(0, min(nsteps, vhor + 1 - vb0));
+    float *qs_slot = qs + (size_t)slot * kChunk * kDynWords;
+
+    // minima of this tile over the earlier chunks: written by the warp that did (t, j-1).  A counter,
+    // not an mbarrier: units (t, j-2), (t, j-1), (t, j) can be in flight at once, and a parity wait
+    // must not run more than one phase ahead.
+    if (j > 0) {
+      while (*reinterpret_cast<volatile int *>(tile_done + t) < j) __nanosleep(32);
+      __threadfence_block();
+    }
 
     if constexpr (PAIRWISE) {
-      // ---- diagonal unit: warp 0 runs the wavefront and publishes Q[vb0 + 1 ..] ----
-      if (warp == 0) {
-        float *qs = extra;
+      if (t == j) {
+        // ================= diagonal unit: the wavefront =================
+        float *sst_j = sst + (j & 1) * kSstWords, *base_j = base_s + (j & 1) * kBaseWords;
         const int vT = vb0 + lane;
         const bool row_ok = vT < H;
         const int vTc = row_ok ? vT : H - 1;
-        uint32_t A[kRecWords];
+        // stage the static transition records of vB = vb0 .. vb0 + 32
+        for (int i = lane; i < (kChunk + 1) * kStatWords; i += 32) {
+          const int vB = vb0 + i / kStatWords;
+          sst_j[i] = vB < H ? __ldg(S + (size_t)vb0 * kStatWords + i) : 0.0f;
+        }
+        {
+          // ---- pass 1: chain-independent part of the 32 x 32 cells ----
+          uint32_t A[kRecWords];
 #pragma unroll
-        for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
-        const float a_disp = f_(A[kRecDisp]), a_valid = f_(A[kRecValid]);
-        const char *pa = lutb + 4 * vTc;
-        // start from the minima over the earlier chunks (lower vB: they keep winning ties)
-        const float4 prev = best[vb0 + lane];
-        float best_gs = prev.x, best_o = prev.y;
-        int vb_gs = __float_as_int(prev.z), vb_o = __float_as_int(prev.w);
-        if (j > 0 && lane < kDynWords) qs[lane] = qs[kChunk * kDynWords + lane];  // Q[vb0] from the previous diagonal
+          for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
+          const char *pa = lutb + 4 * vTc;
+          auto park = [&](int k, const CellBase &b) {
+            float *d = base_j + k * 32 + lane;
+            d[0 * kChunk * 32] = b.seg_gs; d[1 * kChunk * 32] = b.data_gs; d[2 * kChunk * 32] = b.seg_o;
+            d[3 * kChunk * 32] = b.data_o; d[4 * kChunk * 32] = b.fn;
+          };
+          int k0 = 0;
+          if (j == 0) {
+            park(0, cell_base<true, true, HAS_INVALID>(A, bchunk, pa, lutb, (float)(vTc + 1), c));
+            k0 = 1;
+          }
+#pragma unroll 2
+          for (int k = k0; k < max(k0, kg); k++)
+            park(k, cell_base<false, true, HAS_INVALID>(A, bchunk + k * kRecBWords, pa, lutb + 4 * (vb0 + k - 1),
+                                                        (float)max(vTc + 1 - vb0 - k, 1), c));
+#pragma unroll 2
+          for (int k = max(k0, kg); k < nsteps; k++)
+            park(k, cell_base<false, false, HAS_INVALID>(A, bchunk + k * kRecBWords, pa, lutb + 4 * (vb0 + k - 1),
+                                                         (float)max(vTc + 1 - vb0 - k, 1), c));
+        }
+        // Q[vb0] was left in qnext by the previous diagonal (pass 1 above overlapped its pass 2)
+        if (j > 0) mbar_wait(&bar_q[(j - 1) % kStages], (unsigned)((j - 1) / kStages) & 1u);
+        if (j > 0 && lane < kDynWords) qs_slot[lane] = qnext[(j & 1) * kDynWords + lane];
         __syncwarp();
+        // ---- pass 2: row by row ----
+        const float4 prev = best_s[vb0 + lane];  // minima over the earlier chunks (lower vB keeps winning ties)
+        Best best{prev.x, prev.y, __float_as_int(prev.z), __float_as_int(prev.w)};
+        auto finish_row = [&](int vB, int src_lane) {
+          // row vB-1 (lane src_lane) is final: previous_mean of its best object segment (:674-685)
+          const float c_gs = __shfl_sync(full_mask, best.gs, src_lane), c_o = __shfl_sync(full_mask, best.o, src_lane);
+          const int o_vb = __shfl_sync(full_mask, best.vb_o, src_lane);
+          const bool ground_side = vB - 1 < vhor;
+          const float pm = segment_mean(dps[vB], dps[o_vb], vps[vB], vps[o_vb], vB - o_vb, HAS_INVALID);
+          RowPriors rp;
+          return make_row_info(sst_j + (vB - vb0) * kStatWords, ground_side, ground_side ? c_gs : inf, c_o,
+                               ground_side ? inf : c_gs, pm, odr, p, &rp);
+        };
         for (int k = 0; k < nsteps; k++) {
           const int vB = vb0 + k;
-          const int n = max(vTc + 1 - vB, 1);
           RowInfo q{};
           if (k > 0) {
-            // row vB-1 (lane k-1) is final
-            const float c_gs = __shfl_sync(full, best_gs, k - 1), c_o = __shfl_sync(full, best_o, k - 1);
-            const int o_vb = __shfl_sync(full, vb_o, k - 1);
-            const float hi_d = __shfl_sync(full, a_disp, k - 1), hi_v = __shfl_sync(full, a_valid, k - 1);
-            q = finish_row(rec, Hp, S, vB, vhor, c_gs, c_o, o_vb, hi_d, hi_v, object_disparity_range, p,
-                           c.has_invalid);
+            q = finish_row(vB, k - 1);
             if (lane == 0) {
-              store_row_info(qs + k * kDynWords, q);
+              store_row_info(qs_slot + k * kDynWords, q);
               pm_col[vB] = q.pm;
             }
           } else if (vB > 0) {
-            q = load_row_info(qs);
+            q = load_row_info(qs_slot);
+          }
+          CellBase b;
+          {
+            const float *d = base_j + k * 32 + lane;
+            b.seg_gs = d[0 * kChunk * 32]; b.data_gs = d[1 * kChunk * 32]; b.seg_o = d[2 * kChunk * 32];
+            b.data_o = d[3 * kChunk * 32]; b.fn = d[4 * kChunk * 32];
           }
           float cost_gs, cost_o;
-          const uint32_t *brow = bchunk + k * kBStride;
           if (vB == 0) {
             const float first_k_o = fmul(fadd(fadd((vT <= vhor) ? kLn2 : 0.0f, p.rows_log), p.max_dis_log), c.pw);
-            dp_cell<true, true, true, HAS_INVALID>(A, brow, pa, lutb, (float)n, 0.0f, q, first_k_gs, first_k_o, c,
-                                                   cost_gs, cost_o);
+            cell_finish<true, true, true>(b, 0.0f, q, first_k_gs, first_k_o, c, cost_gs, cost_o);
           } else if (k < kg) {
-            dp_cell<true, false, true, HAS_INVALID>(A, brow, pa, lutb + 4 * (vB - 1), (float)n, 0.0f, q, 0.0f,
-                                                    0.0f, c, cost_gs, cost_o);
+            cell_finish<true, false, true>(b, 0.0f, q, 0.0f, 0.0f, c, cost_gs, cost_o);
           } else {
-            dp_cell<true, false, false, HAS_INVALID>(A, brow, pa, lutb + 4 * (vB - 1), (float)n, 0.0f, q, 0.0f,
-                                                     0.0f, c, cost_gs, cost_o);
+            cell_finish<true, false, false>(b, 0.0f, q, 0.0f, 0.0f, c, cost_gs, cost_o);
           }
           const bool live = row_ok && lane >= k;
-          if (live && cost_gs < best_gs) { best_gs = cost_gs; vb_gs = vB; }
-          if (live && cost_o < best_o) { best_o = cost_o; vb_o = vB; }
+          if (live && cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = vB; }
+          if (live && cost_o < best.o) { best.o = cost_o; best.vb_o = vB; }
         }
-        // Q[vb0 + 32] for the next chunk (row vb0 + 31 is final now)
+        // Q[vb0 + 32] for the next diagonal (row vb0 + 31 is final now)
         if (vb0 + kChunk < H) {
-          const int vB = vb0 + kChunk;
-          const float c_gs = __shfl_sync(full, best_gs, 31), c_o = __shfl_sync(full, best_o, 31);
-          const int o_vb = __shfl_sync(full, vb_o, 31);
-          const float hi_d = __shfl_sync(full, a_disp, 31), hi_v = __shfl_sync(full, a_valid, 31);
-          const RowInfo q = finish_row(rec, Hp, S, vB, vhor, c_gs, c_o, o_vb, hi_d, hi_v, object_disparity_range, p,
-                                       c.has_invalid);
+          const RowInfo q = finish_row(vb0 + kChunk, 31);
           if (lane == 0) {
-            store_row_info(qs + kChunk * kDynWords, q);
-            pm_col[vB] = q.pm;
+            store_row_info(qnext + ((j + 1) & 1) * kDynWords, q);
+            pm_col[vb0 + kChunk] = q.pm;
           }
         }
         // the diagonal unit is the last one of its tile: the rows are final
-        best[vb0 + lane] = make_float4(best_gs, best_o, __int_as_float(vb_gs), __int_as_float(vb_o));
+        if (row_ok) out[vT] = make_float4(best.gs, best.o, __int_as_float(best.vb_gs), __int_as_float(best.vb_o));
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bar_q[slot]);
+          atomicAdd(&cnt_fin[j], 1);
+        }
+        continue;
       }
-      __syncthreads();
+      mbar_wait(&bar_q[slot], parity);
     }
 
-    // ---- units of this chunk: tiles t >= j (pairwise: t > j), round-robin over the warps ----
-    for (int t = j + (PAIRWISE ? 1 : 0) + warp; t < nchunks; t += kDpWarps) {
+    {
       const int vT = t * kChunk + lane;
       const bool row_ok = vT < H;
       const int vTc = row_ok ? vT : H - 1;
@@ -348,50 +503,53 @@ dp_kernel(const uint32_t *__restrict__ records, const float *__restrict__ object
 #pragma unroll
       for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
       const char *pa = lutb + 4 * vTc;
-      const float4 prev = best[t * kChunk + lane];
-      float best_gs = prev.x, best_o = prev.y;
-      int vb_gs = __float_as_int(prev.z), vb_o = __float_as_int(prev.w);
+      const float4 prev = best_s[t * kChunk + lane];
+      Best best{prev.x, prev.y, __float_as_int(prev.z), __float_as_int(prev.w)};
       const int n0 = vTc + 1 - vb0;
       int k0 = 0;
       if (j == 0) {
         // first segment, vB = 0 (:481-594)
-        float cost_gs, cost_o;
+        const CellBase b = cell_base<true, true, HAS_INVALID>(A, bchunk, pa, lutb, (float)n0, c);
         RowInfo q{};
         const float first_k_o =
             PAIRWISE ? fmul(fadd(fadd((vT <= vhor) ? kLn2 : 0.0f, p.rows_log), p.max_dis_log), c.pw) : 0.0f;
-        dp_cell<PAIRWISE, true, true, HAS_INVALID>(A, bchunk, pa, lutb, (float)n0, PAIRWISE ? 0.0f : extra[n0], q,
-                                                   first_k_gs, first_k_o, c, cost_gs, cost_o);
-        if (cost_gs < best_gs) { best_gs = cost_gs; vb_gs = 0; }
-        if (cost_o < best_o) { best_o = cost_o; vb_o = 0; }
+        float cost_gs, cost_o;
+        cell_finish<PAIRWISE, true, true>(b, PAIRWISE ? 0.0f : ihs[n0], q, first_k_gs, first_k_o, c, cost_gs, cost_o);
+        if (cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = 0; }
+        if (cost_o < best.o) { best.o = cost_o; best.vb_o = 0; }
         k0 = 1;
       }
-      if (!PAIRWISE && t == j) {  // unary only: the diagonal unit needs the vT >= vB predicate
-        dp_steps<PAIRWISE, true, true, HAS_INVALID>(A, bchunk, lutb, pa, extra, extra, vb0, k0, max(k0, kg), n0, lane,
-                                                    c, best_gs, best_o, vb_gs, vb_o);
-        dp_steps<PAIRWISE, false, true, HAS_INVALID>(A, bchunk, lutb, pa, extra, extra, vb0, max(k0, kg), nsteps, n0,
-                                                     lane, c, best_gs, best_o, vb_gs, vb_o);
+      if (!PAIRWISE && t == j) {
+        // unary diagonal unit: vT >= vB predicate; afterwards the rows are final
+        dp_steps<PAIRWISE, true, true, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, k0, max(k0, kg), n0, lane,
+                                                    c, best);
+        dp_steps<PAIRWISE, false, true, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0,
+                                                     lane, c, best);
+        if (row_ok) out[vT] = make_float4(best.gs, best.o, __int_as_float(best.vb_gs), __int_as_float(best.vb_o));
       } else {
-        dp_steps<PAIRWISE, true, false, HAS_INVALID>(A, bchunk, lutb, pa, extra, extra, vb0, k0, max(k0, kg), n0, lane,
-                                                     c, best_gs, best_o, vb_gs, vb_o);
-        dp_steps<PAIRWISE, false, false, HAS_INVALID>(A, bchunk, lutb, pa, extra, extra, vb0, max(k0, kg), nsteps, n0,
-                                                      lane, c, best_gs, best_o, vb_gs, vb_o);
+        dp_steps<PAIRWISE, true, false, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, k0, max(k0, kg), n0,
+                                                     lane, c, best);
+        dp_steps<PAIRWISE, false, false, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0,
+                                                      lane, c, best);
+        best_s[t * kChunk + lane] =
+            make_float4(best.gs, best.o, __int_as_float(best.vb_gs), __int_as_float(best.vb_o));
       }
-      best[t * kChunk + lane] = make_float4(best_gs, best_o, __int_as_float(vb_gs), __int_as_float(vb_o));
+    }
+    // hand the tile's minima to the next chunk's unit; the chunk's slot has one reader less
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      if (t > j) *reinterpret_cast<volatile int *>(tile_done + t) = j + 1;
+      atomicAdd(&cnt_fin[j], 1);
     }
   }
-  __syncthreads();
-  float4 *out = dp_out + (size_t)gcol * H;
-  for (int i = tid; i < H; i += kDpThreads) out[i] = best[i];
-}
-
-size_t dp_smem_bytes(const KParams &p, bool pairwise) {
-  const int nchunks = (p.rows + kChunk - 1) / kChunk;
-  size_t b = (size_t)2 * kChunk * kBStride * 4 + (size_t)kChunk * nchunks * sizeof(float4);
-  b += pairwise ? (size_t)kQsRows * kDynWords * 4 : (size_t)(p.rows + 1) * 4;
-  return (b + 15) & ~(size_t)15;
 }
 
 }  // namespace
+
+size_t dp_smem_bytes(const KParams &p, bool pairwise) {
+  return DpLayout(p.rows, p.rec_stride, p.max_dis, pairwise).total;
+}
 
 template <bool PAIRWISE, bool HAS_INVALID>
 static void launch_dp_variant(const KParams &p, const BatchBuffers &b, int ncolumns, size_t smem, cudaStream_t s) {
@@ -400,8 +558,9 @@ static void launch_dp_variant(const KParams &p, const BatchBuffers &b, int ncolu
     cudaFuncSetAttribute(dp_kernel<PAIRWISE, HAS_INVALID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  dp_kernel<PAIRWISE, HAS_INVALID><<<ncolumns, kDpThreads, smem, s>>>(
-      b.records, b.object_lut, b.stat, b.pm, b.vhor, b.object_disparity_range, b.inverse_height, b.dp, p);
+  dp_kernel<PAIRWISE, HAS_INVALID><<<ncolumns, kDpThreads, smem, s>>>(b.records, b.records_b, b.object_lut, b.stat,
+                                                                      b.pm, b.vhor, b.object_disparity_range,
+                                                                      b.inverse_height, b.dp, p);
 }
 
 void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s) {

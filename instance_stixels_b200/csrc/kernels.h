@@ -20,6 +20,7 @@ struct BatchBuffers {
   // intermediates
   float *joined = nullptr;             // [B][C][H]
   uint32_t *records = nullptr;         // [B][C][kRecWords][rec_stride], word-major (common.cuh)
+  uint32_t *records_b = nullptr;       // [B][C][rec_stride][kRecBWords], row-major copy (common.cuh)
   float *object_lut = nullptr;         // [B][C][D][lut_stride]
   float *pm = nullptr;                 // [B][C][H] previous_mean of row vB-1 (pairwise; backtracking re-derives priors)
   float4 *dp = nullptr;                // [B][C][H]: {cost_gs, cost_obj, as_float(vB_gs), as_float(vB_obj)}

@@ -186,7 +186,8 @@ struct TabSmem {
 __global__ void __launch_bounds__(kTabThreads)
 column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict__ segmentation,
                      const float *__restrict__ ground, const int *__restrict__ vhor_arr,
-                     uint32_t *__restrict__ records, int *__restrict__ error_flag, KParams p) {
+                     uint32_t *__restrict__ records, uint32_t *__restrict__ records_b,
+                     int *__restrict__ error_flag, KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = p.rows, C = p.realcols;
   const int col = blockIdx.x, f = blockIdx.y;
@@ -275,35 +276,41 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   for (int c = warp; c < 21; c += kTabThreads / 32) exact_prefix_warp<int>(seg_s + c * segld, nq, seg_ps + c * segld);
   __syncthreads();
 
-  // ---- records[word][v], v in [0, H]: word-major, coalesced over v (layout: common.cuh) ----
+  // ---- records, v in [0, H], in both layouts (common.cuh): word-major for the A side of the DP
+  //      (coalesced over v) and row-major 128-byte rows for the bulk-copied B side ----
   uint32_t *rec_col = records + ((size_t)f * C + col) * (size_t)kRecWords * p.rec_stride;
+  uint4 *recb_col = reinterpret_cast<uint4 *>(records_b + ((size_t)f * C + col) * (size_t)p.rec_stride * kRecBWords);
   bool out_of_range = false;
   for (int v = tid; v <= H; v += kTabThreads) {
     const int q = v >> 3, r = v & 7;
-    uint32_t *dst = rec_col + v;
+    uint32_t w[kRecBWords];
 #pragma unroll
     for (int c = 0; c < 19; c++)  // P_c(v) = 8*ps[q] + seg[q]*r  (Cityscapes.h:28-42)
-      dst[(size_t)(kRecSeg + c) * p.rec_stride] =
-          (uint32_t)(seg_ps[c * segld + q] * kDownsample + seg_s[c * segld + q] * r);
-    dst[(size_t)kRecOff * p.rec_stride] =
-        (uint32_t)((seg_ps[19 * segld + q] + seg_ps[20 * segld + q]) * kDownsample +
-                   (seg_s[19 * segld + q] + seg_s[20 * segld + q]) * r);
+      w[kRecSeg + c] = (uint32_t)(seg_ps[c * segld + q] * kDownsample + seg_s[c * segld + q] * r);
+    w[kRecOff] = (uint32_t)((seg_ps[19 * segld + q] + seg_ps[20 * segld + q]) * kDownsample +
+                            (seg_s[19 * segld + q] + seg_s[20 * segld + q]) * r);
     // instance-mean sums as exactly representable floats (see common.cuh)
     const long long smx = ps_i64[0 * L.Hp + v], smy = ps_i64[1 * L.Hp + v];
     const long long smx2 = ps_i64[2 * L.Hp + v], smy2 = ps_i64[3 * L.Hp + v];
     const long long lim1 = 1ll << 24, lim2 = 1ll << (24 + kSqSplitBits);
     out_of_range |= smx <= -lim1 || smx >= lim1 || smy <= -lim1 || smy >= lim1 || smx2 >= lim2 || smy2 >= lim2;
     const long long lomask = (1ll << kSqSplitBits) - 1;
-    dst[(size_t)kRecMx * p.rec_stride] = __float_as_uint((float)smx);
-    dst[(size_t)kRecMy * p.rec_stride] = __float_as_uint((float)smy);
-    dst[(size_t)kRecMx2Hi * p.rec_stride] = __float_as_uint((float)(smx2 & ~lomask));
-    dst[(size_t)kRecMx2Lo * p.rec_stride] = __float_as_uint((float)(smx2 & lomask));
-    dst[(size_t)kRecMy2Hi * p.rec_stride] = __float_as_uint((float)(smy2 & ~lomask));
-    dst[(size_t)kRecMy2Lo * p.rec_stride] = __float_as_uint((float)(smy2 & lomask));
-    dst[(size_t)kRecDisp * p.rec_stride] = __float_as_uint(ps_f[0][v]);
-    dst[(size_t)kRecValid * p.rec_stride] = __float_as_uint(ps_f[1][v]);
-    dst[(size_t)kRecGround * p.rec_stride] = __float_as_uint(ps_f[2][v]);
-    dst[(size_t)kRecSky * p.rec_stride] = __float_as_uint(ps_f[3][v]);
+    w[kRecMx] = __float_as_uint((float)smx);
+    w[kRecMy] = __float_as_uint((float)smy);
+    w[kRecMx2Hi] = __float_as_uint((float)(smx2 & ~lomask));
+    w[kRecMx2Lo] = __float_as_uint((float)(smx2 & lomask));
+    w[kRecMy2Hi] = __float_as_uint((float)(smy2 & ~lomask));
+    w[kRecMy2Lo] = __float_as_uint((float)(smy2 & lomask));
+    w[kRecDisp] = __float_as_uint(ps_f[0][v]);
+    w[kRecValid] = __float_as_uint(ps_f[1][v]);
+    w[kRecGround] = __float_as_uint(ps_f[2][v]);
+    w[kRecSky] = __float_as_uint(ps_f[3][v]);
+    w[30] = w[31] = 0u;
+#pragma unroll
+    for (int k = 0; k < kRecWords; k++) rec_col[(size_t)k * p.rec_stride + v] = w[k];
+#pragma unroll
+    for (int k = 0; k < kRecBWords / 4; k++)
+      recb_col[(size_t)v * (kRecBWords / 4) + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
   }
   if (out_of_range) atomicOr(error_flag, kErrOffsetRange);
   (void)lane;
@@ -358,7 +365,7 @@ void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, 
     configured = smem;
   }
   column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.records,
-                                                        b.error_flag, p);
+                                                        b.records_b, b.error_flag, p);
   dim3 lgrid(p.realcols, (p.max_dis + kLutWarps - 1) / kLutWarps, nframes);
   object_lut_kernel<<<lgrid, kLutThreads, 0, s>>>(b.joined, b.obj_cost_lut, b.object_lut, p);
   g_launch_count += 2;
