@@ -180,14 +180,23 @@ class Stixels:
         C_, S = self.GetRealCols(), self.GetMaxSections()
         if sections_out is None:
             sections_out = np.zeros((n, C_, S), dtype=L.SECTION_DTYPE)
-        cap = 16384 * n
-        inst = np.zeros(cap if want_instances else 1, dtype=L.INSTANCE_DTYPE)
-        offs = np.zeros(n + 1, dtype=np.int32)
+        inst, offs, cap = self._instance_buffers(n) if want_instances else (None, None, 0)
         self._check(self._lib.isx_compute_batch_host(
             self._h, int(pairwise), n, disparity.ctypes.data, segmentation.ctypes.data, _roads(roads),
             sections_out.ctypes.data, inst.ctypes.data if want_instances else None,
-            cap if want_instances else 0, offs.ctypes.data if want_instances else None))
-        return sections_out, inst[:offs[n]], offs
+            cap, offs.ctypes.data if want_instances else None))
+        if not want_instances:
+            return sections_out, np.zeros(0, dtype=L.INSTANCE_DTYPE), np.zeros(n + 1, dtype=np.int32)
+        return sections_out, inst[:offs[n]].copy(), offs.copy()
+
+    def _instance_buffers(self, n: int):
+        """Reusable result buffers for the packed instance records of a batch of n frames."""
+        cap = 16384 * n
+        cached = getattr(self, "_inst_cache", None)
+        if cached is None or cached[2] != cap:
+            cached = (np.empty(cap, dtype=L.INSTANCE_DTYPE), np.zeros(n + 1, dtype=np.int32), cap)
+            self._inst_cache = cached
+        return cached
 
     def ComputeBatchDevice(self, pairwise: bool, n: int, d_disparity: int, d_segmentation: int,
                            roads: Sequence[dict]):
@@ -201,13 +210,13 @@ class Stixels:
     def FetchBatchResults(self, n: int, want_instances: bool = True):
         C_, S = self.GetRealCols(), self.GetMaxSections()
         sections = np.zeros((n, C_, S), dtype=L.SECTION_DTYPE)
-        cap = 16384 * n
-        inst = np.zeros(cap if want_instances else 1, dtype=L.INSTANCE_DTYPE)
-        offs = np.zeros(n + 1, dtype=np.int32)
+        inst, offs, cap = self._instance_buffers(n) if want_instances else (None, None, 0)
         self._check(self._lib.isx_fetch_batch_results(
             self._h, n, sections.ctypes.data, inst.ctypes.data if want_instances else None,
-            cap if want_instances else 0, offs.ctypes.data if want_instances else None))
-        return sections, inst[:offs[n]], offs
+            cap, offs.ctypes.data if want_instances else None))
+        if not want_instances:
+            return sections, np.zeros(0, dtype=L.INSTANCE_DTYPE), np.zeros(n + 1, dtype=np.int32)
+        return sections, inst[:offs[n]].copy(), offs.copy()
 
     STAGES = ("join", "frame_tables", "column_tables", "dp", "backtrack", "grouping")
 

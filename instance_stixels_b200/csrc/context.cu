@@ -48,7 +48,8 @@ struct isx_context {
   int max_batch = 0, chunk = 0;
   std::string last_error;
 
-  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaStream_t s_compute = nullptr, s_emit = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_dp_done[2] = {nullptr, nullptr}, ev_emit_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
   cudaEvent_t ev_chunk_done = nullptr;
 
@@ -59,6 +60,17 @@ struct isx_context {
   float *d_single_disp = nullptr;                 // SetDisparityImage target (d_disparity_big)
   int32_t *d_single_seg = nullptr;                // SetSegmentation target
   isx::BatchBuffers buf;                          // intermediates sized `chunk`, results sized `max_batch`
+  // Buffers the emission stream still reads while the compute stream works on the next chunk exist
+  // twice; chunk k uses set k & 1.
+  struct ChunkSet {
+    float *ground = nullptr;
+    int *vhor = nullptr;
+    float *stat = nullptr;
+    uint32_t *records = nullptr, *records_b = nullptr;
+    float4 *dp = nullptr;
+    float *pm = nullptr;
+  } sets[2];
+  int last_set = 0;
   isx_section *d_sections_all = nullptr;          // [max_batch][C][200]
   int *d_nsections_all = nullptr;                 // [max_batch][C]
   isx_instance *d_inst_all = nullptr;             // [max_batch][inst_cap]
@@ -212,8 +224,12 @@ static const float *road_tables(isx_context *c, const isx_road &r) {
 }
 
 // Enqueue the kernel sequence for `n` frames whose inputs are at d_disp/d_seg.
-// `slot` selects the pinned ground-table staging half; results land at frame
-// offset `first` of the per-batch result arrays.
+// `slot` selects the pinned ground-table staging half and the ChunkSet; results
+// land at frame offset `first` of the per-batch result arrays.
+//
+// Two streams: join -> tables -> LUT -> DP on s_compute; backtracking, candidate
+// collection, grouping and packing (short, latency-bound launches) on s_emit, so
+// that they overlap the next chunk's DP.
 static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const float *d_disp,
                          const int32_t *d_seg, const isx_road *roads, int slot) {
   const KParams &kp = c->kp;
@@ -224,46 +240,62 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
     std::memcpy(hg + (size_t)i * 3 * H, road_tables(c, roads[i]), sizeof(float) * 3 * H);
     hv[i] = H - roads[i].vhor - 1;  // Stixels.cu:377
   }
-  cudaStream_t s = c->s_compute;
-  ISX_TRY(c, cudaMemcpyAsync(c->buf.ground, hg, sizeof(float) * 3 * H * n, cudaMemcpyHostToDevice, s));
-  ISX_TRY(c, cudaMemcpyAsync(c->buf.vhor, hv, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  const isx_context::ChunkSet &cs = c->sets[slot];
+  cudaStream_t s = c->s_compute, se = c->s_emit;
+  // the emission of the chunk that used this set two chunks ago must be done with it
+  ISX_TRY(c, cudaStreamWaitEvent(s, c->ev_emit_done[slot], 0));
+  ISX_TRY(c, cudaMemcpyAsync(cs.ground, hg, sizeof(float) * 3 * H * n, cudaMemcpyHostToDevice, s));
+  ISX_TRY(c, cudaMemcpyAsync(cs.vhor, hv, sizeof(int) * n, cudaMemcpyHostToDevice, s));
   BatchBuffers b = c->buf;
+  b.ground = cs.ground; b.vhor = cs.vhor; b.stat = cs.stat;
+  b.records = cs.records; b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
   b.disparity = d_disp;
   b.segmentation = d_seg;
   b.sections = c->d_sections_all + (size_t)first * C * kMaxSections;
   b.n_sections = c->d_nsections_all + (size_t)first * C;
-  // stage boundaries: 0 join | 1 frame tables | 2 column tables | 3 dp | 4 backtrack+collect | 5 grouping+pack
-  auto mark = [&](int i) {
+  // profiling events per chunk: 0 join | 1 frame tables | 2 column tables + LUT | 3 dp | 4 dp end (s_compute);
+  //                             5 backtrack + collect | 6 grouping + pack | 7 end (s_emit)
+  auto mark = [&](cudaStream_t st) {
     if (!c->profiling) return;
     if (c->prof_used >= c->prof_events.size()) {
       cudaEvent_t e;
       cudaEventCreate(&e);
       c->prof_events.push_back(e);
     }
-    cudaEventRecord(c->prof_events[c->prof_used++], s);
-    (void)i;
+    cudaEventRecord(c->prof_events[c->prof_used++], st);
   };
-  mark(0);
+  mark(s);
   launch_join_columns(kp, b, n, s);
-  mark(1);
+  mark(s);
   if (pairwise) launch_frame_tables(kp, b, n, s);
-  mark(2);
+  mark(s);
   launch_column_tables(kp, b, n, s);
-  mark(3);
+  mark(s);
   launch_dp(kp, b, n, pairwise, s);
-  mark(4);
-  launch_emit(kp, b, n, pairwise, s);
-  mark(5);
-  launch_grouping(kp, b, n, s);
-  pack_instances_kernel<<<n, 256, 0, s>>>(b.cand_count, b.cand_idx, b.cand_label,
-                                          c->d_inst_all + (size_t)first * c->inst_cap,
-                                          c->d_inst_count_all + first, c->inst_cap, kp);
+  mark(s);
+  ISX_TRY(c, cudaEventRecord(c->ev_dp_done[slot], s));
+  ISX_TRY(c, cudaStreamWaitEvent(se, c->ev_dp_done[slot], 0));
+  mark(se);
+  launch_emit(kp, b, n, pairwise, se);
+  mark(se);
+  launch_grouping(kp, b, n, se);
+  pack_instances_kernel<<<n, 256, 0, se>>>(b.cand_count, b.cand_idx, b.cand_label,
+                                           c->d_inst_all + (size_t)first * c->inst_cap,
+                                           c->d_inst_count_all + first, c->inst_cap, kp);
   g_launch_count++;
-  mark(6);
+  mark(se);
+  ISX_TRY(c, cudaEventRecord(c->ev_emit_done[slot], se));
   ISX_TRY(c, cudaGetLastError());
   c->last_chunk_first = first;
   c->last_chunk_n = n;
   c->last_pairwise = pairwise;
+  c->last_set = slot;
+  return ISX_OK;
+}
+
+// Results of every enqueued chunk become visible to work ordered after this on s_compute.
+static int join_emit_stream(isx_context *c) {
+  ISX_TRY(c, cudaStreamWaitEvent(c->s_compute, c->ev_emit_done[c->last_set], 0));
   return ISX_OK;
 }
 
@@ -419,7 +451,8 @@ int isx_initialize(isx_handle h, int max_batch) {
   const size_t H = kp.rows, W = kp.cols, C = kp.realcols, D = kp.max_dis;
   if (C == 0) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no stixel columns");
   h->max_batch = max_batch;
-  int chunk = 64;  // frames per launch: >= 5 waves of one-warp-per-column DP work on 148 SMs
+  int chunk = 16;  // frames per launch: 4096 column CTAs = 14 waves of the DP on 148 SMs x 2 CTAs; small enough
+                   // for the copies of one chunk to hide behind the kernels of its neighbours
   if (const char *e = std::getenv("ISX_CHUNK")) chunk = std::atoi(e) > 0 ? std::atoi(e) : chunk;
   h->chunk = chunk < max_batch ? chunk : max_batch;
   const size_t ch = h->chunk, MB = max_batch;
@@ -427,11 +460,19 @@ int isx_initialize(isx_handle h, int max_batch) {
   h->inst_cap = (int)(cap * kInstanceClasses < 16384 ? cap * kInstanceClasses : 16384);
 
   ISX_TRY(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+  {
+    // the emission stream's short kernels should not queue behind the DP's thousands of CTAs
+    int prio_lo = 0, prio_hi = 0;
+    ISX_TRY(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    ISX_TRY(h, cudaStreamCreateWithPriority(&h->s_emit, cudaStreamNonBlocking, prio_hi));
+  }
   ISX_TRY(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
   ISX_TRY(h, cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) {
     ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_in_ready[i], cudaEventDisableTiming));
     ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_in_free[i], cudaEventDisableTiming));
+    ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_dp_done[i], cudaEventDisableTiming));
+    ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_emit_done[i], cudaEventDisableTiming));
   }
   ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_chunk_done, cudaEventDisableTiming));
 
@@ -442,17 +483,21 @@ int isx_initialize(isx_handle h, int max_batch) {
   }
   ISX_TRY(h, dev_alloc(h, &h->d_single_disp, H * W));
   ISX_TRY(h, dev_alloc(h, &h->d_single_seg, seg_elems(h)));
-  ISX_TRY(h, dev_alloc(h, &b.ground, ch * 3 * H));
-  ISX_TRY(h, dev_alloc(h, &b.vhor, ch));
-  ISX_TRY(h, dev_alloc(h, &b.stat, ch * H * kStatWords));
   ISX_TRY(h, dev_alloc(h, &b.joined, ch * C * H));
-  ISX_TRY(h, dev_alloc(h, &b.records, ch * C * kRecWords * (size_t)kp.rec_stride));
-  ISX_TRY(h, cudaMemset(b.records, 0, ch * C * kRecWords * (size_t)kp.rec_stride * sizeof(uint32_t)));
-  ISX_TRY(h, dev_alloc(h, &b.records_b, ch * C * kRecBWords * (size_t)kp.rec_stride));
-  ISX_TRY(h, cudaMemset(b.records_b, 0, ch * C * kRecBWords * (size_t)kp.rec_stride * sizeof(uint32_t)));
+  for (int i = 0; i < 2; i++) {
+    isx_context::ChunkSet &cs = h->sets[i];
+    ISX_TRY(h, dev_alloc(h, &cs.ground, ch * 3 * H));
+    ISX_TRY(h, dev_alloc(h, &cs.vhor, ch));
+    ISX_TRY(h, dev_alloc(h, &cs.stat, ch * H * kStatWords));
+    ISX_TRY(h, dev_alloc(h, &cs.records, ch * C * kRecWords * (size_t)kp.rec_stride));
+    ISX_TRY(h, cudaMemset(cs.records, 0, ch * C * kRecWords * (size_t)kp.rec_stride * sizeof(uint32_t)));
+    ISX_TRY(h, dev_alloc(h, &cs.records_b, ch * C * kRecBWords * (size_t)kp.rec_stride));
+    ISX_TRY(h, cudaMemset(cs.records_b, 0, ch * C * kRecBWords * (size_t)kp.rec_stride * sizeof(uint32_t)));
+    ISX_TRY(h, dev_alloc(h, &cs.pm, ch * C * H));
+    ISX_TRY(h, cudaMemset(cs.pm, 0, ch * C * H * sizeof(float)));
+    ISX_TRY(h, dev_alloc(h, &cs.dp, ch * C * H));
+  }
   ISX_TRY(h, dev_alloc(h, &b.object_lut, ch * C * D * (size_t)kp.lut_stride));
-  ISX_TRY(h, dev_alloc(h, &b.pm, ch * C * H));
-  ISX_TRY(h, dev_alloc(h, &b.dp, ch * C * H));
   ISX_TRY(h, dev_alloc(h, &b.cand_count, ch * kInstanceClasses));
   ISX_TRY(h, dev_alloc(h, &b.cand_offset, ch * (C + 1) * kInstanceClasses));
   ISX_TRY(h, dev_alloc(h, &b.cand_xy, ch * kInstanceClasses * cap));
@@ -462,7 +507,6 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &b.cand_scratch, ch * kInstanceClasses * cap));
   ISX_TRY(h, dev_alloc(h, &b.error_flag, 1));
   ISX_TRY(h, cudaMemset(b.error_flag, 0, sizeof(int)));
-  ISX_TRY(h, cudaMemset(b.pm, 0, ch * C * H * sizeof(float)));
   ISX_TRY(h, dev_alloc(h, &h->d_sections_all, MB * C * kMaxSections));
   // entries after a column's terminator are never written: start them from zero
   ISX_TRY(h, cudaMemset(h->d_sections_all, 0, MB * C * kMaxSections * sizeof(isx_section)));
@@ -509,9 +553,12 @@ int isx_finish(isx_handle h) {
   for (int i = 0; i < 2; i++) {
     cudaEventDestroy(h->ev_in_ready[i]);
     cudaEventDestroy(h->ev_in_free[i]);
+    cudaEventDestroy(h->ev_dp_done[i]);
+    cudaEventDestroy(h->ev_emit_done[i]);
   }
   cudaEventDestroy(h->ev_chunk_done);
   cudaStreamDestroy(h->s_compute);
+  cudaStreamDestroy(h->s_emit);
   cudaStreamDestroy(h->s_h2d);
   cudaStreamDestroy(h->s_d2h);
   h->buf = BatchBuffers();
@@ -557,10 +604,19 @@ static int fetch_results(isx_handle h, int n, isx_section *sections, isx_instanc
                                cudaMemcpyDeviceToHost, s));
   ISX_TRY(h, cudaMemcpyAsync(h->h_inst_count, h->d_inst_count_all, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
   ISX_TRY(h, cudaMemcpyAsync(h->h_error, h->buf.error_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-  if (instances || instance_offsets)
-    ISX_TRY(h, cudaMemcpyAsync(h->h_inst, h->d_inst_all, sizeof(isx_instance) * n * (size_t)h->inst_cap,
-                               cudaMemcpyDeviceToHost, s));
   ISX_TRY(h, cudaStreamSynchronize(s));
+  if (instances || instance_offsets) {
+    // only the used part of every frame's [inst_cap] record array travels
+    int most = 0;
+    for (int f = 0; f < n; f++) most = h->h_inst_count[f] > most ? h->h_inst_count[f] : most;
+    most = most < h->inst_cap ? most : h->inst_cap;
+    if (most > 0) {
+      const size_t pitch = sizeof(isx_instance) * (size_t)h->inst_cap;
+      ISX_TRY(h, cudaMemcpy2DAsync(h->h_inst, pitch, h->d_inst_all, pitch, sizeof(isx_instance) * (size_t)most, n,
+                                   cudaMemcpyDeviceToHost, s));
+      ISX_TRY(h, cudaStreamSynchronize(s));
+    }
+  }
   if (*h->h_error & kErrOffsetRange)
     return fail(h, ISX_ERR_UNSUPPORTED,
                 "instance offsets out of range: |sum of instance means| of a column must stay below 2^24");
@@ -590,6 +646,7 @@ int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_met
   if (!h->single_has_road) return fail(h, ISX_ERR_INVALID_ARGUMENT, "SetRoadParameters has not been called");
   const int32_t *seg = d_segmentation_local ? d_segmentation_local : h->d_single_seg;
   if (int rc = enqueue_chunk(h, pairwise != 0, 0, 1, h->d_single_disp, seg, &h->single_road, 0)) return rc;
+  if (int rc = join_emit_stream(h)) return rc;
   h->last_batch = 1;
   h->last_roads.assign(1, h->single_road);
   if (int rc = fetch_results(h, 1, sections, nullptr, 0, nullptr, h->s_compute)) return rc;
@@ -630,6 +687,7 @@ int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_d
     ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_compute));
     slot ^= 1;
   }
+  if (int rc = join_emit_stream(h)) return rc;
   h->last_batch = n;
   h->last_roads.assign(roads, roads + n);
   return ISX_OK;
@@ -657,8 +715,11 @@ int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *dispa
   const size_t hw = (size_t)h->kp.rows * h->kp.cols, se = seg_elems(h);
   const size_t C = h->kp.realcols;
   int slot = 0;
-  for (int first = 0; first < n; first += h->chunk) {
-    const int cn = (n - first) < h->chunk ? (n - first) : h->chunk;
+  int cn = 0;
+  for (int first = 0; first < n; first += cn) {
+    cn = (n - first) < h->chunk ? (n - first) : h->chunk;
+    // a short first chunk: its copy is the only one that no kernel hides
+    if (first == 0 && n > h->chunk && h->chunk >= 8) cn = h->chunk / 4;
     // H2D of this chunk on the copy stream, once the kernels that last read this slot are done
     ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_in_free[slot], 0));
     ISX_TRY(h, cudaMemcpyAsync(h->d_in_disp[slot], disparity + first * hw, sizeof(float) * hw * cn,
@@ -674,13 +735,14 @@ int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *dispa
     ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_compute));
     // D2H of this chunk's sections overlaps the next chunk's kernels
     if (sections) {
-      ISX_TRY(h, cudaStreamWaitEvent(h->s_d2h, h->ev_in_free[slot], 0));
+      ISX_TRY(h, cudaStreamWaitEvent(h->s_d2h, h->ev_emit_done[slot], 0));
       ISX_TRY(h, cudaMemcpyAsync(sections + (size_t)first * C * kMaxSections,
                                  h->d_sections_all + (size_t)first * C * kMaxSections,
                                  sizeof(isx_section) * cn * C * kMaxSections, cudaMemcpyDeviceToHost, h->s_d2h));
     }
     slot ^= 1;
   }
+  if (int rc = join_emit_stream(h)) return rc;
   h->last_batch = n;
   h->last_roads.assign(roads, roads + n);
   if (int rc = fetch_results(h, n, nullptr, instances, instances_capacity, instance_offsets, h->s_compute)) return rc;
@@ -719,7 +781,12 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
   ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
   const KParams &kp = h->kp;
   const size_t H = kp.rows, C = kp.realcols, D = kp.max_dis;
-  const BatchBuffers &b = h->buf;
+  BatchBuffers b = h->buf;
+  {
+    const isx_context::ChunkSet &cs = h->sets[h->last_set];
+    b.ground = cs.ground; b.vhor = cs.vhor; b.stat = cs.stat;
+    b.records = cs.records; b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
+  }
   if (tensor == ISX_T_GROUND_TABLES) {
     ISX_TRY(h, cudaMemcpy(host, b.ground + (size_t)local * 3 * H, need, cudaMemcpyDeviceToHost));
   } else if (tensor == ISX_T_OBJ_COST_LUT) {
@@ -761,11 +828,14 @@ int isx_set_profiling(isx_handle h, int enable) {
 int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, int reset) {
   if (int rc = check_ready(h)) return rc;
   ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
-  const int per = 7;
+  ISX_TRY(h, cudaStreamSynchronize(h->s_emit));
+  // 8 events per chunk (enqueue_chunk): stage i < 4 = events i..i+1 on s_compute, stages 4, 5 = events 5..7 on s_emit
+  const int per = 8;
   for (size_t base = 0; base + per <= h->prof_used; base += per) {
     for (int i = 0; i < 6; i++) {
+      const int e0 = i < 4 ? i : i + 1;
       float t = 0.f;
-      if (cudaEventElapsedTime(&t, h->prof_events[base + i], h->prof_events[base + i + 1]) == cudaSuccess) {
+      if (cudaEventElapsedTime(&t, h->prof_events[base + e0], h->prof_events[base + e0 + 1]) == cudaSuccess) {
         h->stage_ms[i] += t;
         h->stage_launches[i]++;
       }
