@@ -43,15 +43,14 @@ unsigned long long g_launch_count = 0;
 
 namespace {
 
-constexpr int kDpWarps = 8;
+constexpr int kDpWarps = 4;
 constexpr int kDpThreads = kDpWarps * 32;
 constexpr int kChunk = 32;
-constexpr int kStages = 6;     // ring slots of 4 KB
-constexpr int kPrefetch = 3;   // chunks the producer runs ahead (< kStages)
+constexpr int kStages = 4;     // ring slots of 4 KB
+constexpr int kPrefetch = 2;   // chunks the producer runs ahead (< kStages)
 constexpr int kSlotWords = kChunk * kRecBWords;
 constexpr int kSlotBytes = kSlotWords * 4;
 constexpr int kSstWords = ((kChunk + 1) * kStatWords + 3) & ~3;  // staged static transition records of a chunk
-constexpr int kBaseWords = 5 * kChunk * 32;                      // parked CellBase of a diagonal unit
 
 struct DpConsts {
   float pw, dw, sw, iw;
@@ -100,9 +99,12 @@ struct CellBase {
 
 //   A : R[vT+1] in registers,  brow: R[vB] in shared memory (warp-uniform address)
 //   nf: segment height as float;  pa / pb: biased byte addresses of LUT[0][vT] / LUT[0][vB-1]
-template <bool FIRST, bool GROUND, bool HAS_INVALID>
+// GROUND: 1 = ground side, 0 = sky side, 2 = decided at run time by `ground_rt` (diagonal units)
+template <bool FIRST, int GROUND, bool HAS_INVALID>
 __device__ __forceinline__ CellBase cell_base(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ brow,
-                                              const char *pa, const char *pb, float nf, const DpConsts &c) {
+                                              const char *pa, const char *pb, float nf, const DpConsts &c,
+                                              bool ground_rt = true) {
+  const bool ground = GROUND == 2 ? ground_rt : GROUND == 1;
   uint32_t Bw[32];
   {
     const uint4 *b4 = reinterpret_cast<const uint4 *>(brow);
@@ -121,7 +123,7 @@ __device__ __forceinline__ CellBase cell_base(const uint32_t (&A)[kRecWords], co
 #pragma unroll
   for (int k = 12; k < 19; k++) s_in = min(s_in, (int)(A[k] - Bw[k]));
   const int s_off = (int)(A[kRecOff] - Bw[kRecOff]);
-  const int s_gs = GROUND ? min((int)(A[0] - Bw[0]), (int)(A[1] - Bw[1])) : (int)(A[kSkyClass] - Bw[kSkyClass]);
+  const int s_gs = ground ? min((int)(A[0] - Bw[0]), (int)(A[1] - Bw[1])) : (int)(A[kSkyClass] - Bw[kSkyClass]);
   const float f_off = (float)s_off;
   const float nic = fmul(f_off, c.iw);  // ComputeNonInstanceOffsetCost * weight (:618-621)
 
@@ -158,14 +160,16 @@ __device__ __forceinline__ CellBase cell_base(const uint32_t (&A)[kRecWords], co
   const float lut_hi = __ldg(reinterpret_cast<const float *>(pa + roff));
   const float lut_lo = FIRST ? 0.0f : __ldg(reinterpret_cast<const float *>(pb + roff));
   b.data_o = fsub(lut_hi, lut_lo);
-  b.data_gs = GROUND ? fsub(f_(A[kRecGround]), f_(Bw[kRecGround])) : fsub(f_(A[kRecSky]), f_(Bw[kRecSky]));
+  b.data_gs = ground ? fsub(f_(A[kRecGround]), f_(Bw[kRecGround])) : fsub(f_(A[kRecSky]), f_(Bw[kRecSky]));
   return b;
 }
 
 // Prior + combine (:548-560, 575-584, 700-720, 740-766, 788-824).
-template <bool PAIRWISE, bool FIRST, bool GROUND>
+template <bool PAIRWISE, bool FIRST, int GROUND>
 __device__ __forceinline__ void cell_finish(const CellBase &b, float ih, const RowInfo &q, float first_k_gs,
-                                            float first_k_o, const DpConsts &c, float &cost_gs, float &cost_o) {
+                                            float first_k_o, const DpConsts &c, float &cost_gs, float &cost_o,
+                                            bool ground_rt = true) {
+  const bool ground = GROUND == 2 ? ground_rt : GROUND == 1;
   if constexpr (PAIRWISE) {
     float k_gs, k_o;
     if constexpr (FIRST) {
@@ -173,7 +177,7 @@ __device__ __forceinline__ void cell_finish(const CellBase &b, float ih, const R
       k_o = first_k_o;
     } else {
       float p1, p2, p3;
-      object_priors(q, GROUND, b.fn, c.epsilon, p1, p2, p3);
+      object_priors(q, ground, b.fn, c.epsilon, p1, p2, p3);
       k_gs = q.gs_k;
       k_o = fmul(fmin_(p3, fmin_(p1, p2)), c.pw);
     }
@@ -226,9 +230,9 @@ __device__ __forceinline__ void dp_steps(const uint32_t (&A)[kRecWords], const u
     if constexpr (PAIRWISE) q = load_row_info(qs + k * kDynWords);
     else ih = DIAG ? ihs[max(n0 - k, 1)] : *ihp;
     const CellBase b =
-        cell_base<false, GROUND, HAS_INVALID>(A, bchunk + k * kRecBWords, pa, lutb + 4 * (vB - 1), nfc, c);
+        cell_base<false, GROUND ? 1 : 0, HAS_INVALID>(A, bchunk + k * kRecBWords, pa, lutb + 4 * (vB - 1), nfc, c);
     float cost_gs, cost_o;
-    cell_finish<PAIRWISE, false, GROUND>(b, ih, q, 0.0f, 0.0f, c, cost_gs, cost_o);
+    cell_finish<PAIRWISE, false, GROUND ? 1 : 0>(b, ih, q, 0.0f, 0.0f, c, cost_gs, cost_o);
     const bool live = !DIAG || lane >= k;
     if (live && cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = vB; }
     if (live && cost_o < best.o) { best.o = cost_o; best.vb_o = vB; }
@@ -237,40 +241,45 @@ __device__ __forceinline__ void dp_steps(const uint32_t (&A)[kRecWords], const u
   }
 }
 
-// Shared-memory carve-up (bytes).
+// Shared-memory carve-up (bytes).  Kept small on purpose: shared memory and L1 share one 228 KB array,
+// and the object-LUT gathers of four resident column CTAs live in what is left.
 struct DpLayout {
   int nt;
-  size_t off_ring, off_bars, off_cnt, off_best, off_ih, off_qs, off_qnext, off_sst, off_dps, off_vps, off_odr, off_base, total;
-  __host__ __device__ DpLayout(int H, int Hp, int D, bool pairwise) {
+  size_t off_ring, off_bars, off_cnt, off_ih, off_qs, off_qnext, off_sst, off_odr, total;
+  __host__ __device__ DpLayout(int H, int D, bool pairwise) {
     nt = (H + kChunk - 1) / kChunk;
     size_t o = 0;
     off_ring = o; o += (size_t)kStages * kSlotBytes;
     off_bars = o; o += (size_t)2 * kStages * 8;            // full[kStages] | qfull[kStages]
     off_cnt = o; o += (size_t)3 * nt * 4;                  // per chunk: units handed out | finished; per tile: chunks done
     o = (o + 15) & ~(size_t)15;
-    off_best = o; o += (size_t)nt * kChunk * 16;
-    off_ih = off_qs = off_qnext = off_sst = off_dps = off_vps = off_odr = off_base = o;
+    off_ih = off_qs = off_qnext = off_sst = off_odr = o;
     if (!pairwise) {
       off_ih = o; o += (size_t)(H + 1) * 4;
     } else {
       off_qs = o; o += (size_t)kStages * kChunk * kDynWords * 4;
       off_qnext = o; o += (size_t)2 * kDynWords * 4;
-      off_sst = o; o += (size_t)2 * kSstWords * 4;           // double-buffered: consecutive diagonals overlap
-      off_dps = o; o += (size_t)Hp * 4;
-      off_vps = o; o += (size_t)Hp * 4;
+      off_sst = o; o += (size_t)kDpWarps * kSstWords * 4;    // one per warp: up to kDpWarps diagonals are staged at once
       off_odr = o; o += (size_t)((D + 3) & ~3) * 4;
-      off_base = o; o += (size_t)2 * kBaseWords * 4;         // double-buffered like sst
     }
     total = (o + 15) & ~(size_t)15;
   }
 };
 
+__device__ __forceinline__ Best load_best(const float4 *p) {
+  const float4 v = __ldcg(p);  // L2: written by another warp of this CTA (st.cg + fence + flag)
+  return Best{v.x, v.y, __float_as_int(v.z), __float_as_int(v.w)};
+}
+__device__ __forceinline__ void store_best(float4 *p, const Best &b) {
+  __stcg(p, make_float4(b.gs, b.o, __int_as_float(b.vb_gs), __int_as_float(b.vb_o)));
+}
+
 template <bool PAIRWISE, bool HAS_INVALID>
-__global__ void __launch_bounds__(kDpThreads, 2)
+__global__ void __launch_bounds__(kDpThreads, 4)
 dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
           const float *__restrict__ object_lut, const float *__restrict__ stat, float *__restrict__ pm_out,
           const int *__restrict__ vhor_arr, const float *__restrict__ object_disparity_range,
-          const float *__restrict__ inverse_height, float4 *__restrict__ dp_out, KParams p) {
+          const float *__restrict__ inverse_height, float4 *dp_out, KParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned full_mask = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -279,7 +288,7 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
   const int f = gcol / C;
   const int vhor = vhor_arr[f];
   const float inf = inf_f();
-  const DpLayout L(H, Hp, p.max_dis, PAIRWISE);
+  const DpLayout L(H, p.max_dis, PAIRWISE);
   const int nt = L.nt;
 
   uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + L.off_ring);
@@ -288,15 +297,11 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
   int *cnt_out = reinterpret_cast<int *>(smem_raw + L.off_cnt);  // [nt] units handed out, per chunk
   int *cnt_fin = cnt_out + nt;                                    // [nt] units finished, per chunk
   int *tile_done = cnt_fin + nt;                                  // [nt] chunks finished, per tile
-  float4 *best_s = reinterpret_cast<float4 *>(smem_raw + L.off_best);
   float *ihs = reinterpret_cast<float *>(smem_raw + L.off_ih);
   float *qs = reinterpret_cast<float *>(smem_raw + L.off_qs);
   float *qnext = reinterpret_cast<float *>(smem_raw + L.off_qnext);
   float *sst = reinterpret_cast<float *>(smem_raw + L.off_sst);
-  float *dps = reinterpret_cast<float *>(smem_raw + L.off_dps);
-  float *vps = reinterpret_cast<float *>(smem_raw + L.off_vps);
   float *odr = reinterpret_cast<float *>(smem_raw + L.off_odr);
-  float *base_s = reinterpret_cast<float *>(smem_raw + L.off_base);
 
   DpConsts c;
   c.pw = p.prior_weight; c.dw = p.disparity_weight; c.sw = p.segmentation_weight; c.iw = p.instance_weight;
@@ -313,6 +318,8 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
   asm volatile("" : "+l"(lutb));
   const float *S = stat + (size_t)f * H * kStatWords;
   float *pm_col = pm_out + (size_t)gcol * H;
+  // The running (cost, vB) minima of a row live in the output array itself between the units of its
+  // tile (L2-resident; one 16-byte load and store per lane and unit).
   float4 *out = dp_out + (size_t)gcol * H;
 
   // ---- one-time setup ----
@@ -323,15 +330,10 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < nt * kChunk; i += kDpThreads) best_s[i] = make_float4(inf, inf, 0.0f, 0.0f);
   for (int i = tid; i < 3 * nt; i += kDpThreads) cnt_out[i] = 0;
   if constexpr (!PAIRWISE) {
     for (int i = tid; i <= H; i += kDpThreads) ihs[i] = __ldg(inverse_height + i);
   } else {
-    for (int i = tid; i <= H; i += kDpThreads) {
-      dps[i] = f_(__ldg(rec + (size_t)kRecDisp * Hp + i));
-      vps[i] = f_(__ldg(rec + (size_t)kRecValid * Hp + i));
-    }
     for (int i = tid; i < p.max_dis; i += kDpThreads) odr[i] = __ldg(object_disparity_range + i);
   }
   __syncthreads();
@@ -374,81 +376,85 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
     __syncwarp();
     const int slot = j % kStages;
     const unsigned parity = (unsigned)(j / kStages) & 1u;
-    mbar_wait(&bar_full[slot], parity);
-    const uint32_t *bchunk = ring + (size_t)slot * kSlotWords;
     const int vb0 = j * kChunk;
     const int nsteps = min(kChunk, H - vb0);
     // steps with vB <= vhor are on the ground side (predecessor row vB-1 below the horizon)
     const int kg = max(0, min(nsteps, vhor + 1 - vb0));
+    const uint32_t *bchunk = ring + (size_t)slot * kSlotWords;
     float *qs_slot = qs + (size_t)slot * kChunk * kDynWords;
+    const int vT = t * kChunk + lane;
+    const bool row_ok = vT < H;
+    const int vTc = row_ok ? vT : H - 1;
 
+    // A side of the unit (independent of every wait below)
+    uint32_t A[kRecWords];
+#pragma unroll
+    for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
+    const char *pa = lutb + 4 * vTc;
+
+    if constexpr (PAIRWISE) {
+      if (t == j) {
+        // stage the static transition records of vB = vb0 .. vb0 + 32 for the wavefront
+        float *sst_j = sst + (j % kDpWarps) * kSstWords;
+        for (int i = lane; i < (kChunk + 1) * kStatWords; i += 32)
+          sst_j[i] = (vb0 + i / kStatWords) < H ? __ldg(S + (size_t)vb0 * kStatWords + i) : 0.0f;
+      }
+    }
+
+    mbar_wait(&bar_full[slot], parity);
     // minima of this tile over the earlier chunks: written by the warp that did (t, j-1).  A counter,
     // not an mbarrier: units (t, j-2), (t, j-1), (t, j) can be in flight at once, and a parity wait
     // must not run more than one phase ahead.
+    Best best{inf, inf, 0, 0};
     if (j > 0) {
       while (*reinterpret_cast<volatile int *>(tile_done + t) < j) __nanosleep(32);
       __threadfence_block();
+      best = load_best(out + vTc);
     }
 
     if constexpr (PAIRWISE) {
       if (t == j) {
         // ================= diagonal unit: the wavefront =================
-        float *sst_j = sst + (j & 1) * kSstWords, *base_j = base_s + (j & 1) * kBaseWords;
-        const int vT = vb0 + lane;
-        const bool row_ok = vT < H;
-        const int vTc = row_ok ? vT : H - 1;
-        // stage the static transition records of vB = vb0 .. vb0 + 32
-        for (int i = lane; i < (kChunk + 1) * kStatWords; i += 32) {
-          const int vB = vb0 + i / kStatWords;
-          sst_j[i] = vB < H ? __ldg(S + (size_t)vb0 * kStatWords + i) : 0.0f;
+        // One pass, software-pipelined: the chain-independent part of step k+1 (cell_base) is issued
+        // before the chain of step k (row vB-1 final -> Q[vB] -> cell -> row vB) so that it fills the
+        // chain's latency.
+        const float *sst_j = sst + (j % kDpWarps) * kSstWords;
+        // prefix values at the start row of the best object segment so far (previous_mean needs them)
+        float lo_d = f_(__ldg(rec + (size_t)kRecDisp * Hp + best.vb_o));
+        float lo_v = f_(__ldg(rec + (size_t)kRecValid * Hp + best.vb_o));
+        // Q[vb0] comes from the previous diagonal
+        if (j > 0) {
+          mbar_wait(&bar_q[(j - 1) % kStages], (unsigned)((j - 1) / kStages) & 1u);
+          if (lane < kDynWords) qs_slot[lane] = qnext[(j & 1) * kDynWords + lane];
+          __syncwarp();
         }
-        {
-          // ---- pass 1: chain-independent part of the 32 x 32 cells ----
-          uint32_t A[kRecWords];
-#pragma unroll
-          for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
-          const char *pa = lutb + 4 * vTc;
-          auto park = [&](int k, const CellBase &b) {
-            float *d = base_j + k * 32 + lane;
-            d[0 * kChunk * 32] = b.seg_gs; d[1 * kChunk * 32] = b.data_gs; d[2 * kChunk * 32] = b.seg_o;
-            d[3 * kChunk * 32] = b.data_o; d[4 * kChunk * 32] = b.fn;
-          };
-          int k0 = 0;
-          if (j == 0) {
-            park(0, cell_base<true, true, HAS_INVALID>(A, bchunk, pa, lutb, (float)(vTc + 1), c));
-            k0 = 1;
-          }
-#pragma unroll 2
-          for (int k = k0; k < max(k0, kg); k++)
-            park(k, cell_base<false, true, HAS_INVALID>(A, bchunk + k * kRecBWords, pa, lutb + 4 * (vb0 + k - 1),
-                                                        (float)max(vTc + 1 - vb0 - k, 1), c));
-#pragma unroll 2
-          for (int k = max(k0, kg); k < nsteps; k++)
-            park(k, cell_base<false, false, HAS_INVALID>(A, bchunk + k * kRecBWords, pa, lutb + 4 * (vb0 + k - 1),
-                                                         (float)max(vTc + 1 - vb0 - k, 1), c));
-        }
-        // Q[vb0] was left in qnext by the previous diagonal (pass 1 above overlapped its pass 2)
-        if (j > 0) mbar_wait(&bar_q[(j - 1) % kStages], (unsigned)((j - 1) / kStages) & 1u);
-        if (j > 0 && lane < kDynWords) qs_slot[lane] = qnext[(j & 1) * kDynWords + lane];
-        __syncwarp();
-        // ---- pass 2: row by row ----
-        const float4 prev = best_s[vb0 + lane];  // minima over the earlier chunks (lower vB keeps winning ties)
-        Best best{prev.x, prev.y, __float_as_int(prev.z), __float_as_int(prev.w)};
-        auto finish_row = [&](int vB, int src_lane) {
+        auto finish_row = [&](int vB, int src_lane, float hi_d, float hi_v) {
           // row vB-1 (lane src_lane) is final: previous_mean of its best object segment (:674-685)
           const float c_gs = __shfl_sync(full_mask, best.gs, src_lane), c_o = __shfl_sync(full_mask, best.o, src_lane);
           const int o_vb = __shfl_sync(full_mask, best.vb_o, src_lane);
+          const float l_d = __shfl_sync(full_mask, lo_d, src_lane), l_v = __shfl_sync(full_mask, lo_v, src_lane);
           const bool ground_side = vB - 1 < vhor;
-          const float pm = segment_mean(dps[vB], dps[o_vb], vps[vB], vps[o_vb], vB - o_vb, HAS_INVALID);
+          const float pm = segment_mean(hi_d, l_d, hi_v, l_v, vB - o_vb, HAS_INVALID);
           RowPriors rp;
           return make_row_info(sst_j + (vB - vb0) * kStatWords, ground_side, ground_side ? c_gs : inf, c_o,
                                ground_side ? inf : c_gs, pm, odr, p, &rp);
         };
+        auto base_of = [&](int k) {
+          const int vB = vb0 + k;
+          return cell_base<false, 2, HAS_INVALID>(A, bchunk + k * kRecBWords, pa, lutb + 4 * (vB - 1),
+                                                  (float)max(vTc + 1 - vB, 1), c, k < kg);
+        };
+        CellBase b_cur = (j == 0) ? cell_base<true, 1, HAS_INVALID>(A, bchunk, pa, lutb, (float)(vTc + 1), c)
+                                  : base_of(0);
         for (int k = 0; k < nsteps; k++) {
           const int vB = vb0 + k;
+          // prefix sums at row vB: "hi" of the finished row vB-1 and "lo" of segments starting at vB
+          const float ps_d = f_(bchunk[k * kRecBWords + kRecDisp]), ps_v = f_(bchunk[k * kRecBWords + kRecValid]);
+          CellBase b_next = b_cur;
+          if (k + 1 < nsteps) b_next = base_of(k + 1);
           RowInfo q{};
           if (k > 0) {
-            q = finish_row(vB, k - 1);
+            q = finish_row(vB, k - 1, ps_d, ps_v);
             if (lane == 0) {
               store_row_info(qs_slot + k * kDynWords, q);
               pm_col[vB] = q.pm;
@@ -456,35 +462,30 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
           } else if (vB > 0) {
             q = load_row_info(qs_slot);
           }
-          CellBase b;
-          {
-            const float *d = base_j + k * 32 + lane;
-            b.seg_gs = d[0 * kChunk * 32]; b.data_gs = d[1 * kChunk * 32]; b.seg_o = d[2 * kChunk * 32];
-            b.data_o = d[3 * kChunk * 32]; b.fn = d[4 * kChunk * 32];
-          }
           float cost_gs, cost_o;
           if (vB == 0) {
             const float first_k_o = fmul(fadd(fadd((vT <= vhor) ? kLn2 : 0.0f, p.rows_log), p.max_dis_log), c.pw);
-            cell_finish<true, true, true>(b, 0.0f, q, first_k_gs, first_k_o, c, cost_gs, cost_o);
-          } else if (k < kg) {
-            cell_finish<true, false, true>(b, 0.0f, q, 0.0f, 0.0f, c, cost_gs, cost_o);
+            cell_finish<true, true, 1>(b_cur, 0.0f, q, first_k_gs, first_k_o, c, cost_gs, cost_o);
           } else {
-            cell_finish<true, false, false>(b, 0.0f, q, 0.0f, 0.0f, c, cost_gs, cost_o);
+            cell_finish<true, false, 2>(b_cur, 0.0f, q, 0.0f, 0.0f, c, cost_gs, cost_o, k < kg);
           }
           const bool live = row_ok && lane >= k;
           if (live && cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = vB; }
-          if (live && cost_o < best.o) { best.o = cost_o; best.vb_o = vB; }
+          if (live && cost_o < best.o) { best.o = cost_o; best.vb_o = vB; lo_d = ps_d; lo_v = ps_v; }
+          b_cur = b_next;
         }
         // Q[vb0 + 32] for the next diagonal (row vb0 + 31 is final now)
         if (vb0 + kChunk < H) {
-          const RowInfo q = finish_row(vb0 + kChunk, 31);
+          const int vB = vb0 + kChunk;
+          const RowInfo q = finish_row(vB, 31, f_(__ldg(rec + (size_t)kRecDisp * Hp + vB)),
+                                       f_(__ldg(rec + (size_t)kRecValid * Hp + vB)));
           if (lane == 0) {
             store_row_info(qnext + ((j + 1) & 1) * kDynWords, q);
-            pm_col[vb0 + kChunk] = q.pm;
+            pm_col[vB] = q.pm;
           }
         }
         // the diagonal unit is the last one of its tile: the rows are final
-        if (row_ok) out[vT] = make_float4(best.gs, best.o, __int_as_float(best.vb_gs), __int_as_float(best.vb_o));
+        if (row_ok) store_best(out + vT, best);
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&bar_q[slot]);
@@ -496,25 +497,16 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
     }
 
     {
-      const int vT = t * kChunk + lane;
-      const bool row_ok = vT < H;
-      const int vTc = row_ok ? vT : H - 1;
-      uint32_t A[kRecWords];
-#pragma unroll
-      for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
-      const char *pa = lutb + 4 * vTc;
-      const float4 prev = best_s[t * kChunk + lane];
-      Best best{prev.x, prev.y, __float_as_int(prev.z), __float_as_int(prev.w)};
       const int n0 = vTc + 1 - vb0;
       int k0 = 0;
       if (j == 0) {
         // first segment, vB = 0 (:481-594)
-        const CellBase b = cell_base<true, true, HAS_INVALID>(A, bchunk, pa, lutb, (float)n0, c);
+        const CellBase b = cell_base<true, 1, HAS_INVALID>(A, bchunk, pa, lutb, (float)n0, c);
         RowInfo q{};
         const float first_k_o =
             PAIRWISE ? fmul(fadd(fadd((vT <= vhor) ? kLn2 : 0.0f, p.rows_log), p.max_dis_log), c.pw) : 0.0f;
         float cost_gs, cost_o;
-        cell_finish<PAIRWISE, true, true>(b, PAIRWISE ? 0.0f : ihs[n0], q, first_k_gs, first_k_o, c, cost_gs, cost_o);
+        cell_finish<PAIRWISE, true, 1>(b, PAIRWISE ? 0.0f : ihs[n0], q, first_k_gs, first_k_o, c, cost_gs, cost_o);
         if (cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = 0; }
         if (cost_o < best.o) { best.o = cost_o; best.vb_o = 0; }
         k0 = 1;
@@ -525,15 +517,13 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
                                                     c, best);
         dp_steps<PAIRWISE, false, true, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0,
                                                      lane, c, best);
-        if (row_ok) out[vT] = make_float4(best.gs, best.o, __int_as_float(best.vb_gs), __int_as_float(best.vb_o));
       } else {
         dp_steps<PAIRWISE, true, false, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, k0, max(k0, kg), n0,
                                                      lane, c, best);
         dp_steps<PAIRWISE, false, false, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0,
                                                       lane, c, best);
-        best_s[t * kChunk + lane] =
-            make_float4(best.gs, best.o, __int_as_float(best.vb_gs), __int_as_float(best.vb_o));
       }
+      if (row_ok) store_best(out + vT, best);
     }
     // hand the tile's minima to the next chunk's unit; the chunk's slot has one reader less
     __syncwarp();
@@ -548,7 +538,7 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
 }  // namespace
 
 size_t dp_smem_bytes(const KParams &p, bool pairwise) {
-  return DpLayout(p.rows, p.rec_stride, p.max_dis, pairwise).total;
+  return DpLayout(p.rows, p.max_dis, pairwise).total;
 }
 
 template <bool PAIRWISE, bool HAS_INVALID>
