@@ -90,6 +90,7 @@ struct KParams {
   // derived strides
   int rec_stride;    // entries per (column, word) row of the records: H + 1 rounded up to 32
   int lut_stride;    // floats per fn row of the object LUT (>= H, multiple of 32)
+  int lut_cols;      // column slots of the object-LUT buffer (chunk * C), see lut_column_address
 };
 
 // ---- pinned float ops (all .ftz through -ftz=true) ----
@@ -120,6 +121,25 @@ __device__ __forceinline__ float neg_log_div(float a, float b) {
 __device__ __forceinline__ float clamp_neg(float x) { return (x < 0.0f) ? 0.0f : x; }
 
 __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
+
+// ---- placement of the per-column object LUTs ----
+// The DP forms LUT addresses with 32-bit arithmetic (one IMAD per gather, dp.cu), so the LUT of a
+// column (col_bytes < 4 GB) must not straddle a multiple of 4 GB.  Column g normally sits at
+// base + g * col_bytes; a column that would straddle the m-th 4 GB boundary inside the buffer moves
+// to a spare slot behind the regular area (two slots per boundary, one of which cannot straddle).
+__host__ __device__ inline size_t lut_buffer_bytes(size_t ncols, size_t col_bytes) {
+  const size_t boundaries = ((ncols + 2) * col_bytes >> 32) + 2;
+  return (ncols + 2 * boundaries) * col_bytes;
+}
+__host__ __device__ inline unsigned long long lut_column_address(unsigned long long base, size_t gcol, size_t ncols,
+                                                                 size_t col_bytes) {
+  const unsigned long long a = base + gcol * col_bytes;
+  if (((a ^ (a + col_bytes - 1)) >> 32) == 0) return a;
+  const unsigned long long m = ((a + col_bytes - 1) >> 32) - (base >> 32) - 1;
+  unsigned long long sp = base + (ncols + 2 * m) * col_bytes;
+  if (((sp ^ (sp + col_bytes - 1)) >> 32) != 0) sp += col_bytes;
+  return sp;
+}
 
 }  // namespace isx
 

@@ -455,6 +455,7 @@ int isx_initialize(isx_handle h, int max_batch) {
                    // for the copies of one chunk to hide behind the kernels of its neighbours
   if (const char *e = std::getenv("ISX_CHUNK")) chunk = std::atoi(e) > 0 ? std::atoi(e) : chunk;
   h->chunk = chunk < max_batch ? chunk : max_batch;
+  h->kp.lut_cols = h->chunk * (int)C;
   const size_t ch = h->chunk, MB = max_batch;
   const size_t cap = C * kMaxSections;
   h->inst_cap = (int)(cap * kInstanceClasses < 16384 ? cap * kInstanceClasses : 16384);
@@ -497,7 +498,7 @@ int isx_initialize(isx_handle h, int max_batch) {
     ISX_TRY(h, cudaMemset(cs.pm, 0, ch * C * H * sizeof(float)));
     ISX_TRY(h, dev_alloc(h, &cs.dp, ch * C * H));
   }
-  ISX_TRY(h, dev_alloc(h, &b.object_lut, ch * C * D * (size_t)kp.lut_stride));
+  ISX_TRY(h, dev_alloc(h, &b.object_lut, lut_buffer_bytes(ch * C, D * (size_t)kp.lut_stride * 4) / 4));
   ISX_TRY(h, dev_alloc(h, &b.cand_count, ch * kInstanceClasses));
   ISX_TRY(h, dev_alloc(h, &b.cand_offset, ch * (C + 1) * kInstanceClasses));
   ISX_TRY(h, dev_alloc(h, &b.cand_xy, ch * kInstanceClasses * cap));
@@ -799,8 +800,12 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
     // device rows hold LUT[fn][1..H]; the reference layout has a leading 0 (StixelsKernels.cu:283-285)
     float *dst = static_cast<float *>(host);
     for (size_t r = 0; r < C * D; r++) dst[r * (H + 1)] = 0.0f;
-    ISX_TRY(h, cudaMemcpy2D(dst + 1, (H + 1) * 4, b.object_lut + (size_t)local * C * D * kp.lut_stride,
-                            (size_t)kp.lut_stride * 4, H * 4, C * D, cudaMemcpyDeviceToHost));
+    for (size_t col = 0; col < C; col++) {
+      const void *src = reinterpret_cast<const void *>(lut_column_address(
+          (unsigned long long)b.object_lut, (size_t)local * C + col, kp.lut_cols, D * (size_t)kp.lut_stride * 4));
+      ISX_TRY(h, cudaMemcpy2D(dst + 1 + col * D * (H + 1), (H + 1) * 4, src, (size_t)kp.lut_stride * 4, H * 4, D,
+                              cudaMemcpyDeviceToHost));
+    }
   } else if (tensor >= ISX_T_DISPARITY_PS && tensor <= ISX_T_SKY_PS) {
     const int word = tensor == ISX_T_DISPARITY_PS ? kRecDisp
                      : tensor == ISX_T_VALID_PS   ? kRecValid

@@ -56,8 +56,20 @@ struct DpConsts {
   float pw, dw, sw, iw;
   float dm1f;            // max_dis - 1 as float (LUT row clamp)
   unsigned lut_stride4;  // bytes per fn row of the object LUT
+  unsigned lut_hi;       // upper 32 address bits of this column's LUT (it never straddles 4 GB, common.cuh)
   float epsilon;
 };
+
+// LUT gather with a 32-bit computed low address word: {lo, hi} + OFF.  The immediate is added by
+// the load unit in 64 bits, so it may carry; lo itself is exact modulo 2^32 inside the column.
+template <int OFF>
+__device__ __forceinline__ float ldg_lut(unsigned lo, unsigned hi) {
+  float r;
+  asm("{\n\t.reg .b64 a;\n\tmov.b64 a, {%1, %2};\n\tld.global.nc.f32 %0, [a+%3];\n\t}"
+      : "=f"(r)
+      : "r"(lo), "r"(hi), "n"(OFF));
+  return r;
+}
 
 __device__ __forceinline__ float f_(uint32_t u) { return __uint_as_float(u); }
 
@@ -98,11 +110,12 @@ struct CellBase {
 };
 
 //   A : R[vT+1] in registers,  brow: R[vB] in shared memory (warp-uniform address)
-//   nf: segment height as float;  pa / pb: biased byte addresses of LUT[0][vT] / LUT[0][vB-1]
+//   nf: segment height as float;  ca / cb: biased low address words of LUT[0][vT] / LUT[0][vB-1]
+//   (cb + BOFF addresses row vB - 1; BOFF is the compile-time part of the unrolled step)
 // GROUND: 1 = ground side, 0 = sky side, 2 = decided at run time by `ground_rt` (diagonal units)
-template <bool FIRST, int GROUND, bool HAS_INVALID>
+template <bool FIRST, int GROUND, bool HAS_INVALID, int BOFF = 0>
 __device__ __forceinline__ CellBase cell_base(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ brow,
-                                              const char *pa, const char *pb, float nf, const DpConsts &c,
+                                              unsigned ca, unsigned cb, float nf, const DpConsts &c,
                                               bool ground_rt = true) {
   const bool ground = GROUND == 2 ? ground_rt : GROUND == 1;
   uint32_t Bw[32];
@@ -152,13 +165,13 @@ __device__ __forceinline__ CellBase cell_base(const uint32_t (&A)[kRecWords], co
     mean = fmul(sd, rn);
   }
   b.fn = fmaxf(mean, 0.0f);  // == clamp_neg for every comparison downstream (mean is never NaN)
-  // floor(fn) as LUT row: add.rz of 2^23 leaves floor(fn) in the mantissa; pa / pb are the byte
-  // addresses of LUT[0][vT] / LUT[0][vB-1] minus 0x4B000000 rows, so one 32x32+64 multiply-add
-  // (IMAD.WIDE.U32) forms each address.
+  // floor(fn) as LUT row: add.rz of 2^23 leaves floor(fn) in the mantissa; ca / cb are the low
+  // address words of LUT[0][vT] / LUT[0][vB-1] minus 0x4B000000 rows (mod 2^32), so one 32-bit
+  // multiply-add (IMAD) forms each address; the upper word is constant per column.
   const float fbias = __fadd_rz(fminf(b.fn, c.dm1f), 8388608.0f);
-  const unsigned long long roff = (unsigned long long)(unsigned)__float_as_int(fbias) * c.lut_stride4;
-  const float lut_hi = __ldg(reinterpret_cast<const float *>(pa + roff));
-  const float lut_lo = FIRST ? 0.0f : __ldg(reinterpret_cast<const float *>(pb + roff));
+  const unsigned roff = (unsigned)__float_as_int(fbias) * c.lut_stride4;
+  const float lut_hi = ldg_lut<0>(roff + ca, c.lut_hi);
+  const float lut_lo = FIRST ? 0.0f : ldg_lut<BOFF>(roff + cb, c.lut_hi);
   b.data_o = fsub(lut_hi, lut_lo);
   b.data_gs = ground ? fsub(f_(A[kRecGround]), f_(Bw[kRecGround])) : fsub(f_(A[kRecSky]), f_(Bw[kRecSky]));
   return b;
@@ -213,32 +226,51 @@ struct Best {
 
 // Steps [k0, k1) of one unit; the whole range lies on one side of the horizon.
 //   DIAG (unary only): tile == chunk, lane l is live for k <= l only (vT >= vB).
+// One step: U = position inside the manually unrolled pair (compile-time LUT / record offsets).
+template <bool PAIRWISE, bool GROUND, bool DIAG, bool HAS_INVALID, int U>
+__device__ __forceinline__ void dp_step(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ brow,
+                                        unsigned ca, unsigned cb, const float *__restrict__ ihs,
+                                        const float *__restrict__ ihp, int nk, const float *__restrict__ qrow,
+                                        int vB, int k, int lane, float nf, const DpConsts &c, Best &best) {
+  // dead lanes of the diagonal unit (vT < vB) evaluate a harmless dummy cell of height >= 1
+  const float nfc = DIAG ? fmaxf(nf, 1.0f) : nf;
+  RowInfo q{};
+  float ih = 0.0f;
+  if constexpr (PAIRWISE) q = load_row_info(qrow + U * kDynWords);
+  else ih = DIAG ? ihs[max(nk - U, 1)] : ihp[-U];  // ihp = ihs + nk, nk = vT + 1 - vB of step U = 0
+  const CellBase b = cell_base<false, GROUND ? 1 : 0, HAS_INVALID, 4 * U>(A, brow + U * kRecBWords, ca, cb, nfc, c);
+  float cost_gs, cost_o;
+  cell_finish<PAIRWISE, false, GROUND ? 1 : 0>(b, ih, q, 0.0f, 0.0f, c, cost_gs, cost_o);
+  const bool live = !DIAG || lane >= k;
+  if (live && cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = vB; }
+  if (live && cost_o < best.o) { best.o = cost_o; best.vb_o = vB; }
+}
+
 template <bool PAIRWISE, bool GROUND, bool DIAG, bool HAS_INVALID>
 __device__ __forceinline__ void dp_steps(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ bchunk,
-                                         const char *lutb, const char *pa, const float *__restrict__ ihs,
+                                         unsigned cb0, unsigned ca, const float *__restrict__ ihs,
                                          const float *__restrict__ qs, int vb0, int k0, int k1, int n0, int lane,
                                          const DpConsts &c, Best &best) {
-  RowInfo q{};
   float nf = (float)(n0 - k0);  // segment height vT + 1 - vB, kept as a float counter
   const float *ihp = ihs + (n0 - k0);
-#pragma unroll 2
-  for (int k = k0; k < k1; k++) {
-    const int vB = vb0 + k;
-    // dead lanes of the diagonal unit (vT < vB) evaluate a harmless dummy cell of height >= 1
-    const float nfc = DIAG ? fmaxf(nf, 1.0f) : nf;
-    float ih = 0.0f;
-    if constexpr (PAIRWISE) q = load_row_info(qs + k * kDynWords);
-    else ih = DIAG ? ihs[max(n0 - k, 1)] : *ihp;
-    const CellBase b =
-        cell_base<false, GROUND ? 1 : 0, HAS_INVALID>(A, bchunk + k * kRecBWords, pa, lutb + 4 * (vB - 1), nfc, c);
-    float cost_gs, cost_o;
-    cell_finish<PAIRWISE, false, GROUND ? 1 : 0>(b, ih, q, 0.0f, 0.0f, c, cost_gs, cost_o);
-    const bool live = !DIAG || lane >= k;
-    if (live && cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = vB; }
-    if (live && cost_o < best.o) { best.o = cost_o; best.vb_o = vB; }
-    nf = fadd(nf, -1.0f);
-    ihp--;
+  unsigned cb = cb0 + 4u * (unsigned)k0;
+  const uint32_t *brow = bchunk + k0 * kRecBWords;
+  const float *qrow = qs + k0 * kDynWords;
+  int k = k0;
+  for (; k + 1 < k1; k += 2) {
+    dp_step<PAIRWISE, GROUND, DIAG, HAS_INVALID, 0>(A, brow, ca, cb, ihs, ihp, n0 - k, qrow, vb0 + k, k, lane, nf, c,
+                                                    best);
+    dp_step<PAIRWISE, GROUND, DIAG, HAS_INVALID, 1>(A, brow, ca, cb, ihs, ihp, n0 - k, qrow, vb0 + k + 1, k + 1, lane,
+                                                    fadd(nf, -1.0f), c, best);
+    nf = fadd(nf, -2.0f);
+    ihp -= 2;
+    cb += 8u;
+    brow += 2 * kRecBWords;
+    qrow += 2 * kDynWords;
   }
+  if (k < k1)
+    dp_step<PAIRWISE, GROUND, DIAG, HAS_INVALID, 0>(A, brow, ca, cb, ihs, ihp, n0 - k, qrow, vb0 + k, k, lane, nf, c,
+                                                    best);
 }
 
 // Shared-memory carve-up (bytes).  Kept small on purpose: shared memory and L1 share one 228 KB array,
@@ -311,11 +343,12 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
 
   const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
   const uint32_t *recb = records_b + (size_t)gcol * Hp * kRecBWords;
-  const float *lut = object_lut + (size_t)gcol * p.max_dis * p.lut_stride;
-  // byte address of LUT[0][0] of this column minus the 2^23 bias rows (see cell_base); opaque to the
-  // compiler so that it stays one materialised 64-bit base
-  const char *lutb = reinterpret_cast<const char *>(lut) - (unsigned long long)0x4B000000u * c.lut_stride4;
-  asm volatile("" : "+l"(lutb));
+  // low / high address words of LUT[0][0] of this column; the low word carries the -2^23-rows bias of
+  // the float -> row trick in cell_base (all modulo 2^32)
+  const unsigned long long lut_addr = lut_column_address((unsigned long long)object_lut, (size_t)gcol, p.lut_cols,
+                                                         (size_t)p.max_dis * p.lut_stride * 4);
+  c.lut_hi = (unsigned)(lut_addr >> 32);
+  const unsigned lutb = (unsigned)lut_addr - 0x4B000000u * c.lut_stride4;
   const float *S = stat + (size_t)f * H * kStatWords;
   float *pm_col = pm_out + (size_t)gcol * H;
   // The running (cost, vB) minima of a row live in the output array itself between the units of its
@@ -390,7 +423,8 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
     uint32_t A[kRecWords];
 #pragma unroll
     for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
-    const char *pa = lutb + 4 * vTc;
+    const unsigned ca = lutb + 4u * (unsigned)vTc;
+    const unsigned cb0 = lutb + 4u * (unsigned)(vb0 - 1);  // row vB - 1 of step k: cb0 + 4k
 
     if constexpr (PAIRWISE) {
       if (t == j) {
@@ -441,10 +475,10 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
         };
         auto base_of = [&](int k) {
           const int vB = vb0 + k;
-          return cell_base<false, 2, HAS_INVALID>(A, bchunk + k * kRecBWords, pa, lutb + 4 * (vB - 1),
+          return cell_base<false, 2, HAS_INVALID>(A, bchunk + k * kRecBWords, ca, lutb + 4u * (unsigned)(vB - 1),
                                                   (float)max(vTc + 1 - vB, 1), c, k < kg);
         };
-        CellBase b_cur = (j == 0) ? cell_base<true, 1, HAS_INVALID>(A, bchunk, pa, lutb, (float)(vTc + 1), c)
+        CellBase b_cur = (j == 0) ? cell_base<true, 1, HAS_INVALID>(A, bchunk, ca, lutb, (float)(vTc + 1), c)
                                   : base_of(0);
         for (int k = 0; k < nsteps; k++) {
           const int vB = vb0 + k;
@@ -501,7 +535,7 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
       int k0 = 0;
       if (j == 0) {
         // first segment, vB = 0 (:481-594)
-        const CellBase b = cell_base<true, 1, HAS_INVALID>(A, bchunk, pa, lutb, (float)n0, c);
+        const CellBase b = cell_base<true, 1, HAS_INVALID>(A, bchunk, ca, lutb, (float)n0, c);
         RowInfo q{};
         const float first_k_o =
             PAIRWISE ? fmul(fadd(fadd((vT <= vhor) ? kLn2 : 0.0f, p.rows_log), p.max_dis_log), c.pw) : 0.0f;
@@ -513,14 +547,14 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
       }
       if (!PAIRWISE && t == j) {
         // unary diagonal unit: vT >= vB predicate; afterwards the rows are final
-        dp_steps<PAIRWISE, true, true, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, k0, max(k0, kg), n0, lane,
+        dp_steps<PAIRWISE, true, true, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, k0, max(k0, kg), n0, lane,
                                                     c, best);
-        dp_steps<PAIRWISE, false, true, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0,
+        dp_steps<PAIRWISE, false, true, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0,
                                                      lane, c, best);
       } else {
-        dp_steps<PAIRWISE, true, false, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, k0, max(k0, kg), n0,
+        dp_steps<PAIRWISE, true, false, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, k0, max(k0, kg), n0,
                                                      lane, c, best);
-        dp_steps<PAIRWISE, false, false, HAS_INVALID>(A, bchunk, lutb, pa, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0,
+        dp_steps<PAIRWISE, false, false, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0,
                                                       lane, c, best);
       }
       if (row_ok) store_best(out + vT, best);

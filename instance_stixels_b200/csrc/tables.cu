@@ -342,7 +342,8 @@ object_lut_kernel(const float *__restrict__ joined, const float *__restrict__ ob
   __syncthreads();
   const int fn = blockIdx.y * kLutWarps + warp;
   if (fn >= D) return;
-  float *lut_col = object_lut + ((size_t)f * C + col) * (size_t)D * p.lut_stride;
+  float *lut_col = reinterpret_cast<float *>(lut_column_address(
+      (unsigned long long)object_lut, (size_t)f * C + col, p.lut_cols, (size_t)D * p.lut_stride * 4));
   object_lut_row(obj_cost_lut + (size_t)fn * D, dis_s, H, lut_col + (size_t)fn * p.lut_stride);
 }
 
