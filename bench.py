@@ -35,6 +35,8 @@ WORKLOADS = {
     "pairwise_b64": dict(mode="pairwise", step=8, batch=64),
     # configs[3]: pairwise at stixel width 4
     "pairwise_w4_b64": dict(mode="pairwise", step=4, batch=64),
+    # configs[4]: the 4096-frame stream at the largest batch; --steps 4096 / (256 * N) covers the stream
+    "pairwise_stream_b256": dict(mode="pairwise", step=8, batch=256),
 }
 ROWS, COLS = 1024, 2048
 OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
@@ -50,28 +52,69 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line):
+    NVML in-process every 10 ms, nvidia-smi as the fallback."""
+
+    _REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.sm = []
+        self.reasons = set()
+        self.sm_max = None
+        self.source = "nvml"
         self._stop = threading.Event()
         self._t = None
+        self._h = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        nv = self._nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for bit, name in self._REASONS.items():
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 6:
+            self.sm.append(float(parts[0]))
+            self.sm_max = float(parts[1])
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _loop(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self._h is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01 if self._h is not None else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._loop, daemon=True)
@@ -83,13 +126,11 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=float(self.rows[0][1]),
-                    reasons=reasons, samples=len(self.rows))
+        if not self.sm:
+            return dict(sm_mhz=None, sm_max_mhz=self.sm_max, reasons=["unavailable"], samples=0, source=self.source)
+        sm = sorted(self.sm)
+        return dict(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], sm_max_mhz=self.sm_max, reasons=sorted(self.reasons),
+                    samples=len(sm), source=self.source)
 
 
 def cpu_baseline(wl, nframes=1):
@@ -152,7 +193,7 @@ def run_reference(args, wl, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="unary_b64", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -258,9 +299,14 @@ def main():
         dp_avg_s = dp_ms * 1e-3 / max(dp_launches, 1)
         achieved = ops_per_launch / dp_avg_s / 1e12
         peak = 148 * 128 * peaks["sm_max_mhz"] * 1e6 / 1e12
-        # table build (join + column tables): algorithmic HBM bytes per frame
+        # table build (join + column tables + object LUT).  Bytes the three kernels must move per frame in this
+        # design: the inputs (disparity + unpadded segmentation), the joined disparity (written once,
+        # read by two kernels), and the tables the DP consumes (prefix records in both layouts, object LUT).
         seg_bytes = C_ * 21 * (H // 8) * 4
-        tab_bytes = (H * COLS * 4 + seg_bytes) * chunk
+        in_bytes = H * COLS * 4 + seg_bytes
+        rec_stride = (H + 1 + 31) // 32 * 32
+        table_bytes = C_ * H * 4 * 3 + C_ * (30 + 32) * rec_stride * 4 + C_ * 128 * H * 4
+        tab_bytes = (in_bytes + table_bytes) * chunk
         tab_ms = stages["join"][0] + stages["column_tables"][0]
         tab_launches = max(stages["join"][1], 1)
         line = dict(
@@ -285,7 +331,9 @@ def main():
                                  achieved=tab_bytes / (tab_ms * 1e-3 / tab_launches) / 1e9,
                                  peak=peaks["hbm_gbs"], unit="GB/s",
                                  frac=tab_bytes / (tab_ms * 1e-3 / tab_launches) / 1e9 / peaks["hbm_gbs"],
-                                 traffic=None),
+                                 traffic=None,
+                                 note=f"bytes per frame: inputs {in_bytes} + joined/records/object LUT {table_bytes}; "
+                                      f"inputs alone are {in_bytes * chunk / (tab_ms * 1e-3 / tab_launches) / 1e9:.0f} GB/s"),
             stage_ms_per_step={k: v[0] / args.steps for k, v in stages.items()},
         )
         if not args.no_extra and world == 1:

@@ -307,7 +307,7 @@ __device__ __forceinline__ void store_best(float4 *p, const Best &b) {
 }
 
 template <bool PAIRWISE, bool HAS_INVALID>
-__global__ void __launch_bounds__(kDpThreads, 4)
+__global__ void __launch_bounds__(kDpThreads, PAIRWISE ? 4 : 5)
 dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
           const float *__restrict__ object_lut, const float *__restrict__ stat, float *__restrict__ pm_out,
           const int *__restrict__ vhor_arr, const float *__restrict__ object_disparity_range,
