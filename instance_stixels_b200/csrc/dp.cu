@@ -283,7 +283,7 @@ struct DpLayout {
     size_t o = 0;
     off_ring = o; o += (size_t)kStages * kSlotBytes;
     off_bars = o; o += (size_t)2 * kStages * 8;            // full[kStages] | qfull[kStages]
-    off_cnt = o; o += (size_t)3 * nt * 4;                  // per chunk: units handed out | finished; per tile: chunks done
+    off_cnt = o; o += (size_t)(3 * nt + 1) * 4;            // per chunk: units handed out | finished; per tile: chunks done; next diagonal
     o = (o + 15) & ~(size_t)15;
     off_ih = off_qs = off_qnext = off_sst = off_odr = o;
     if (!pairwise) {
@@ -329,6 +329,7 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
   int *cnt_out = reinterpret_cast<int *>(smem_raw + L.off_cnt);  // [nt] units handed out, per chunk
   int *cnt_fin = cnt_out + nt;                                    // [nt] units finished, per chunk
   int *tile_done = cnt_fin + nt;                                  // [nt] chunks finished, per tile
+  int *diag_next = tile_done + nt;                                // next diagonal unit to run (pairwise)
   float *ihs = reinterpret_cast<float *>(smem_raw + L.off_ih);
   float *qs = reinterpret_cast<float *>(smem_raw + L.off_qs);
   float *qnext = reinterpret_cast<float *>(smem_raw + L.off_qnext);
@@ -363,7 +364,7 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 3 * nt; i += kDpThreads) cnt_out[i] = 0;
+  for (int i = tid; i < 3 * nt + 1; i += kDpThreads) cnt_out[i] = 0;
   if constexpr (!PAIRWISE) {
     for (int i = tid; i <= H; i += kDpThreads) ihs[i] = __ldg(inverse_height + i);
   } else {
@@ -392,19 +393,53 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
 
   int jcur = 0;  // chunk this warp currently draws units from (warp-uniform, only grows)
   while (true) {
-    // ---- draw the next unit: chunk-major, lowest tile first ----
-    int idx = 0;
+    // ---- draw the next unit ----
+    int idx = 0, jsel = nt, tsel = 0;
     if (lane == 0) {
-      while (jcur < nt) {
-        idx = atomicAdd(&cnt_out[jcur], 1);
-        if (jcur + idx < nt) break;
-        jcur++;
+      if constexpr (PAIRWISE) {
+        // The diagonal units form the serial chain of the column (diag j -> unit (j+1, j) -> diag j+1), so a
+        // diagonal is taken the moment its tile has finished all earlier chunks; otherwise the next
+        // off-diagonal unit, chunk-major, lowest tile first.  A warp that finds neither retires: the warp
+        // that finishes unit (d, d-1) re-enters here and finds diagonal d ready.
+        volatile int *vdiag = diag_next;
+        while (true) {
+          const int d = *vdiag;
+          if (d < nt && *reinterpret_cast<volatile int *>(tile_done + d) >= d) {
+            if (atomicCAS(diag_next, d, d + 1) == d) {
+              jsel = tsel = d;
+              idx = -1;
+              break;
+            }
+            continue;
+          }
+          while (jcur < nt) {
+            idx = atomicAdd(&cnt_out[jcur], 1);
+            if (jcur + 1 + idx < nt) break;
+            jcur++;
+          }
+          if (jcur < nt) {
+            jsel = jcur;
+            tsel = jcur + 1 + idx;
+          }
+          break;
+        }
+      } else {
+        // chunk-major, lowest tile first (the diagonal unit is index 0 of its chunk)
+        while (jcur < nt) {
+          idx = atomicAdd(&cnt_out[jcur], 1);
+          if (jcur + idx < nt) break;
+          jcur++;
+        }
+        jsel = jcur;
+        tsel = jcur + idx;
       }
     }
     jcur = __shfl_sync(full_mask, jcur, 0);
     idx = __shfl_sync(full_mask, idx, 0);
-    if (jcur >= nt) break;
-    const int j = jcur, t = j + idx;
+    jsel = __shfl_sync(full_mask, jsel, 0);
+    tsel = __shfl_sync(full_mask, tsel, 0);
+    if (jsel >= nt) break;
+    const int j = jsel, t = tsel;
     if (idx == 0 && lane == 0) produce(j + kPrefetch);  // the first unit of a chunk keeps the ring filled
     __syncwarp();
     const int slot = j % kStages;
