@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libinstance_stixels_b200.so")
+# ISX_LIB_PATH: a differently tuned build of the same library (kernel A/B runs); there is no other fallback
+LIB_PATH = os.environ.get("ISX_LIB_PATH") or os.path.join(_HERE, "libinstance_stixels_b200.so")
 
 # every symbol include/instance_stixels_b200.h declares
 EXPORTS = [

@@ -48,6 +48,16 @@ constexpr int kDpThreads = kDpWarps * 32;
 constexpr int kChunk = 32;
 constexpr int kStages = 4;     // ring slots of 4 KB
 constexpr int kPrefetch = 2;   // chunks the producer runs ahead (< kStages)
+// steps per iteration of the inner loop (2 or 4) and resident CTAs per SM the register budget aims at
+#ifndef ISX_UNARY_UNROLL
+#define ISX_UNARY_UNROLL 2
+#endif
+#ifndef ISX_UNARY_CTAS
+#define ISX_UNARY_CTAS 5
+#endif
+#ifndef ISX_PAIRWISE_UNROLL
+#define ISX_PAIRWISE_UNROLL 4
+#endif
 constexpr int kSlotWords = kChunk * kRecBWords;
 constexpr int kSlotBytes = kSlotWords * 4;
 constexpr int kSstWords = ((kChunk + 1) * kStatWords + 3) & ~3;  // staged static transition records of a chunk
@@ -256,21 +266,33 @@ __device__ __forceinline__ void dp_steps(const uint32_t (&A)[kRecWords], const u
   unsigned cb = cb0 + 4u * (unsigned)k0;
   const uint32_t *brow = bchunk + k0 * kRecBWords;
   const float *qrow = qs + k0 * kDynWords;
+  constexpr int kDpUnroll = PAIRWISE ? ISX_PAIRWISE_UNROLL : ISX_UNARY_UNROLL;
   int k = k0;
-  for (; k + 1 < k1; k += 2) {
-    dp_step<PAIRWISE, GROUND, DIAG, HAS_INVALID, 0>(A, brow, ca, cb, ihs, ihp, n0 - k, qrow, vb0 + k, k, lane, nf, c,
-                                                    best);
-    dp_step<PAIRWISE, GROUND, DIAG, HAS_INVALID, 1>(A, brow, ca, cb, ihs, ihp, n0 - k, qrow, vb0 + k + 1, k + 1, lane,
-                                                    fadd(nf, -1.0f), c, best);
-    nf = fadd(nf, -2.0f);
-    ihp -= 2;
-    cb += 8u;
-    brow += 2 * kRecBWords;
-    qrow += 2 * kDynWords;
+#define ISX_DP_STEP(U)                                                                                          \
+  dp_step<PAIRWISE, GROUND, DIAG, HAS_INVALID, U>(A, brow, ca, cb, ihs, ihp, n0 - k, qrow, vb0 + k + U, k + U, lane, \
+                                                  U == 0 ? nf : fadd(nf, -(float)U), c, best)
+  for (; k + kDpUnroll <= k1; k += kDpUnroll) {
+    ISX_DP_STEP(0);
+    ISX_DP_STEP(1);
+    if constexpr (kDpUnroll == 4) {
+      ISX_DP_STEP(2);
+      ISX_DP_STEP(3);
+    }
+    nf = fadd(nf, -(float)kDpUnroll);
+    ihp -= kDpUnroll;
+    cb += 4u * kDpUnroll;
+    brow += kDpUnroll * kRecBWords;
+    qrow += kDpUnroll * kDynWords;
   }
-  if (k < k1)
-    dp_step<PAIRWISE, GROUND, DIAG, HAS_INVALID, 0>(A, brow, ca, cb, ihs, ihp, n0 - k, qrow, vb0 + k, k, lane, nf, c,
-                                                    best);
+  for (; k < k1; k++) {
+    ISX_DP_STEP(0);
+    nf = fadd(nf, -1.0f);
+    ihp -= 1;
+    cb += 4u;
+    brow += kRecBWords;
+    qrow += kDynWords;
+  }
+#undef ISX_DP_STEP
 }
 
 // Shared-memory carve-up (bytes).  Kept small on purpose: shared memory and L1 share one 228 KB array,
@@ -307,7 +329,7 @@ __device__ __forceinline__ void store_best(float4 *p, const Best &b) {
 }
 
 template <bool PAIRWISE, bool HAS_INVALID>
-__global__ void __launch_bounds__(kDpThreads, PAIRWISE ? 4 : 5)
+__global__ void __launch_bounds__(kDpThreads, PAIRWISE ? 4 : ISX_UNARY_CTAS)
 dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
           const float *__restrict__ object_lut, const float *__restrict__ stat, float *__restrict__ pm_out,
           const int *__restrict__ vhor_arr, const float *__restrict__ object_disparity_range,
