@@ -521,6 +521,16 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &d_tmp, D * D));
   ISX_TRY(h, cudaMemcpy(d_tmp, m.obj_cost_lut.data(), sizeof(float) * D * D, cudaMemcpyHostToDevice));
   b.obj_cost_lut = d_tmp;
+  {
+    // transposed copy [dis][fn], fn padded to 32: the LUT kernel reads one 128-byte line per (row, 32 fn)
+    const size_t Dp = (D + 31) & ~(size_t)31;
+    std::vector<float> t(D * Dp, 0.0f);
+    for (size_t fn = 0; fn < D; fn++)
+      for (size_t dis = 0; dis < D; dis++) t[dis * Dp + fn] = m.obj_cost_lut[fn * D + dis];
+    ISX_TRY(h, dev_alloc(h, &d_tmp, D * Dp));
+    ISX_TRY(h, cudaMemcpy(d_tmp, t.data(), sizeof(float) * D * Dp, cudaMemcpyHostToDevice));
+    b.obj_cost_lut_t = d_tmp;
+  }
   ISX_TRY(h, dev_alloc(h, &d_tmp, D));
   ISX_TRY(h, cudaMemcpy(d_tmp, m.object_disparity_range.data(), sizeof(float) * D, cudaMemcpyHostToDevice));
   b.object_disparity_range = d_tmp;

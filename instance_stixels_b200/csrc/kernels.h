@@ -26,6 +26,7 @@ struct BatchBuffers {
   float4 *dp = nullptr;                // [B][C][H]: {cost_gs, cost_obj, as_float(vB_gs), as_float(vB_obj)}
   // model tables (device copies of HostModel vectors)
   const float *obj_cost_lut = nullptr;       // [D][D]
+  const float *obj_cost_lut_t = nullptr;     // [D][D rounded up to 32], transposed: [dis][fn]
   const float *object_disparity_range = nullptr;  // [D]
   const float *inverse_height = nullptr;     // [H+1]
   // outputs

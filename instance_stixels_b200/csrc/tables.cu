@@ -139,43 +139,20 @@ __device__ void exact_prefix_warp(const T *e, int n, T *ps) {
   if (lane == 0) ps[n] = carry;
 }
 
-// One fn row of the object LUT in the reference's summation order
-// (warp_prefix_sum / ComputePrefixSumWarp2, StixelsKernels.cu:236-296):
-// 32-row chunks, the running total joins lane 0 BEFORE the Kogge-Stone scan.
-// out[v] = LUT[fn][v+1]; LUT[fn][0] = 0 is implicit.
-__device__ __forceinline__ void object_lut_row(const float *__restrict__ cost_row, const uint8_t *dis, int H,
-                                               float *__restrict__ out) {
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  float add = 0.0f;
-  for (int i = 0; i < H; i += 32) {
-    const int v = i + lane;
-    float c = __ldg(cost_row + (v < H ? dis[v] : 0));
-    if (lane == 0) c = fadd(c, add);
-#pragma unroll
-    for (int j = 1; j < 32; j <<= 1) {
-      const float n = __shfl_up_sync(full, c, j);
-      if (lane >= j) c = fadd(c, n);
-    }
-    if (v < H) out[v] = c;
-    add = __shfl_sync(full, c, 31);
-  }
-}
-
 constexpr int kTabThreads = 256;
 
 // Dynamic shared memory carve-up (bytes), Hp = H + 1 rounded up to 4.
+// The per-row terms are scanned in place (every scan reads e[v] and writes ps[v] from the same lane), which keeps
+// the CTA at 71 KB so that three of them share an SM.
 struct TabSmem {
   int Hp, nq;
-  size_t off_e[4], off_ps[4], off_segps, off_seg, off_i64e, off_i64ps, total;
+  size_t off_e[4], off_segps, off_seg, off_i64e, total;
   __host__ __device__ TabSmem(int H, int hs2) {
     Hp = (H + 1 + 3) & ~3;
     nq = H / 8 + 1;  // prefix entries per 1/8-res channel (index v>>3 for v <= H)
     size_t o = 0;
-    for (int i = 0; i < 4; i++) { off_e[i] = o; o += (size_t)Hp * 4; }
-    for (int i = 0; i < 4; i++) { off_ps[i] = o; o += (size_t)Hp * 4; }
     off_i64e = o; o += (size_t)Hp * 8 * 4;
-    off_i64ps = o; o += (size_t)Hp * 8 * 4;
+    for (int i = 0; i < 4; i++) { off_e[i] = o; o += (size_t)Hp * 4; }
     off_seg = o; o += (size_t)21 * (nq + 1) * 4;
     off_segps = o; o += (size_t)21 * (nq + 1) * 4;
     total = (o + 15) & ~(size_t)15;
@@ -197,10 +174,9 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   float *e_valid = reinterpret_cast<float *>(smem + L.off_e[1]);
   float *e_ground = reinterpret_cast<float *>(smem + L.off_e[2]);
   float *e_sky = reinterpret_cast<float *>(smem + L.off_e[3]);
-  float *ps_f[4];
-  for (int i = 0; i < 4; i++) ps_f[i] = reinterpret_cast<float *>(smem + L.off_ps[i]);
+  float *ps_f[4] = {e_disp, e_valid, e_ground, e_sky};                   // scanned in place
   long long *e_i64 = reinterpret_cast<long long *>(smem + L.off_i64e);    // [4][Hp]
-  long long *ps_i64 = reinterpret_cast<long long *>(smem + L.off_i64ps);  // [4][Hp]
+  long long *ps_i64 = e_i64;                                              // scanned in place
   int *seg_s = reinterpret_cast<int *>(smem + L.off_seg);                 // [21][nq+1]
   int *seg_ps = reinterpret_cast<int *>(smem + L.off_segps);              // [21][nq+1]
   const int nq = L.nq, segld = nq + 1;
@@ -317,34 +293,73 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
 }
 
 // ---------------------------------------------------------------------------
-// Object-cost LUT (ComputeObjectLUT, StixelsKernels.cu:959-978): one warp per
-// (column, fn) row.  The reference's summation order makes the 32-row chunks of
-// a row a serial chain of shuffles, so the kernel is built for occupancy: no
-// shared memory beyond the column's 1 KB of quantised disparities, 16 warps per
-// CTA, every warp an independent row; each chunk is stored as one 128-byte line.
+// Object-cost LUT (ComputeObjectLUT, StixelsKernels.cu:236-296, 959-978):
+//   LUT[fn][v+1] = sum_{r<=v} obj_cost_lut[fn][(int)d[r]]
+// in the reference's summation order (warp_prefix_sum / ComputePrefixSumWarp2): 32-row chunks, the
+// running total joins row 0 of the chunk BEFORE a Kogge-Stone scan (lane L: x += x[L-j], j = 1,2,4,8,16).
+//
+// The reference runs that scan across the lanes of a warp (5 shuffles per chunk and fn row), which made
+// the first version of this kernel LSU-bound.  Here one THREAD owns a whole chunk of one fn row: its 32
+// values sit in registers, the Kogge-Stone network is 129 FADDs in exactly the reference's association,
+// and the chunk carry is a register.  A warp covers 32 consecutive fn rows (lane = fn), reads the
+// transposed cost table [dis][fn] (one 128-byte line per row of the chunk) and transposes its 32 x 32
+// result tile through shared memory so that every store is a full 128-byte line of one fn row.
 // ---------------------------------------------------------------------------
-constexpr int kLutWarps = 16;
+constexpr int kLutWarps = 4;
 constexpr int kLutThreads = kLutWarps * 32;
 
-__global__ void __launch_bounds__(kLutThreads, 4)
-object_lut_kernel(const float *__restrict__ joined, const float *__restrict__ obj_cost_lut,
+__global__ void __launch_bounds__(kLutThreads)
+object_lut_kernel(const float *__restrict__ joined, const float *__restrict__ cost_t,
                   float *__restrict__ object_lut, KParams p) {
-  __shared__ uint8_t dis_s[1024];
+  __shared__ __align__(16) uint8_t dis_s[1024 + 32];
+  __shared__ float tile[kLutWarps][32][33];
   const int H = p.rows, C = p.realcols, D = p.max_dis;
+  const int Dp = (D + 31) & ~31;
   const int col = blockIdx.x, f = blockIdx.z;
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float *d_col = joined + ((size_t)f * C + col) * H;
-  for (int v = threadIdx.x; v < H; v += kLutThreads) {
-    int di = (int)d_col[v];  // (int) d as LUT index (:246-248)
-    di = di < 0 ? 0 : (di >= D ? D - 1 : di);
+  const int Hc = (H + 31) & ~31;
+  for (int v = threadIdx.x; v < Hc; v += kLutThreads) {
+    int di = 0;  // rows past H count as disparity 0, like the reference's padded loop (:262-272)
+    if (v < H) {
+      di = (int)d_col[v];  // (int) d as LUT index (:246-248)
+      di = di < 0 ? 0 : (di >= D ? D - 1 : di);
+    }
     dis_s[v] = (uint8_t)di;
   }
   __syncthreads();
-  const int fn = blockIdx.y * kLutWarps + warp;
-  if (fn >= D) return;
+  const int fn0 = (blockIdx.y * kLutWarps + warp) * 32;
+  if (fn0 >= D) return;
   float *lut_col = reinterpret_cast<float *>(lut_column_address(
       (unsigned long long)object_lut, (size_t)f * C + col, p.lut_cols, (size_t)D * p.lut_stride * 4));
-  object_lut_row(obj_cost_lut + (size_t)fn * D, dis_s, H, lut_col + (size_t)fn * p.lut_stride);
+  const float *cost_fn = cost_t + fn0 + lane;  // column fn of the transposed table (padded, always in range)
+  float(*tl)[33] = tile[warp];
+  float carry = 0.0f;
+  for (int i = 0; i < Hc; i += 32) {
+    float x[32];
+    const uint4 *dq = reinterpret_cast<const uint4 *>(dis_s + i);
+    const uint4 d0 = dq[0], d1 = dq[1];
+    const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+    for (int r = 0; r < 32; r++) x[r] = __ldg(cost_fn + ((dw[r >> 2] >> (8 * (r & 3))) & 0xffu) * Dp);
+    x[0] = fadd(x[0], carry);
+#pragma unroll
+    for (int j = 1; j < 32; j <<= 1) {
+#pragma unroll
+      for (int L = 31; L >= j; L--) x[L] = fadd(x[L], x[L - j]);
+    }
+    carry = x[31];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; r++) tl[lane][r] = x[r];
+    __syncwarp();
+    const int v = i + lane;
+    if (v < H) {
+#pragma unroll
+      for (int r = 0; r < 32; r++)
+        if (fn0 + r < D) lut_col[(size_t)(fn0 + r) * p.lut_stride + v] = tl[r][lane];  // out[v] = LUT[fn][v + 1]
+    }
+  }
 }
 
 }  // namespace
@@ -367,8 +382,8 @@ void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, 
   }
   column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.records,
                                                         b.records_b, b.error_flag, p);
-  dim3 lgrid(p.realcols, (p.max_dis + kLutWarps - 1) / kLutWarps, nframes);
-  object_lut_kernel<<<lgrid, kLutThreads, 0, s>>>(b.joined, b.obj_cost_lut, b.object_lut, p);
+  dim3 lgrid(p.realcols, (p.max_dis + 32 * kLutWarps - 1) / (32 * kLutWarps), nframes);
+  object_lut_kernel<<<lgrid, kLutThreads, 0, s>>>(b.joined, b.obj_cost_lut_t, b.object_lut, p);
   g_launch_count += 2;
 }
 
