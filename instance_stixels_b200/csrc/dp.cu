@@ -55,6 +55,13 @@ constexpr int kPrefetch = 2;   // chunks the producer runs ahead (< kStages)
 #ifndef ISX_UNARY_CTAS
 #define ISX_UNARY_CTAS 5
 #endif
+// whether the dead-ground-slot variant of the inner loop is instantiated (it costs registers in pairwise mode)
+#ifndef ISX_DEAD_SLOT
+#define ISX_DEAD_SLOT(pairwise) (!(pairwise))
+#endif
+#ifndef ISX_PAIRWISE_CTAS
+#define ISX_PAIRWISE_CTAS 4
+#endif
 #ifndef ISX_PAIRWISE_UNROLL
 #define ISX_PAIRWISE_UNROLL 4
 #endif
@@ -122,12 +129,16 @@ struct CellBase {
 //   A : R[vT+1] in registers,  brow: R[vB] in shared memory (warp-uniform address)
 //   nf: segment height as float;  ca / cb: biased low address words of LUT[0][vT] / LUT[0][vB-1]
 //   (cb + BOFF addresses row vB - 1; BOFF is the compile-time part of the unrolled step)
-// GROUND: 1 = ground side, 0 = sky side, 2 = decided at run time by `ground_rt` (diagonal units)
+// GROUND: 1 = ground side, 0 = sky side, 2 = decided at run time by `ground_rt` (diagonal units),
+//         3 = ground side of a tile that lies entirely at/above the horizon: the ground prefix of every row
+//             of the tile is +inf (ground_lut, StixelsKernels.cu:437-446), so the ground slot can never win
+//             and its terms are not evaluated
 template <bool FIRST, int GROUND, bool HAS_INVALID, int BOFF = 0>
 __device__ __forceinline__ CellBase cell_base(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ brow,
                                               unsigned ca, unsigned cb, float nf, const DpConsts &c,
                                               bool ground_rt = true) {
-  const bool ground = GROUND == 2 ? ground_rt : GROUND == 1;
+  const bool ground = GROUND == 2 ? ground_rt : GROUND != 0;
+  constexpr bool kGsDead = GROUND == 3;
   uint32_t Bw[32];
   {
     const uint4 *b4 = reinterpret_cast<const uint4 *>(brow);
@@ -146,7 +157,7 @@ __device__ __forceinline__ CellBase cell_base(const uint32_t (&A)[kRecWords], co
 #pragma unroll
   for (int k = 12; k < 19; k++) s_in = min(s_in, (int)(A[k] - Bw[k]));
   const int s_off = (int)(A[kRecOff] - Bw[kRecOff]);
-  const int s_gs = ground ? min((int)(A[0] - Bw[0]), (int)(A[1] - Bw[1])) : (int)(A[kSkyClass] - Bw[kSkyClass]);
+  const int s_gs = kGsDead ? 0 : ground ? min((int)(A[0] - Bw[0]), (int)(A[1] - Bw[1])) : (int)(A[kSkyClass] - Bw[kSkyClass]);
   const float f_off = (float)s_off;
   const float nic = fmul(f_off, c.iw);  // ComputeNonInstanceOffsetCost * weight (:618-621)
 
@@ -162,7 +173,7 @@ __device__ __forceinline__ CellBase cell_base(const uint32_t (&A)[kRecWords], co
   b.seg_o = fmin_(fadd(nic, (float)s_ni), fadd(ic, (float)s_in));
   // In the first-segment block nvcc contracted `min(road, sidewalk) + weight * offsets` into one
   // FFMA (reference SASS of StixelsKernels.cu:502-506); everywhere else it is FMUL + FADD.
-  b.seg_gs = FIRST ? ffma(f_off, c.iw, (float)s_gs) : fadd(nic, (float)s_gs);
+  b.seg_gs = kGsDead ? 0.0f : FIRST ? ffma(f_off, c.iw, (float)s_gs) : fadd(nic, (float)s_gs);
 
   // ---- disparity terms: ComputeMean (:47-60) + clamp (:651-653) ----
   const float sd = fsub(f_(A[kRecDisp]), f_(Bw[kRecDisp]));
@@ -183,7 +194,7 @@ __device__ __forceinline__ CellBase cell_base(const uint32_t (&A)[kRecWords], co
   const float lut_hi = ldg_lut<0>(roff + ca, c.lut_hi);
   const float lut_lo = FIRST ? 0.0f : ldg_lut<BOFF>(roff + cb, c.lut_hi);
   b.data_o = fsub(lut_hi, lut_lo);
-  b.data_gs = ground ? fsub(f_(A[kRecGround]), f_(Bw[kRecGround])) : fsub(f_(A[kRecSky]), f_(Bw[kRecSky]));
+  b.data_gs = kGsDead ? 0.0f : ground ? fsub(f_(A[kRecGround]), f_(Bw[kRecGround])) : fsub(f_(A[kRecSky]), f_(Bw[kRecSky]));
   return b;
 }
 
@@ -192,7 +203,21 @@ template <bool PAIRWISE, bool FIRST, int GROUND>
 __device__ __forceinline__ void cell_finish(const CellBase &b, float ih, const RowInfo &q, float first_k_gs,
                                             float first_k_o, const DpConsts &c, float &cost_gs, float &cost_o,
                                             bool ground_rt = true) {
-  const bool ground = GROUND == 2 ? ground_rt : GROUND == 1;
+  const bool ground = GROUND == 2 ? ground_rt : GROUND != 0;
+  if constexpr (GROUND == 3) {
+    // the ground slot is dead (see cell_base): only the object slot
+    float k_o = 0.0f;
+    if constexpr (PAIRWISE) {
+      float p1, p2, p3;
+      object_priors(q, true, b.fn, c.epsilon, p1, p2, p3);
+      k_o = fmul(fmin_(p3, fmin_(p1, p2)), c.pw);
+      cost_o = ffma(b.seg_o, c.sw, ffma(b.data_o, c.dw, k_o));
+    } else {
+      cost_o = ffma(b.seg_o, c.sw, ffma(ih, c.pw, fmul(b.data_o, c.dw)));
+    }
+    cost_gs = inf_f();
+    return;
+  }
   if constexpr (PAIRWISE) {
     float k_gs, k_o;
     if constexpr (FIRST) {
@@ -237,7 +262,7 @@ struct Best {
 // Steps [k0, k1) of one unit; the whole range lies on one side of the horizon.
 //   DIAG (unary only): tile == chunk, lane l is live for k <= l only (vT >= vB).
 // One step: U = position inside the manually unrolled pair (compile-time LUT / record offsets).
-template <bool PAIRWISE, bool GROUND, bool DIAG, bool HAS_INVALID, int U>
+template <bool PAIRWISE, int GROUND, bool DIAG, bool HAS_INVALID, int U>
 __device__ __forceinline__ void dp_step(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ brow,
                                         unsigned ca, unsigned cb, const float *__restrict__ ihs,
                                         const float *__restrict__ ihp, int nk, const float *__restrict__ qrow,
@@ -248,15 +273,15 @@ __device__ __forceinline__ void dp_step(const uint32_t (&A)[kRecWords], const ui
   float ih = 0.0f;
   if constexpr (PAIRWISE) q = load_row_info(qrow + U * kDynWords);
   else ih = DIAG ? ihs[max(nk - U, 1)] : ihp[-U];  // ihp = ihs + nk, nk = vT + 1 - vB of step U = 0
-  const CellBase b = cell_base<false, GROUND ? 1 : 0, HAS_INVALID, 4 * U>(A, brow + U * kRecBWords, ca, cb, nfc, c);
+  const CellBase b = cell_base<false, GROUND, HAS_INVALID, 4 * U>(A, brow + U * kRecBWords, ca, cb, nfc, c);
   float cost_gs, cost_o;
-  cell_finish<PAIRWISE, false, GROUND ? 1 : 0>(b, ih, q, 0.0f, 0.0f, c, cost_gs, cost_o);
+  cell_finish<PAIRWISE, false, GROUND>(b, ih, q, 0.0f, 0.0f, c, cost_gs, cost_o);
   const bool live = !DIAG || lane >= k;
-  if (live && cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = vB; }
+  if (GROUND != 3 && live && cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = vB; }
   if (live && cost_o < best.o) { best.o = cost_o; best.vb_o = vB; }
 }
 
-template <bool PAIRWISE, bool GROUND, bool DIAG, bool HAS_INVALID>
+template <bool PAIRWISE, int GROUND, bool DIAG, bool HAS_INVALID>
 __device__ __forceinline__ void dp_steps(const uint32_t (&A)[kRecWords], const uint32_t *__restrict__ bchunk,
                                          unsigned cb0, unsigned ca, const float *__restrict__ ihs,
                                          const float *__restrict__ qs, int vb0, int k0, int k1, int n0, int lane,
@@ -329,7 +354,7 @@ __device__ __forceinline__ void store_best(float4 *p, const Best &b) {
 }
 
 template <bool PAIRWISE, bool HAS_INVALID>
-__global__ void __launch_bounds__(kDpThreads, PAIRWISE ? 4 : ISX_UNARY_CTAS)
+__global__ void __launch_bounds__(kDpThreads, PAIRWISE ? ISX_PAIRWISE_CTAS : ISX_UNARY_CTAS)
 dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
           const float *__restrict__ object_lut, const float *__restrict__ stat, float *__restrict__ pm_out,
           const int *__restrict__ vhor_arr, const float *__restrict__ object_disparity_range,
@@ -604,15 +629,20 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
       }
       if (!PAIRWISE && t == j) {
         // unary diagonal unit: vT >= vB predicate; afterwards the rows are final
-        dp_steps<PAIRWISE, true, true, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, k0, max(k0, kg), n0, lane,
-                                                    c, best);
-        dp_steps<PAIRWISE, false, true, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0,
-                                                     lane, c, best);
+        dp_steps<PAIRWISE, 1, true, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, k0, max(k0, kg), n0, lane, c,
+                                                 best);
+        dp_steps<PAIRWISE, 0, true, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0, lane,
+                                                 c, best);
       } else {
-        dp_steps<PAIRWISE, true, false, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, k0, max(k0, kg), n0,
-                                                     lane, c, best);
-        dp_steps<PAIRWISE, false, false, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0,
-                                                      lane, c, best);
+        // ground-side steps of a tile that lies entirely at/above the horizon cannot yield a ground stixel
+        if (ISX_DEAD_SLOT(PAIRWISE) && t * kChunk >= vhor)
+          dp_steps<PAIRWISE, 3, false, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, k0, max(k0, kg), n0, lane,
+                                                    c, best);
+        else
+          dp_steps<PAIRWISE, 1, false, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, k0, max(k0, kg), n0, lane,
+                                                    c, best);
+        dp_steps<PAIRWISE, 0, false, HAS_INVALID>(A, bchunk, cb0, ca, ihs, qs_slot, vb0, max(k0, kg), nsteps, n0, lane,
+                                                  c, best);
       }
       if (row_ok) store_best(out + vT, best);
     }
