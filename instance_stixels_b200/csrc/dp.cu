@@ -34,6 +34,8 @@
 // Because one of GROUND/SKY is +inf for every row (ground only exists below
 // the horizon, sky only at/above it) the cost table keeps two slots per row:
 // "gs" (ground if vT < vhor else sky) and "object".
+#include <cstdlib>
+
 #include "dp_common.cuh"
 #include "kernels.h"
 
@@ -43,8 +45,11 @@ unsigned long long g_launch_count = 0;
 
 namespace {
 
+// Warps per column CTA: 4 for throughput (4-5 CTAs per SM); 8 when a launch has fewer columns than
+// two per SM (single frames), where the latency of one column is what the caller waits for.
 constexpr int kDpWarps = 4;
-constexpr int kDpThreads = kDpWarps * 32;
+constexpr int kDpWarpsLatency = 8;
+constexpr int kSstBufs = 2;    // staged static transition records: diagonal j uses buffer j & 1
 constexpr int kChunk = 32;
 constexpr int kStages = 4;     // ring slots of 4 KB
 constexpr int kPrefetch = 2;   // chunks the producer runs ahead (< kStages)
@@ -338,7 +343,7 @@ struct DpLayout {
     } else {
       off_qs = o; o += (size_t)kStages * kChunk * kDynWords * 4;
       off_qnext = o; o += (size_t)2 * kDynWords * 4;
-      off_sst = o; o += (size_t)kDpWarps * kSstWords * 4;    // one per warp: up to kDpWarps diagonals are staged at once
+      off_sst = o; o += (size_t)kSstBufs * kSstWords * 4;    // one diagonal runs at a time; the next may already stage
       off_odr = o; o += (size_t)((D + 3) & ~3) * 4;
     }
     total = (o + 15) & ~(size_t)15;
@@ -353,13 +358,14 @@ __device__ __forceinline__ void store_best(float4 *p, const Best &b) {
   __stcg(p, make_float4(b.gs, b.o, __int_as_float(b.vb_gs), __int_as_float(b.vb_o)));
 }
 
-template <bool PAIRWISE, bool HAS_INVALID>
-__global__ void __launch_bounds__(kDpThreads, PAIRWISE ? ISX_PAIRWISE_CTAS : ISX_UNARY_CTAS)
+template <bool PAIRWISE, bool HAS_INVALID, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == kDpWarps ? (PAIRWISE ? ISX_PAIRWISE_CTAS : ISX_UNARY_CTAS) : 2)
 dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
           const float *__restrict__ object_lut, const float *__restrict__ stat, float *__restrict__ pm_out,
           const int *__restrict__ vhor_arr, const float *__restrict__ object_disparity_range,
           const float *__restrict__ inverse_height, float4 *dp_out, KParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kDpThreads = WARPS * 32;
   const unsigned full_mask = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31;
   const int gcol = blockIdx.x;  // frame * C + column
@@ -511,7 +517,7 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
     if constexpr (PAIRWISE) {
       if (t == j) {
         // stage the static transition records of vB = vb0 .. vb0 + 32 for the wavefront
-        float *sst_j = sst + (j % kDpWarps) * kSstWords;
+        float *sst_j = sst + (j % kSstBufs) * kSstWords;
         for (int i = lane; i < (kChunk + 1) * kStatWords; i += 32)
           sst_j[i] = (vb0 + i / kStatWords) < H ? __ldg(S + (size_t)vb0 * kStatWords + i) : 0.0f;
       }
@@ -534,7 +540,7 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
         // One pass, software-pipelined: the chain-independent part of step k+1 (cell_base) is issued
         // before the chain of step k (row vB-1 final -> Q[vB] -> cell -> row vB) so that it fills the
         // chain's latency.
-        const float *sst_j = sst + (j % kDpWarps) * kSstWords;
+        const float *sst_j = sst + (j % kSstBufs) * kSstWords;
         // prefix values at the start row of the best object segment so far (previous_mean needs them)
         float lo_d = f_(__ldg(rec + (size_t)kRecDisp * Hp + best.vb_o));
         float lo_v = f_(__ldg(rec + (size_t)kRecValid * Hp + best.vb_o));
@@ -662,16 +668,33 @@ size_t dp_smem_bytes(const KParams &p, bool pairwise) {
   return DpLayout(p.rows, p.max_dis, pairwise).total;
 }
 
-template <bool PAIRWISE, bool HAS_INVALID>
-static void launch_dp_variant(const KParams &p, const BatchBuffers &b, int ncolumns, size_t smem, cudaStream_t s) {
+template <bool PAIRWISE, bool HAS_INVALID, int WARPS>
+static void launch_dp_warps(const KParams &p, const BatchBuffers &b, int ncolumns, size_t smem, cudaStream_t s) {
   static size_t configured = 0;
   if (smem > configured) {
-    cudaFuncSetAttribute(dp_kernel<PAIRWISE, HAS_INVALID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(dp_kernel<PAIRWISE, HAS_INVALID, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
     configured = smem;
   }
-  dp_kernel<PAIRWISE, HAS_INVALID><<<ncolumns, kDpThreads, smem, s>>>(b.records, b.records_b, b.object_lut, b.stat,
-                                                                      b.pm, b.vhor, b.object_disparity_range,
-                                                                      b.inverse_height, b.dp, p);
+  dp_kernel<PAIRWISE, HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
+      b.records, b.records_b, b.object_lut, b.stat, b.pm, b.vhor, b.object_disparity_range, b.inverse_height, b.dp, p);
+}
+
+template <bool PAIRWISE, bool HAS_INVALID>
+static void launch_dp_variant(const KParams &p, const BatchBuffers &b, int ncolumns, size_t smem, cudaStream_t s) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  bool latency = ncolumns < 2 * sms;
+  if (const char *e = std::getenv("ISX_DP_WARPS")) {  // tests pin the variant
+    if (std::atoi(e) == kDpWarps) latency = false;
+    if (std::atoi(e) == kDpWarpsLatency) latency = true;
+  }
+  if (latency) launch_dp_warps<PAIRWISE, HAS_INVALID, kDpWarpsLatency>(p, b, ncolumns, smem, s);
+  else launch_dp_warps<PAIRWISE, HAS_INVALID, kDpWarps>(p, b, ncolumns, smem, s);
 }
 
 void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s) {

@@ -44,9 +44,16 @@ def _run_ours(pre, pairwise, fr, max_batch=1):
     return st, data, inst
 
 
+@pytest.fixture(params=["4", "8"], ids=["dp4warps", "dp8warps"])
+def dp_warps(request, monkeypatch):
+    """Both DP kernel variants (throughput: 4 warps per column, latency: 8) on every case."""
+    monkeypatch.setenv("ISX_DP_WARPS", request.param)
+    return request.param
+
+
 @pytest.mark.skipif(not refbind.available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_bit_exact_against_reference_cuda_build(case):
+def test_bit_exact_against_reference_cuda_build(case, dp_warps):
     name, mode, rows, cols, step, frame, invalid, median = case
     pairwise = mode == "pairwise"
     pre = _preset(mode, rows, cols, step, invalid, median)
