@@ -251,6 +251,49 @@ int isx_chunk_frames(isx_handle h);
 size_t isx_tensor_elems(isx_handle h, int tensor);
 int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t bytes);
 
+
+/* ------------------------------------------------------------------------
+ * Road estimation: the step in front of the stixel path.
+ * Replaces `class RoadEstimation` (InstanceStixels/include/InstanceStixels/RoadEstimation.h:31-93,
+ * src/RoadEstimation.cu:24-193, src/RoadEstimationKernels.cu:25-60) including its one third-party
+ * step, cv::HoughLines(vDisp, lines, 1.0, CV_PI/180, 25) (RoadEstimation.cu:152), which runs on
+ * the device here: v-disparity histogram -> maximum -> binary image -> standard Hough accumulator
+ * -> local maxima.  Only the candidate lines (a few hundred (index, votes) pairs) travel to the
+ * host, where they are ordered like OpenCV orders them and the first line with a pitch inside
+ * +-50 degrees yields the camera properties with the reference's own sinf/cosf/atanf
+ * (RoadEstimation.cu:155-193).
+ * ------------------------------------------------------------------------ */
+typedef struct isx_road_estimator *isx_road_handle;
+
+/* What RoadEstimation::Compute leaves in its getters (RoadEstimation.h:46-50). */
+typedef struct isx_road_estimate {
+  int32_t ok;            /* return value of RoadEstimation::Compute */
+  int32_t horizon_point; /* GetHorizonPoint(): (int)ceil(rho / sin(theta)), image row from the top */
+  float pitch;           /* GetPitch() */
+  float camera_height;   /* GetCameraHeight() */
+  float slope;           /* GetSlope() -> alpha_ground of SetRoadParameters (apps/run_cityscapes.cu:396-407) */
+  float rho, theta;      /* the Hough line behind it */
+} isx_road_estimate;
+
+int isx_road_create(isx_road_handle *out, int device);
+void isx_road_destroy(isx_road_handle h);
+/* RoadEstimation::Initialize (RoadEstimation.cu:32-84); max_batch sizes the batched entry point. */
+int isx_road_initialize(isx_road_handle h, float camera_center_y, float baseline, float focal, int rows, int cols,
+                        int max_dis, float road_vdisparity_threshold, int max_batch);
+int isx_road_finish(isx_road_handle h);        /* RoadEstimation::Finish (:86-94) */
+int isx_road_is_initialized(isx_road_handle h);
+/* RoadEstimation::Compute(const std::vector<pixel_t>&) (:96-105): host image [rows][cols]. */
+int isx_road_compute_host(isx_road_handle h, const float *disparity, size_t n_pixels, isx_road_estimate *out);
+/* RoadEstimation::Compute(pixel_t* d_im) (:107-137): device image, e.g. Stixels::GetInputDisparityImageOnDevice(). */
+int isx_road_compute_device(isx_road_handle h, const float *d_disparity, isx_road_estimate *out);
+/* Extension: n frames [n][rows][cols] resident on the device, one estimate per frame. */
+int isx_road_compute_batch_device(isx_road_handle h, int n, const float *d_disparity, isx_road_estimate *out);
+const char *isx_road_last_error(isx_road_handle h);
+/* Intermediates of the last call, frame `frame` of it (tests): 0 = v-disparity int32 [rows][max_dis],
+ * 1 = binary image uint8 [rows][max_dis], 2 = Hough accumulator int32 [numangle+2][numrho+2]. */
+size_t isx_road_tensor_bytes(isx_road_handle h, int tensor);
+int isx_road_read_tensor(isx_road_handle h, int tensor, int frame, void *host, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

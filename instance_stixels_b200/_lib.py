@@ -27,6 +27,10 @@ EXPORTS = [
     "isx_compute_batch_host", "isx_compute_batch_device", "isx_synchronize", "isx_fetch_batch_results",
     "isx_stream", "isx_tensor_elems", "isx_read_tensor", "isx_set_profiling", "isx_get_stage_times",
     "isx_chunk_frames",
+    # road estimation
+    "isx_road_create", "isx_road_destroy", "isx_road_initialize", "isx_road_finish", "isx_road_is_initialized",
+    "isx_road_compute_host", "isx_road_compute_device", "isx_road_compute_batch_device", "isx_road_last_error",
+    "isx_road_tensor_bytes", "isx_road_read_tensor",
 ]
 
 
@@ -60,6 +64,12 @@ class FrameMeta(C.Structure):
 class Road(C.Structure):
     _fields_ = [("vhor", C.c_int32), ("camera_tilt", C.c_float), ("camera_height", C.c_float),
                 ("alpha_ground", C.c_float)]
+
+
+class RoadEstimate(C.Structure):
+    """isx_road_estimate: what RoadEstimation::Compute leaves in its getters (RoadEstimation.h:46-50)."""
+    _fields_ = [("ok", C.c_int32), ("horizon_point", C.c_int32), ("pitch", C.c_float), ("camera_height", C.c_float),
+                ("slope", C.c_float), ("rho", C.c_float), ("theta", C.c_float)]
 
 
 # numpy views of isx_section (== Section, types.h:186-194) and isx_instance
@@ -123,6 +133,20 @@ def _declare(lib):
     lib.isx_set_profiling.argtypes = [H, i]
     lib.isx_get_stage_times.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_long), i, i]
     lib.isx_chunk_frames.argtypes = [H]
+    lib.isx_road_create.argtypes = [C.POINTER(H), i]
+    lib.isx_road_destroy.argtypes = [H]
+    lib.isx_road_destroy.restype = None
+    lib.isx_road_initialize.argtypes = [H, f, f, f, i, i, i, f, i]
+    lib.isx_road_finish.argtypes = [H]
+    lib.isx_road_is_initialized.argtypes = [H]
+    lib.isx_road_compute_host.argtypes = [H, C.c_void_p, C.c_size_t, C.POINTER(RoadEstimate)]
+    lib.isx_road_compute_device.argtypes = [H, C.c_void_p, C.POINTER(RoadEstimate)]
+    lib.isx_road_compute_batch_device.argtypes = [H, i, C.c_void_p, C.POINTER(RoadEstimate)]
+    lib.isx_road_last_error.argtypes = [H]
+    lib.isx_road_last_error.restype = C.c_char_p
+    lib.isx_road_tensor_bytes.argtypes = [H, i]
+    lib.isx_road_tensor_bytes.restype = C.c_size_t
+    lib.isx_road_read_tensor.argtypes = [H, i, i, C.c_void_p, C.c_size_t]
 
 
 def load():

@@ -243,6 +243,87 @@ class Stixels:
         return out
 
 
+class RoadEstimation:
+    """Python mirror of the reference's `RoadEstimation` class (RoadEstimation.h:31-93) over the C ABI:
+    Initialize / Finish / Compute / GetCameraHeight / GetPitch / GetSlope / GetHorizonPoint / IsInitialized."""
+
+    def __init__(self, device: int = 0):
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        rc = self._lib.isx_road_create(C.byref(self._h), device)
+        if rc != L.ISX_OK:
+            raise StixelsError(f"isx_road_create: {self._lib.isx_road_last_error(None).decode()} ({rc})")
+        self._est = L.RoadEstimate()
+        self._shape = None
+
+    def _check(self, rc):
+        if rc != L.ISX_OK:
+            msg = self._lib.isx_road_last_error(self._h).decode()
+            raise (InvalidArgument if rc == -1 else StixelsError)(f"{msg} ({rc})")
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.isx_road_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def Initialize(self, camera_center_y: float, baseline: float, focal: float, rows: int, cols: int, max_dis: int,
+                   road_vdisparity_threshold: float = 0.2, max_batch: int = 1):
+        self._check(self._lib.isx_road_initialize(self._h, camera_center_y, baseline, focal, rows, cols, max_dis,
+                                                  road_vdisparity_threshold, max_batch))
+        self._shape = (rows, cols, max_dis, max_batch)
+
+    def Finish(self):
+        self._check(self._lib.isx_road_finish(self._h))
+
+    def IsInitialized(self) -> bool:
+        return bool(self._lib.isx_road_is_initialized(self._h))
+
+    def Compute(self, im) -> bool:
+        """`im`: host image (numpy, [rows][cols] float32) or a device pointer (int), like the two overloads."""
+        if isinstance(im, int):
+            self._check(self._lib.isx_road_compute_device(self._h, im, C.byref(self._est)))
+        else:
+            im = np.ascontiguousarray(im, dtype=np.float32)
+            self._check(self._lib.isx_road_compute_host(self._h, im.ctypes.data, im.size, C.byref(self._est)))
+        return bool(self._est.ok)
+
+    def ComputeBatchDevice(self, n: int, d_disparity: int):
+        """Extension: n device-resident frames -> list of dicts ready for SetRoadParameters / ComputeBatch."""
+        est = (L.RoadEstimate * n)()
+        self._check(self._lib.isx_road_compute_batch_device(self._h, n, d_disparity, est))
+        return [dict(ok=bool(e.ok), vhor=e.horizon_point, camera_tilt=e.pitch, camera_height=e.camera_height,
+                     alpha_ground=e.slope, rho=e.rho, theta=e.theta) for e in est]
+
+    def GetCameraHeight(self) -> float:
+        return self._est.camera_height
+
+    def GetPitch(self) -> float:
+        return self._est.pitch
+
+    def GetSlope(self) -> float:
+        return self._est.slope
+
+    def GetHorizonPoint(self) -> int:
+        return self._est.horizon_point
+
+    def line(self):
+        return self._est.rho, self._est.theta
+
+    def read_tensor(self, tensor: int, frame: int = 0) -> np.ndarray:
+        rows, cols, max_dis, _ = self._shape
+        nbytes = self._lib.isx_road_tensor_bytes(self._h, tensor)
+        out = np.zeros(nbytes, dtype=np.uint8)
+        self._check(self._lib.isx_road_read_tensor(self._h, tensor, frame, out.ctypes.data, nbytes))
+        if tensor == 0:
+            return out.view(np.int32).reshape(rows, max_dis)
+        if tensor == 1:
+            return out.reshape(rows, max_dis)
+        return out.view(np.int32).reshape(-1, 2 * (rows + max_dis) + 3)
+
+
 def make_stixels(preset: dict, max_batch: int = 1, device: int = 0) -> Stixels:
     """SetConfig + Initialize from a synth.preset() dict."""
     s = Stixels(device)

@@ -2,6 +2,8 @@
 // 328-343, 346, 383-387, 406-411, 430-449) against the drop-in `class Stixels`, with the file
 // loaders replaced by raw binary inputs written by the test:
 //   dropin_harness <disparity.f32> <segmentation.i32> <rows> <cols> <pairwise> <vhor> <alpha> <out.stixels>
+// With vhor = -1 the road parameters come from the drop-in `class RoadEstimation`, like
+// apps/run_cityscapes.cu:332-343, 390-407, and a line "road <vhor> <pitch> <height> <slope>" is printed.
 // Prints "sections <n> instances <m>"; exit code 0 on success.
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +11,7 @@
 #include <iostream>
 #include <vector>
 
+#include "RoadEstimation.h"   // RoadEstimation
 #include "Stixels.hpp"        // Stixels
 #include "configuration.h"    // pixel_t
 
@@ -25,8 +28,9 @@ int main(int argc, char* argv[]) {
     if (argc < 9) return 2;
     const int rows = atoi(argv[3]), cols = atoi(argv[4]);
     const bool pairwise = atoi(argv[5]);
-    const int vhorizon_point = atoi(argv[6]);
-    const float alpha_ground = atof(argv[7]);
+    int vhorizon_point = atoi(argv[6]);
+    float alpha_ground = atof(argv[7]);
+    float camera_tilt = 0.0f, camera_height = 1.18f;
 
     StixelConfig stixel_config;
     stixel_config.column_step = 8;
@@ -64,7 +68,30 @@ int main(int argc, char* argv[]) {
     const auto segmentation = read_all<int32_t>(argv[2], (size_t)(cols / 8) * 21 * hs2);
     stixels.SetDisparityImage(disparity_img);
     stixels.SetSegmentation(segmentation);
-    stixels.SetRoadParameters(vhorizon_point, 0.0f, 1.18f, alpha_ground);
+    if (vhorizon_point < 0) {
+        RoadEstimation road_estimation;
+        if (road_estimation.IsInitialized()) road_estimation.Finish();
+        road_estimation.Initialize(stixel_config.camera_center_y, stixel_config.baseline, stixel_config.focal,
+                                   stixel_config.rows, stixel_config.cols, stixel_config.max_dis,
+                                   stixel_config.road_vdisparity_threshold);
+        const bool ok = road_estimation.Compute(disparity_img);
+        if (!ok) { std::printf("Road estimation failed.\n"); return 5; }
+        // the overload the ROS node uses: the image Stixels already holds on the device
+        RoadEstimation on_device;
+        on_device.Initialize(stixel_config.camera_center_y, stixel_config.baseline, stixel_config.focal,
+                             stixel_config.rows, stixel_config.cols, stixel_config.max_dis);
+        if (!on_device.Compute(stixels.GetInputDisparityImageOnDevice()) ||
+            on_device.GetHorizonPoint() != road_estimation.GetHorizonPoint() ||
+            on_device.GetSlope() != road_estimation.GetSlope()) { std::cerr << "device overload differs\n"; return 6; }
+        on_device.Finish();
+        camera_tilt = road_estimation.GetPitch();
+        camera_height = road_estimation.GetCameraHeight();
+        vhorizon_point = road_estimation.GetHorizonPoint();
+        alpha_ground = road_estimation.GetSlope();
+        std::printf("road %d %.9g %.9g %.9g\n", vhorizon_point, camera_tilt, camera_height, alpha_ground);
+        road_estimation.Finish();
+    }
+    stixels.SetRoadParameters(vhorizon_point, camera_tilt, camera_height, alpha_ground);
     stixels.Compute(pairwise, stixels_data);
 
     Section* stx = stixels_data.sections.data();

@@ -59,3 +59,25 @@ def test_dropin_class_matches_c_abi(tmp_path, pairwise):
             n_sec += 1
         assert data.sections[c, j + 1]["type"] == -1
     assert p.stdout.split() == ["sections", str(n_sec), "instances", str(len(inst))]
+
+
+@pytest.mark.gpu
+def test_dropin_road_estimation_class(tmp_path):
+    """The drop-in `class RoadEstimation` (include/InstanceStixels/RoadEstimation.h) in the caller's sequence
+    of apps/run_cityscapes.cu:390-407, against the CPU restatement."""
+    from oracle import road_cpu
+    build_harness()
+    rows, cols = 256, 512
+    fr = synth.make_frame(12, rows=rows, cols=cols)
+    dpath, spath, out = tmp_path / "d.f32", tmp_path / "s.i32", tmp_path / "o.stixels"
+    fr.disparity.tofile(dpath)
+    fr.segmentation.tofile(spath)
+    p = subprocess.run([EXE, str(dpath), str(spath), str(rows), str(cols), "1", "-1", "0", str(out)],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr + p.stdout
+    road = [l for l in p.stdout.splitlines() if l.startswith("road ")][0].split()
+    est, _ = road_cpu.estimate(fr.disparity, 128, 512.0, 0.209313, 2262.52)
+    assert est["ok"] and int(road[1]) == est["horizon_point"]
+    got = np.array([float(x) for x in road[2:5]], dtype=np.float32)
+    want = np.array([est["pitch"], est["camera_height"], est["slope"]], dtype=np.float32)
+    assert np.array_equal(got.view(np.int32), want.view(np.int32))
