@@ -253,6 +253,23 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
 
 
 /* ------------------------------------------------------------------------
+ * Segmentation ingest.  The reference bakes the layout transform between the
+ * CNN and the stixel path into its ONNX export: `FlipAndPad` (tools/CNN_training/models/
+ * wrappers.py:35-61: permute(0,3,1,2), rows flipped, zero-padded to rows_power2_segmentation, x *= 8,
+ * x.int()), whose output TRTOnnxCNN::inferOnDevice (InstanceStixels/src/TRTOnnxCNN.cpp:134-165) hands
+ * to Compute as d_segmentation_local.  These two entry points run that transform on the handle's
+ * stream, so any CNN runtime can feed the path with its plain [channels][rows/8][cols/8] float output
+ * (19 x -log softmax, y offset, x offset; rows top-down).  With column_step 4 every CNN column feeds
+ * two stixel columns.
+ * ------------------------------------------------------------------------ */
+/* single frame: fills the tensor SetSegmentation would upload (ordered before the next isx_compute) */
+int isx_set_segmentation_from_cnn_device(isx_handle h, const float *d_cnn, int cnn_rows, int cnn_cols);
+/* n frames [n][channels][cnn_rows][cnn_cols] -> d_segmentation [n][realcols][channels][rows_power2_segmentation],
+ * the layout isx_compute_batch_device takes; asynchronous on isx_stream() */
+int isx_flip_and_pad_batch_device(isx_handle h, int n, const float *d_cnn, int cnn_rows, int cnn_cols,
+                                  int32_t *d_segmentation);
+
+/* ------------------------------------------------------------------------
  * Road estimation: the step in front of the stixel path.
  * Replaces `class RoadEstimation` (InstanceStixels/include/InstanceStixels/RoadEstimation.h:31-93,
  * src/RoadEstimation.cu:24-193, src/RoadEstimationKernels.cu:25-60) including its one third-party

@@ -114,6 +114,15 @@ class Stixels:
         self._keep_seg = a
         self._check(self._lib.isx_set_segmentation(self._h, a.ctypes.data, a.size))
 
+    def SetSegmentationFromCNN(self, d_cnn: int, cnn_rows: int, cnn_cols: int):
+        """FlipAndPad on the device (wrappers.py:35-61): plain CNN output float [21][rows/8][cols/8] (device
+        pointer) -> the tensor SetSegmentation uploads."""
+        self._check(self._lib.isx_set_segmentation_from_cnn_device(self._h, d_cnn, cnn_rows, cnn_cols))
+
+    def FlipAndPadBatchDevice(self, n: int, d_cnn: int, cnn_rows: int, cnn_cols: int, d_segmentation: int):
+        """n CNN outputs -> the segmentation layout ComputeBatchDevice takes; asynchronous."""
+        self._check(self._lib.isx_flip_and_pad_batch_device(self._h, n, d_cnn, cnn_rows, cnn_cols, d_segmentation))
+
     def SetRoadParameters(self, vhor: int, camera_tilt: float, camera_height: float, alpha_ground: float):
         self._check(self._lib.isx_set_road_parameters(self._h, vhor, camera_tilt, camera_height, alpha_ground))
 

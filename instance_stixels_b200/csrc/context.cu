@@ -600,6 +600,36 @@ int isx_set_segmentation(isx_handle h, const int32_t *host, size_t n) {
   return ISX_OK;
 }
 
+// FlipAndPad on the device (ingest.cu).  The CNN grid is [channels][rows/8][cols/8]; width_margin must be 0 and
+// column_step must divide 8, as in every configuration the reference ships.
+static int check_cnn_grid(isx_handle h, int cnn_rows, int cnn_cols) {
+  const KParams &kp = h->kp;
+  if (kp.width_margin != 0 || kp.column_step < 1 || kDownsample % kp.column_step != 0)
+    return fail(h, ISX_ERR_UNSUPPORTED, "segmentation ingest needs width_margin == 0 and column_step dividing 8");
+  if (cnn_rows != kp.rows / kDownsample || cnn_cols * (kDownsample / kp.column_step) != kp.realcols)
+    return fail(h, ISX_ERR_INVALID_ARGUMENT, "CNN output must be [channels][rows/8][cols/8]");
+  return ISX_OK;
+}
+
+int isx_set_segmentation_from_cnn_device(isx_handle h, const float *d_cnn, int cnn_rows, int cnn_cols) {
+  if (int rc = check_ready(h)) return rc;
+  if (!d_cnn) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  if (int rc = check_cnn_grid(h, cnn_rows, cnn_cols)) return rc;
+  launch_flip_and_pad(h->kp, d_cnn, h->d_single_seg, 1, cnn_rows, cnn_cols, h->s_compute);
+  ISX_TRY(h, cudaGetLastError());
+  return ISX_OK;
+}
+
+int isx_flip_and_pad_batch_device(isx_handle h, int n, const float *d_cnn, int cnn_rows, int cnn_cols,
+                                  int32_t *d_segmentation) {
+  if (int rc = check_ready(h)) return rc;
+  if (!d_cnn || !d_segmentation || n < 1) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument or empty batch");
+  if (int rc = check_cnn_grid(h, cnn_rows, cnn_cols)) return rc;
+  launch_flip_and_pad(h->kp, d_cnn, d_segmentation, n, cnn_rows, cnn_cols, h->s_compute);
+  ISX_TRY(h, cudaGetLastError());
+  return ISX_OK;
+}
+
 int isx_set_road_parameters(isx_handle h, int vhor, float camera_tilt, float camera_height, float alpha_ground) {
   if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
   h->single_road = isx_road{vhor, camera_tilt, camera_height, alpha_ground};

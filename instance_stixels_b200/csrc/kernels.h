@@ -48,6 +48,9 @@ void launch_frame_tables(const KParams &p, const BatchBuffers &b, int nframes, c
 void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
 void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s);
 void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s);
+// segmentation ingest (FlipAndPad, ingest.cu): cnn float [n][channels][hs][ws] -> seg int32 [n][C][channels][hs2]
+void launch_flip_and_pad(const KParams &p, const float *cnn, int32_t *seg, int nframes, int hs, int ws,
+                         cudaStream_t s);
 void launch_grouping(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
 // reference-format views for the parity tests
 void launch_export_tables(const KParams &p, const BatchBuffers &b, int frame, bool pairwise, float *cost_table,

@@ -35,13 +35,15 @@ vdisp_kernel(const float *__restrict__ disparity, int *__restrict__ vdisp, int *
   for (int i = threadIdx.x; i < max_dis; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   const float *src = disparity + ((size_t)f * rows + row) * cols;
+  const int lane = threadIdx.x & 31;
   auto vote = [&](float d) {
     // RoadEstimationKernels.cu:32-36: d != 0 -> bin (int)d.  The reference writes out of bounds for
-    // d < 0 or d >= max_dis; those pixels are ignored here.
-    if (d != 0.0f) {
-      const int c = (int)d;
-      if (c >= 0 && c < max_dis) atomicAdd(&hist[c], 1);
-    }
+    // d < 0 or d >= max_dis; those pixels are ignored here.  Neighbouring pixels of a row mostly fall
+    // into the same bin (the road surface), so the votes of a warp are merged before the atomic.
+    int c = (d != 0.0f) ? (int)d : -1;
+    if (c >= max_dis) c = -1;
+    const unsigned peers = __match_any_sync(__activemask(), c);
+    if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[c], __popc(peers));
   };
   if ((cols & 3) == 0 && ((size_t)src & 15) == 0) {
     const float4 *s4 = reinterpret_cast<const float4 *>(src);
@@ -61,7 +63,7 @@ vdisp_kernel(const float *__restrict__ disparity, int *__restrict__ vdisp, int *
     m = max(m, v);
   }
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maximum + f, m);
+  if (lane == 0 && m > 0) atomicMax(maximum + f, m);
 }
 
 __global__ void __launch_bounds__(256)

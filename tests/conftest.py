@@ -17,6 +17,6 @@ def pytest_configure(config):
 def golden_files():
     import glob
     files = [f for f in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
-             if not os.path.basename(f).startswith("road_")]   # road_*.npz: tests/test_road_oracle.py
+             if not os.path.basename(f).startswith(("road_", "ingest_"))]   # those: test_road_oracle.py, test_ingest.py
     assert files, "tests/golden/*.npz missing"
     return files
