@@ -270,6 +270,19 @@ int isx_flip_and_pad_batch_device(isx_handle h, int n, const float *d_cnn, int c
                                   int32_t *d_segmentation);
 
 /* ------------------------------------------------------------------------
+ * Result images: the stixels of frames [first, first + n) of the last batch (or of the last
+ * isx_compute: first = 0, n = 1) drawn as the reference's evaluation tooling draws them
+ * (tools/visualization/clustering_visualization.py: draw_stixels :397-409, draw_instance_masks :118-142) -- every
+ * stixel fills the inclusive rectangle x in [c*w, c*w+w-1], y in [rows-1-vT, rows-1-vB]:
+ *   d_label_ids    uint8 [n][rows][cols]  Cityscapes label id of the class (trainId2label[class].id)
+ *   d_instance_ids int32 [n][rows][cols]  class*1000 + label for instance stixels with 0 <= label < 1000, else 0
+ *   d_disparity    float [n][rows][cols]  stixel disparity
+ * Any of the three may be NULL.  Device buffers, asynchronous on isx_stream().
+ * ------------------------------------------------------------------------ */
+int isx_rasterize_batch_device(isx_handle h, int first, int n, uint8_t *d_label_ids, int32_t *d_instance_ids,
+                               float *d_disparity);
+
+/* ------------------------------------------------------------------------
  * Road estimation: the step in front of the stixel path.
  * Replaces `class RoadEstimation` (InstanceStixels/include/InstanceStixels/RoadEstimation.h:31-93,
  * src/RoadEstimation.cu:24-193, src/RoadEstimationKernels.cu:25-60) including its one third-party

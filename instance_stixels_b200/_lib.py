@@ -29,6 +29,8 @@ EXPORTS = [
     "isx_chunk_frames",
     # segmentation ingest
     "isx_set_segmentation_from_cnn_device", "isx_flip_and_pad_batch_device",
+    # result images
+    "isx_rasterize_batch_device",
     # road estimation
     "isx_road_create", "isx_road_destroy", "isx_road_initialize", "isx_road_finish", "isx_road_is_initialized",
     "isx_road_compute_host", "isx_road_compute_device", "isx_road_compute_batch_device", "isx_road_last_error",
@@ -137,6 +139,7 @@ def _declare(lib):
     lib.isx_chunk_frames.argtypes = [H]
     lib.isx_set_segmentation_from_cnn_device.argtypes = [H, C.c_void_p, i, i]
     lib.isx_flip_and_pad_batch_device.argtypes = [H, i, C.c_void_p, i, i, C.c_void_p]
+    lib.isx_rasterize_batch_device.argtypes = [H, i, i, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.isx_road_create.argtypes = [C.POINTER(H), i]
     lib.isx_road_destroy.argtypes = [H]
     lib.isx_road_destroy.restype = None

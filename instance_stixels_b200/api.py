@@ -123,6 +123,13 @@ class Stixels:
         """n CNN outputs -> the segmentation layout ComputeBatchDevice takes; asynchronous."""
         self._check(self._lib.isx_flip_and_pad_batch_device(self._h, n, d_cnn, cnn_rows, cnn_cols, d_segmentation))
 
+    def RasterizeBatchDevice(self, first: int, n: int, d_label_ids: int = 0, d_instance_ids: int = 0,
+                             d_disparity: int = 0):
+        """Stixels of frames [first, first+n) of the last batch -> label-id / instance-id / disparity images on
+        the device (clustering_visualization.py:118-142, 397-409); pointers may be 0."""
+        self._check(self._lib.isx_rasterize_batch_device(self._h, first, n, d_label_ids or None,
+                                                         d_instance_ids or None, d_disparity or None))
+
     def SetRoadParameters(self, vhor: int, camera_tilt: float, camera_height: float, alpha_ground: float):
         self._check(self._lib.isx_set_road_parameters(self._h, vhor, camera_tilt, camera_height, alpha_ground))
 

@@ -75,6 +75,7 @@ struct isx_context {
   int *d_nsections_all = nullptr;                 // [max_batch][C]
   isx_instance *d_inst_all = nullptr;             // [max_batch][inst_cap]
   int *d_inst_count_all = nullptr;                // [max_batch]
+  int *d_raster_table = nullptr;                  // [max_batch][C][200] instance id per stixel (rasteriser)
   int inst_cap = 0;
   float *d_export_cost = nullptr;
   int *d_export_index = nullptr;
@@ -514,6 +515,7 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &h->d_nsections_all, MB * C));
   ISX_TRY(h, dev_alloc(h, &h->d_inst_all, MB * (size_t)h->inst_cap));
   ISX_TRY(h, dev_alloc(h, &h->d_inst_count_all, MB));
+  ISX_TRY(h, dev_alloc(h, &h->d_raster_table, MB * C * kMaxSections));
   ISX_TRY(h, dev_alloc(h, &h->d_export_cost, C * H * 3));
   ISX_TRY(h, dev_alloc(h, &h->d_export_index, C * H * 3));
 
@@ -788,6 +790,20 @@ int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *dispa
   h->last_roads.assign(roads, roads + n);
   if (int rc = fetch_results(h, n, nullptr, instances, instances_capacity, instance_offsets, h->s_compute)) return rc;
   ISX_TRY(h, cudaStreamSynchronize(h->s_d2h));
+  return ISX_OK;
+}
+
+int isx_rasterize_batch_device(isx_handle h, int first, int n, uint8_t *d_label_ids, int32_t *d_instance_ids,
+                               float *d_disparity) {
+  if (int rc = check_ready(h)) return rc;
+  if (first < 0 || n < 1 || first + n > h->last_batch)
+    return fail(h, ISX_ERR_INVALID_ARGUMENT, "frames outside the last computed batch");
+  if (!d_label_ids && !d_instance_ids && !d_disparity) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no output image");
+  const size_t C = h->kp.realcols;
+  launch_rasterize(h->kp, h->d_sections_all + (size_t)first * C * kMaxSections, h->d_nsections_all + (size_t)first * C,
+                   h->d_inst_all + (size_t)first * h->inst_cap, h->d_inst_count_all + first, h->inst_cap,
+                   h->d_raster_table, n, d_label_ids, d_instance_ids, d_disparity, h->s_compute);
+  ISX_TRY(h, cudaGetLastError());
   return ISX_OK;
 }
 

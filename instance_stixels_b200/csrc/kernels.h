@@ -51,6 +51,10 @@ void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pair
 // segmentation ingest (FlipAndPad, ingest.cu): cnn float [n][channels][hs][ws] -> seg int32 [n][C][channels][hs2]
 void launch_flip_and_pad(const KParams &p, const float *cnn, int32_t *seg, int nframes, int hs, int ws,
                          cudaStream_t s);
+// stixels -> label / instance / disparity images (raster.cu)
+void launch_rasterize(const KParams &p, const isx_section *sections, const int *n_sections, const isx_instance *inst,
+                      const int *inst_count, int inst_cap, int *table, int nframes, uint8_t *label_img,
+                      int32_t *instance_img, float *disparity_img, cudaStream_t s);
 void launch_grouping(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
 // reference-format views for the parity tests
 void launch_export_tables(const KParams &p, const BatchBuffers &b, int frame, bool pairwise, float *cost_table,
