@@ -377,7 +377,7 @@ def main():
             lat = sorted(lat[3:])
             line["latency_ms_batch1"] = dict(p50=lat[len(lat) // 2], p99=lat[-1])
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(wl, 1)
+            line["cpu_baseline"] = cpu_baseline(wl, 24)
         print(json.dumps(line), flush=True)
     st.Finish()
     if world > 1:
