@@ -160,7 +160,7 @@ struct TabSmem {
   }
 };
 
-__global__ void __launch_bounds__(kTabThreads)
+__global__ void __launch_bounds__(kTabThreads, 3)
 column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict__ segmentation,
                      const float *__restrict__ ground, const int *__restrict__ vhor_arr,
                      uint32_t *__restrict__ records, uint32_t *__restrict__ records_b,
@@ -259,34 +259,45 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   bool out_of_range = false;
   for (int v = tid; v <= H; v += kTabThreads) {
     const int q = v >> 3, r = v & 7;
-    uint32_t w[kRecBWords];
-#pragma unroll
-    for (int c = 0; c < 19; c++)  // P_c(v) = 8*ps[q] + seg[q]*r  (Cityscapes.h:28-42)
-      w[kRecSeg + c] = (uint32_t)(seg_ps[c * segld + q] * kDownsample + seg_s[c * segld + q] * r);
-    w[kRecOff] = (uint32_t)((seg_ps[19 * segld + q] + seg_ps[20 * segld + q]) * kDownsample +
-                            (seg_s[19 * segld + q] + seg_s[20 * segld + q]) * r);
     // instance-mean sums as exactly representable floats (see common.cuh)
     const long long smx = ps_i64[0 * L.Hp + v], smy = ps_i64[1 * L.Hp + v];
     const long long smx2 = ps_i64[2 * L.Hp + v], smy2 = ps_i64[3 * L.Hp + v];
     const long long lim1 = 1ll << 24, lim2 = 1ll << (24 + kSqSplitBits);
     out_of_range |= smx <= -lim1 || smx >= lim1 || smy <= -lim1 || smy >= lim1 || smx2 >= lim2 || smy2 >= lim2;
     const long long lomask = (1ll << kSqSplitBits) - 1;
-    w[kRecMx] = __float_as_uint((float)smx);
-    w[kRecMy] = __float_as_uint((float)smy);
-    w[kRecMx2Hi] = __float_as_uint((float)(smx2 & ~lomask));
-    w[kRecMx2Lo] = __float_as_uint((float)(smx2 & lomask));
-    w[kRecMy2Hi] = __float_as_uint((float)(smy2 & ~lomask));
-    w[kRecMy2Lo] = __float_as_uint((float)(smy2 & lomask));
-    w[kRecDisp] = __float_as_uint(ps_f[0][v]);
-    w[kRecValid] = __float_as_uint(ps_f[1][v]);
-    w[kRecGround] = __float_as_uint(ps_f[2][v]);
-    w[kRecSky] = __float_as_uint(ps_f[3][v]);
-    w[30] = w[31] = 0u;
+    // word k of the record of row v (k is a compile-time constant after unrolling)
+    auto word = [&](int k) -> uint32_t {
+      if (k < 19)  // P_c(v) = 8*ps[q] + seg[q]*r  (Cityscapes.h:28-42)
+        return (uint32_t)(seg_ps[k * segld + q] * kDownsample + seg_s[k * segld + q] * r);
+      switch (k) {
+        case kRecOff:
+          return (uint32_t)((seg_ps[19 * segld + q] + seg_ps[20 * segld + q]) * kDownsample +
+                            (seg_s[19 * segld + q] + seg_s[20 * segld + q]) * r);
+        case kRecMx: return __float_as_uint((float)smx);
+        case kRecMy: return __float_as_uint((float)smy);
+        case kRecMx2Hi: return __float_as_uint((float)(smx2 & ~lomask));
+        case kRecMx2Lo: return __float_as_uint((float)(smx2 & lomask));
+        case kRecMy2Hi: return __float_as_uint((float)(smy2 & ~lomask));
+        case kRecMy2Lo: return __float_as_uint((float)(smy2 & lomask));
+        case kRecDisp: return __float_as_uint(ps_f[0][v]);
+        case kRecValid: return __float_as_uint(ps_f[1][v]);
+        case kRecGround: return __float_as_uint(ps_f[2][v]);
+        case kRecSky: return __float_as_uint(ps_f[3][v]);
+        default: return 0u;
+      }
+    };
+    // four words at a time: four word-major stores (coalesced over v) and one 16-byte store of the row-major copy,
+    // so that only four words are live at once (the kernel runs three CTAs per SM)
 #pragma unroll
-    for (int k = 0; k < kRecWords; k++) rec_col[(size_t)k * p.rec_stride + v] = w[k];
+    for (int g = 0; g < kRecBWords / 4; g++) {
+      uint32_t w4[4];
 #pragma unroll
-    for (int k = 0; k < kRecBWords / 4; k++)
-      recb_col[(size_t)v * (kRecBWords / 4) + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+      for (int u = 0; u < 4; u++) w4[u] = word(4 * g + u);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (4 * g + u < kRecWords) rec_col[(size_t)(4 * g + u) * p.rec_stride + v] = w4[u];
+      recb_col[(size_t)v * (kRecBWords / 4) + g] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
   }
   if (out_of_range) atomicOr(error_flag, kErrOffsetRange);
   (void)lane;
