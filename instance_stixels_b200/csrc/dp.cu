@@ -60,15 +60,19 @@ constexpr int kPrefetch = 2;   // chunks the producer runs ahead (< kStages)
 #ifndef ISX_UNARY_CTAS
 #define ISX_UNARY_CTAS 5
 #endif
-// whether the dead-ground-slot variant of the inner loop is instantiated (it costs registers in pairwise mode)
+// whether the dead-ground-slot variant of the inner loop is instantiated
 #ifndef ISX_DEAD_SLOT
-#define ISX_DEAD_SLOT(pairwise) (!(pairwise))
+#define ISX_DEAD_SLOT(pairwise) true
+#endif
+#ifndef ISX_PAIRWISE_UNROLL_DEAD
+#define ISX_PAIRWISE_UNROLL_DEAD 4
 #endif
 #ifndef ISX_PAIRWISE_CTAS
 #define ISX_PAIRWISE_CTAS 4
 #endif
+// pairwise (128 registers): the dead-slot loop (45 % of the units) is unrolled by four, the others by two
 #ifndef ISX_PAIRWISE_UNROLL
-#define ISX_PAIRWISE_UNROLL 4
+#define ISX_PAIRWISE_UNROLL 2
 #endif
 constexpr int kSlotWords = kChunk * kRecBWords;
 constexpr int kSlotBytes = kSlotWords * 4;
@@ -296,7 +300,7 @@ __device__ __forceinline__ void dp_steps(const uint32_t (&A)[kRecWords], const u
   unsigned cb = cb0 + 4u * (unsigned)k0;
   const uint32_t *brow = bchunk + k0 * kRecBWords;
   const float *qrow = qs + k0 * kDynWords;
-  constexpr int kDpUnroll = PAIRWISE ? ISX_PAIRWISE_UNROLL : ISX_UNARY_UNROLL;
+  constexpr int kDpUnroll = PAIRWISE ? (GROUND == 3 ? ISX_PAIRWISE_UNROLL_DEAD : ISX_PAIRWISE_UNROLL) : ISX_UNARY_UNROLL;
   int k = k0;
 #define ISX_DP_STEP(U)                                                                                          \
   dp_step<PAIRWISE, GROUND, DIAG, HAS_INVALID, U>(A, brow, ca, cb, ihs, ihp, n0 - k, qrow, vb0 + k + U, k + U, lane, \
