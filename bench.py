@@ -327,7 +327,7 @@ def main():
         # read by two kernels), and the tables the DP consumes (prefix records in both layouts, object LUT).
         seg_bytes = C_ * 21 * (H // 8) * 4
         in_bytes = H * COLS * 4 + seg_bytes
-        rec_stride = (H + 1 + 31) // 32 * 32
+        rec_stride = 1056  # kRecStride (common.cuh)
         table_bytes = C_ * H * 4 * 3 + C_ * (30 + 32) * rec_stride * 4 + C_ * 128 * H * 4
         tab_bytes = (in_bytes + table_bytes) * chunk
         tab_ms = stages["join"][0] + stages["column_tables"][0]

@@ -31,6 +31,9 @@ constexpr float kLg2_03 = -1.7369655370712280273f;     // lg2(0.3f) folded by nv
 // rounded up to 32, so that both access patterns of the DP are coalesced 128-byte lines:
 //   * "A side": lane l reads word w of row vT + 1 = a + l + 1  (one line per word),
 //   * "B side": the 32 rows of a vB chunk are staged once per CTA into shared memory.
+// The row length is the constant kRecStride (H <= 1024) whatever the image height, so that the word
+// offsets of the A-side loads are immediates of the load instructions (one address per unit, not 30).
+constexpr int kRecStride = 1056;  // 1024 + 1 rounded up to 32
 constexpr int kRecWords = 30;
 constexpr int kRecSeg = 0;     // 19 words: full-resolution prefix of class c, exact int32
                                //   P_c(v) = 8*ps_c[v/8] + seg_c[v/8]*(v%8)   (Cityscapes.h:28-42)
@@ -88,7 +91,7 @@ struct KParams {
   float pord, epsilon, pgrav, pblg;
   float prior_weight, disparity_weight, segmentation_weight, instance_weight;
   // derived strides
-  int rec_stride;    // entries per (column, word) row of the records: H + 1 rounded up to 32
+  int rec_stride;    // entries per (column, word) row of the records: always kRecStride
   int lut_stride;    // floats per fn row of the object LUT (>= H, multiple of 32)
   int lut_cols;      // column slots of the object-LUT buffer (chunk * C), see lut_column_address
 };

@@ -180,7 +180,7 @@ static void fill_kparams(isx_context *c) {
   k.disparity_weight = m.disparity_weight;
   k.segmentation_weight = m.segmentation_weight;
   k.instance_weight = m.instance_weight;
-  k.rec_stride = (m.rows + 1 + 31) & ~31;
+  k.rec_stride = kRecStride;  // constant whatever the height (rows <= 1024 is checked in isx_initialize)
   k.lut_stride = (m.rows + 31) & ~31;
 }
 

@@ -373,7 +373,8 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
   const unsigned full_mask = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31;
   const int gcol = blockIdx.x;  // frame * C + column
-  const int H = p.rows, C = p.realcols, Hp = p.rec_stride;
+  const int H = p.rows, C = p.realcols;
+  constexpr int Hp = kRecStride;  // == p.rec_stride; a constant so that the A-side word offsets are immediates
   const int f = gcol / C;
   const int vhor = vhor_arr[f];
   const float inf = inf_f();
