@@ -176,7 +176,7 @@ class Stixels:
     def GetInstanceStixels(self) -> dict:
         """{(column, index): label} like the reference's std::map (Stixels.cu:744-776)."""
         inst = self.instance_records()
-        return {(int(r["column"]), int(r["index"])): int(r["label"]) for r in inst}
+        return dict(zip(zip(inst["column"].tolist(), inst["index"].tolist()), inst["label"].tolist()))
 
     def instance_records(self) -> np.ndarray:
         n = C.c_int(0)
