@@ -255,6 +255,7 @@ def main():
         e0.record(stream)
         for _ in range(args.steps):
             device_step()
+        st.Flush()  # the emission stream's last results are ordered before the closing event
         e1.record(stream)
         st.Synchronize()
         barrier()

@@ -190,6 +190,12 @@ int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_met
 /* Stixels::ClusterInstances (Stixels.cu:639-681).  Grouping already ran in
  * isx_compute; kept because the reference exposes it publicly. Idempotent. */
 int isx_cluster_instances(isx_handle h);
+/* The grouping step on its own: what Stixels::ClusterInstances asks of the cuML fork per class,
+ * `ML::dbscanFit(handle, X, n, 2, eps, min_pts, labels, 0, false, core_candidates)` (Stixels.cu:660-666).
+ * `xy` = n x 2 instance-centre votes, `core_candidates` = the size-filter mask, `labels` out
+ * (-1 = noise, clusters numbered by their lowest-index core point).  Host buffers, runs on `device`. */
+int isx_dbscan_fit_host(int device, const float *xy, int n, float eps, int min_pts,
+                        const unsigned char *core_candidates, int *labels);
 /* Stixels::GetInstanceStixels (Stixels.cu:744-776).  Writes up to `capacity`
  * entries, ordered by (semantic class, column, index); *n = total count. */
 int isx_get_instance_stixels(isx_handle h, isx_instance *out, int capacity, int *n);
@@ -221,6 +227,11 @@ int isx_fetch_batch_results(isx_handle h, int n, isx_section *sections, isx_inst
 /* cudaStream_t of the handle as an integer (for CUDA-event timing by the
  * caller on the stream the kernels are launched on). */
 uint64_t isx_stream(isx_handle h);
+/* Orders every result of the batches enqueued so far (backtracking and instance grouping run on a second
+ * stream) before whatever the caller enqueues next on isx_stream().  isx_synchronize, isx_fetch_batch_results
+ * and isx_rasterize_batch_device do this themselves; a caller that records its own events or launches its own
+ * consumers on isx_stream() after isx_compute_batch_device calls it first.  Asynchronous. */
+int isx_flush(isx_handle h);
 
 /* ------------------------------------------------------------------ */
 /* Introspection for parity tests / profiling (device -> host copies of

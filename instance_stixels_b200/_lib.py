@@ -23,7 +23,8 @@ EXPORTS = [
     "isx_set_camera_parameters", "isx_set_model_parameters", "isx_initialize", "isx_finish",
     "isx_is_initialized", "isx_real_cols", "isx_max_sections", "isx_segmentation_elems",
     "isx_set_disparity_image", "isx_input_disparity_device", "isx_set_segmentation",
-    "isx_set_road_parameters", "isx_compute", "isx_cluster_instances", "isx_get_instance_stixels",
+    "isx_set_road_parameters", "isx_compute", "isx_cluster_instances", "isx_dbscan_fit_host", "isx_flush",
+    "isx_get_instance_stixels",
     "isx_compute_batch_host", "isx_compute_batch_device", "isx_synchronize", "isx_fetch_batch_results",
     "isx_stream", "isx_tensor_elems", "isx_read_tensor", "isx_set_profiling", "isx_get_stage_times",
     "isx_chunk_frames",
@@ -123,11 +124,13 @@ def _declare(lib):
     lib.isx_set_road_parameters.argtypes = [H, i, f, f, f]
     lib.isx_compute.argtypes = [H, i, C.c_void_p, C.POINTER(FrameMeta), C.c_void_p]
     lib.isx_cluster_instances.argtypes = [H]
+    lib.isx_dbscan_fit_host.argtypes = [i, C.c_void_p, i, f, i, C.c_void_p, C.c_void_p]
     lib.isx_get_instance_stixels.argtypes = [H, C.c_void_p, i, C.POINTER(i)]
     lib.isx_compute_batch_host.argtypes = [H, i, i, C.c_void_p, C.c_void_p, C.POINTER(Road), C.c_void_p,
                                            C.c_void_p, i, C.c_void_p]
     lib.isx_compute_batch_device.argtypes = [H, i, i, C.c_void_p, C.c_void_p, C.POINTER(Road)]
     lib.isx_synchronize.argtypes = [H]
+    lib.isx_flush.argtypes = [H]
     lib.isx_fetch_batch_results.argtypes = [H, i, C.c_void_p, C.c_void_p, i, C.c_void_p]
     lib.isx_stream.argtypes = [H]
     lib.isx_stream.restype = C.c_uint64

@@ -220,6 +220,10 @@ class Stixels:
         self._check(self._lib.isx_compute_batch_device(self._h, int(pairwise), n, d_disparity, d_segmentation,
                                                        _roads(roads)))
 
+    def Flush(self):
+        """Order the results of every enqueued batch before later work on stream(); asynchronous."""
+        self._check(self._lib.isx_flush(self._h))
+
     def Synchronize(self):
         self._check(self._lib.isx_synchronize(self._h))
 
@@ -338,6 +342,21 @@ class RoadEstimation:
         if tensor == 1:
             return out.reshape(rows, max_dis)
         return out.view(np.int32).reshape(-1, 2 * (rows + max_dis) + 3)
+
+
+def dbscan_fit(xy: np.ndarray, eps: float, min_pts: int, core_candidates: np.ndarray, device: int = 0) -> np.ndarray:
+    """The grouping step on one point set, i.e. the reference's
+    `ML::dbscanFit(handle, X, n, 2, eps, min_pts, labels, 0, false, core_candidates)` (Stixels.cu:660-666)."""
+    lib = L.load()
+    xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+    cand = np.ascontiguousarray(core_candidates, dtype=np.uint8)
+    if len(cand) != len(xy):
+        raise InvalidArgument("core_candidates must have one entry per point")
+    labels = np.full(len(xy), -1, dtype=np.int32)
+    rc = lib.isx_dbscan_fit_host(device, xy.ctypes.data, len(xy), eps, min_pts, cand.ctypes.data, labels.ctypes.data)
+    if rc != L.ISX_OK:
+        raise StixelsError(f"isx_dbscan_fit_host: {lib.isx_last_error(None).decode()} ({rc})")
+    return labels
 
 
 def make_stixels(preset: dict, max_batch: int = 1, device: int = 0) -> Stixels:

@@ -71,6 +71,7 @@ struct isx_context {
     float *pm = nullptr;
   } sets[2];
   int last_set = 0;
+  bool emit_join_pending = false;  // results of the last device batch are not yet ordered on s_compute
   isx_section *d_sections_all = nullptr;          // [max_batch][C][200]
   int *d_nsections_all = nullptr;                 // [max_batch][C]
   isx_instance *d_inst_all = nullptr;             // [max_batch][inst_cap]
@@ -297,8 +298,12 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
 // Results of every enqueued chunk become visible to work ordered after this on s_compute.
 static int join_emit_stream(isx_context *c) {
   ISX_TRY(c, cudaStreamWaitEvent(c->s_compute, c->ev_emit_done[c->last_set], 0));
+  c->emit_join_pending = false;
   return ISX_OK;
 }
+// isx_compute_batch_device leaves the join to whoever touches the results next (or to isx_flush), so that the
+// first kernels of a following batch do not wait for the emission tail of this one.
+static int ensure_joined(isx_context *c) { return c->emit_join_pending ? join_emit_stream(c) : ISX_OK; }
 
 static int check_ready(isx_context *c) {
   if (!c) return fail(nullptr, ISX_ERR_INVALID_ARGUMENT, "null handle");
@@ -642,6 +647,7 @@ int isx_set_road_parameters(isx_handle h, int vhor, float camera_tilt, float cam
 static int fetch_results(isx_handle h, int n, isx_section *sections, isx_instance *instances, int instances_capacity,
                          int32_t *instance_offsets, cudaStream_t s) {
   const size_t C = h->kp.realcols;
+  if (int rc = ensure_joined(h)) return rc;
   if (sections)
     ISX_TRY(h, cudaMemcpyAsync(sections, h->d_sections_all, sizeof(isx_section) * n * C * kMaxSections,
                                cudaMemcpyDeviceToHost, s));
@@ -704,6 +710,16 @@ int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_met
 
 int isx_cluster_instances(isx_handle h) { return check_ready(h); }
 
+int isx_dbscan_fit_host(int device, const float *xy, int n, float eps, int min_pts,
+                        const unsigned char *core_candidates, int *labels) {
+  if (n < 0 || (n > 0 && (!xy || !core_candidates || !labels)))
+    return fail(nullptr, ISX_ERR_INVALID_ARGUMENT, "isx_dbscan_fit_host: null argument");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, ISX_ERR_CUDA, "isx_dbscan_fit_host: no such CUDA device");
+  if (isx::dbscan_fit_host(xy, n, eps, min_pts, core_candidates, labels) != 0)
+    return fail(nullptr, ISX_ERR_CUDA, "isx_dbscan_fit_host: CUDA error");
+  return ISX_OK;
+}
+
 int isx_get_instance_stixels(isx_handle h, isx_instance *out, int capacity, int *n) {
   if (int rc = check_ready(h)) return rc;
   if (h->last_batch < 1) return fail(h, ISX_ERR_INVALID_ARGUMENT, "Compute has not been called");
@@ -730,14 +746,20 @@ int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_d
     ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_compute));
     slot ^= 1;
   }
-  if (int rc = join_emit_stream(h)) return rc;
+  h->emit_join_pending = true;  // joined lazily: isx_flush / isx_synchronize / any result access
   h->last_batch = n;
   h->last_roads.assign(roads, roads + n);
   return ISX_OK;
 }
 
+int isx_flush(isx_handle h) {
+  if (int rc = check_ready(h)) return rc;
+  return ensure_joined(h);
+}
+
 int isx_synchronize(isx_handle h) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = ensure_joined(h)) return rc;
   ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
   return ISX_OK;
 }
@@ -799,6 +821,7 @@ int isx_rasterize_batch_device(isx_handle h, int first, int n, uint8_t *d_label_
   if (first < 0 || n < 1 || first + n > h->last_batch)
     return fail(h, ISX_ERR_INVALID_ARGUMENT, "frames outside the last computed batch");
   if (!d_label_ids && !d_instance_ids && !d_disparity) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no output image");
+  if (int rc = ensure_joined(h)) return rc;
   const size_t C = h->kp.realcols;
   launch_rasterize(h->kp, h->d_sections_all + (size_t)first * C * kMaxSections, h->d_nsections_all + (size_t)first * C,
                    h->d_inst_all + (size_t)first * h->inst_cap, h->d_inst_count_all + first, h->inst_cap,
@@ -835,6 +858,7 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
   const int local = frame - h->last_chunk_first;
   if (local < 0 || local >= h->last_chunk_n)
     return fail(h, ISX_ERR_INVALID_ARGUMENT, "intermediates are only kept for the last chunk of the last batch");
+  if (int rc = ensure_joined(h)) return rc;
   ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
   const KParams &kp = h->kp;
   const size_t H = kp.rows, C = kp.realcols, D = kp.max_dis;

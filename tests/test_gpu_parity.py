@@ -173,6 +173,26 @@ def test_device_resident_entry_point_matches_host_entry_point():
     assert np.array_equal(inst_h.view(np.uint8), inst_d.view(np.uint8))
     # unlike the reference (StixelsKernels.cu:411-416, 462-469) the borrowed tensor is not modified
     assert np.array_equal(d_seg.cpu().numpy(), before)
+    # back-to-back device batches (the emission stream is joined lazily): the results fetched afterwards are
+    # those of the LAST batch, whichever entry point touches them first (fetch / flush + own stream work)
+    disp2, seg2, roads2 = synth.make_batch(n, start=11, rows=rows, cols=cols)
+    sec_h2, inst_h2, _ = st.ComputeBatch(False, disp2, seg2, roads2)
+    d_disp2, d_seg2 = torch.from_numpy(disp2).cuda(), torch.from_numpy(seg2).cuda()
+    for _ in range(3):
+        st.ComputeBatchDevice(False, n, d_disp.data_ptr(), d_seg.data_ptr(), roads)
+        st.ComputeBatchDevice(False, n, d_disp2.data_ptr(), d_seg2.data_ptr(), roads2)
+    sec_d2, inst_d2, _ = st.FetchBatchResults(n)
+    assert all(parity.same_used_sections(sec_h2[f], sec_d2[f]) for f in range(n))
+    assert np.array_equal(inst_h2.view(np.uint8), inst_d2.view(np.uint8))
+    st.ComputeBatchDevice(False, n, d_disp.data_ptr(), d_seg.data_ptr(), roads)
+    st.Flush()
+    stream = torch.cuda.ExternalStream(st.stream())
+    with torch.cuda.stream(stream):
+        marker = torch.zeros(1, device="cuda") + 1   # caller's own work on isx_stream(), ordered after the results
+    stream.synchronize()
+    sec_d3, inst_d3, _ = st.FetchBatchResults(n)
+    assert all(parity.same_used_sections(sec_h[f], sec_d3[f]) for f in range(n)) and float(marker.item()) == 1.0
+    assert np.array_equal(inst_h.view(np.uint8), inst_d3.view(np.uint8))
     st.Finish()
 
 
