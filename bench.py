@@ -269,42 +269,35 @@ def main():
     ms_max = float(t.item())
 
     # ---- e2e: host buffers through the public batch API, copies inside the timed region ----
-    # E2E_WORKERS host worker threads, one Stixels context each, take alternate batches: the head (first H2D)
-    # and the tail (last emission + D2H, result fetch) of one batch hide behind the kernels of the others, the
-    # way a multi-buffered streaming caller drives the library.  The threads start staggered by a fraction of a
-    # batch: streams of equal work share the GPU evenly, so batches started together would also end together.
-    # Every step still moves its own inputs from pinned host memory and reads its own results back.
-    # e2e_single is one context, one thread.
-    E2E_WORKERS = 4
-    sections_host = [torch.empty((B, C_, 200, 32), dtype=torch.uint8).pin_memory() for _ in range(E2E_WORKERS)]
+    # One host thread, one context, the streaming form of the batch call: isx_submit_batch_host enqueues a batch
+    # (H2D of its inputs from pinned memory, kernels, D2H of all Sections and instance records) and
+    # isx_wait_batch_host delivers the oldest one; two batches are in flight, so the first copy and the last
+    # emission + copy-out of one batch hide behind the kernels of the other.  Every step moves its own inputs and
+    # reads its own results back.  e2e_single is the synchronous call (isx_compute_batch_host), one batch at a time.
+    sections_host = [torch.empty((B, C_, 200, 32), dtype=torch.uint8).pin_memory() for _ in range(2)]
     sec_np = [t.numpy().view(api.L.SECTION_DTYPE).reshape(B, C_, 200) for t in sections_host]
-    workers = [st] + [api.make_stixels(pre, max_batch=B, device=local) for _ in range(E2E_WORKERS - 1)]
-    n_inst_seen = [0] * E2E_WORKERS
-    step_s = ms_max * 1e-3 / args.steps
+    n_inst_seen = [0]
 
-    def host_step(w):
-        _, inst, _ = workers[w].ComputeBatch(pairwise, h_disp.numpy(), h_seg.numpy(), roads, sections_out=sec_np[w])
-        n_inst_seen[w] = len(inst)
-
-    def run_e2e(nworkers):
-        for w in range(nworkers):
-            host_step(w)
+    def run_e2e(pipelined):
+        for w in range(2):  # warm-up of the path that is timed (the second result set is allocated on first use)
+            if pipelined:
+                st.SubmitBatch(pairwise, h_disp.numpy(), h_seg.numpy(), roads, sec_np[w])
+                st.WaitBatch()
+            else:
+                st.ComputeBatch(pairwise, h_disp.numpy(), h_seg.numpy(), roads, sections_out=sec_np[w])
         barrier()
         t0 = time.perf_counter()
-        if nworkers == 1:
+        if not pipelined:
             for _ in range(args.steps):
-                host_step(0)
+                _, inst, _ = st.ComputeBatch(pairwise, h_disp.numpy(), h_seg.numpy(), roads, sections_out=sec_np[0])
+                n_inst_seen[0] = len(inst)
         else:
-            def loop(w):
-                torch.cuda.set_device(local)
-                time.sleep(step_s * w / nworkers)   # inside the timed region
-                for _ in range(w, args.steps, nworkers):
-                    host_step(w)
-            ths = [threading.Thread(target=loop, args=(w,)) for w in range(nworkers)]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
+            for i in range(args.steps):
+                st.SubmitBatch(pairwise, h_disp.numpy(), h_seg.numpy(), roads, sec_np[i & 1])
+                if i > 0:
+                    _, inst, _ = st.WaitBatch()
+                    n_inst_seen[0] = len(inst)
+            _, inst, _ = st.WaitBatch()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -312,11 +305,9 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    e2e_single_s = run_e2e(1)
-    e2e_s = run_e2e(E2E_WORKERS)
+    e2e_single_s = run_e2e(False)
+    e2e_s = run_e2e(True)
     n_inst = n_inst_seen[0]
-    for w in workers[1:]:
-        w.Finish()
 
     if rank == 0:
         peaks = measured_peaks()
@@ -347,8 +338,8 @@ def main():
                         l2="inputs (890 MB/step) and tables (>2 GB/chunk) exceed the 126 MB L2"),
             e2e=dict(value=world * B * args.steps / e2e_s, unit="frames/s",
                      h2d_bytes_per_step=int(h_disp.numel() * 4 + h_seg.numel() * 4),
-                     d2h_bytes_per_step=int(sections_host[0].numel() + n_inst * 16 + B * 4),
-                     pipeline=f"{E2E_WORKERS} host threads x 1 context, alternate batches, staggered start"),
+                     d2h_bytes_per_step=int(sections_host[0].numel() + B * st.instance_capacity() * 16 + B * 4 + 4),
+                     pipeline="1 host thread, isx_submit_batch_host / isx_wait_batch_host, 2 batches in flight"),
             e2e_single=dict(value=world * B * args.steps / e2e_single_s, unit="frames/s",
                             pipeline="1 host thread, 1 context, synchronous batches"),
             gpu_launches=int(launches),

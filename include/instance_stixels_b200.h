@@ -220,6 +220,16 @@ int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *dispa
 int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_disparity,
                              const int32_t *d_segmentation, const isx_road *roads);
 int isx_synchronize(isx_handle h);
+/* Asynchronous form of isx_compute_batch_host for a streaming caller: isx_submit_batch_host enqueues the
+ * copies and kernels of one batch (same arguments, same layouts) and returns once they are queued;
+ * isx_wait_batch_host waits for the OLDEST batch in flight, after which that batch's `sections` buffer is
+ * complete, and delivers its packed instance records.  At most two batches may be in flight per handle
+ * (submit, submit, wait, submit, wait, ...): the head and tail of one batch then hide behind the kernels of
+ * the other.  `disparity`, `segmentation` and `sections` must stay valid (and should be pinned) until the
+ * batch has been waited for.  The synchronous entry points refuse to run while batches are in flight. */
+int isx_submit_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
+                          const isx_road *roads, isx_section *sections);
+int isx_wait_batch_host(isx_handle h, isx_instance *instances, int instances_capacity, int32_t *instance_offsets);
 /* Copy results of the last device batch to host buffers (same layouts as
  * isx_compute_batch_host). */
 int isx_fetch_batch_results(isx_handle h, int n, isx_section *sections, isx_instance *instances,
@@ -259,6 +269,8 @@ int isx_set_profiling(isx_handle h, int enable);
 int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, int reset);
 /* Frames per kernel launch (batches are cut into chunks of this many frames). */
 int isx_chunk_frames(isx_handle h);
+/* instance records per frame the packed result arrays hold (isx_submit_batch_host copies that many per frame) */
+int isx_instance_capacity(isx_handle h);
 size_t isx_tensor_elems(isx_handle h, int tensor);
 int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t bytes);
 

@@ -205,6 +205,32 @@ class Stixels:
             return sections_out, np.zeros(0, dtype=L.INSTANCE_DTYPE), np.zeros(n + 1, dtype=np.int32)
         return sections_out, inst[:offs[n]].copy(), offs.copy()
 
+    def SubmitBatch(self, pairwise: bool, disparity: np.ndarray, segmentation: np.ndarray, roads: Sequence[dict],
+                    sections_out: np.ndarray):
+        """Asynchronous ComputeBatch: enqueue one batch (host buffers, which must stay alive and unchanged until
+        the matching WaitBatch) and return.  At most two batches in flight."""
+        n = len(roads)
+        if disparity.dtype != np.float32 or segmentation.dtype != np.int32 or \
+                not disparity.flags.c_contiguous or not segmentation.flags.c_contiguous:
+            raise InvalidArgument("SubmitBatch needs C-contiguous float32 / int32 arrays (no hidden copies)")
+        self._check(self._lib.isx_submit_batch_host(self._h, int(pairwise), n, disparity.ctypes.data,
+                                                    segmentation.ctypes.data, _roads(roads),
+                                                    sections_out.ctypes.data))
+        self._in_flight = getattr(self, "_in_flight", [])
+        self._in_flight.append((n, disparity, segmentation, sections_out))
+
+    def WaitBatch(self, want_instances: bool = True):
+        """Wait for the oldest submitted batch; returns (sections, instances, offsets) like ComputeBatch."""
+        if not getattr(self, "_in_flight", None):
+            raise InvalidArgument("no submitted batch is in flight")
+        n, _, _, sections_out = self._in_flight.pop(0)
+        inst, offs, cap = self._instance_buffers(n) if want_instances else (None, None, 0)
+        self._check(self._lib.isx_wait_batch_host(self._h, inst.ctypes.data if want_instances else None, cap,
+                                                  offs.ctypes.data if want_instances else None))
+        if not want_instances:
+            return sections_out, np.zeros(0, dtype=L.INSTANCE_DTYPE), np.zeros(n + 1, dtype=np.int32)
+        return sections_out, inst[:offs[n]].copy(), offs.copy()
+
     def _instance_buffers(self, n: int):
         """Reusable result buffers for the packed instance records of a batch of n frames."""
         cap = 16384 * n
@@ -252,6 +278,9 @@ class Stixels:
 
     def chunk_frames(self) -> int:
         return self._lib.isx_chunk_frames(self._h)
+
+    def instance_capacity(self) -> int:
+        return self._lib.isx_instance_capacity(self._h)
 
     def stream(self) -> int:
         return self._lib.isx_stream(self._h)

@@ -87,6 +87,22 @@ struct isx_context {
   isx_instance *h_inst = nullptr;                 // [max_batch][inst_cap]
   int *h_inst_count = nullptr;                    // [max_batch]
   int *h_error = nullptr;
+  // isx_submit_batch_host keeps up to two batches in flight: the result arrays above (device and pinned host) are
+  // the CURRENT set; the other one lives here and the two are swapped at every submit.
+  struct ResultSet {
+    isx_section *d_sections = nullptr;
+    int *d_nsections = nullptr;
+    isx_instance *d_inst = nullptr;
+    int *d_inst_count = nullptr;
+    isx_instance *h_inst = nullptr;
+    int *h_inst_count = nullptr;
+    int *h_error = nullptr;
+  } other_results;
+  bool other_results_allocated = false;
+  cudaEvent_t ev_batch_done[2] = {nullptr, nullptr};  // by ticket parity
+  int batch_n[2] = {0, 0};                            // frames of the batch in flight with that parity, 0 = none
+  unsigned long long submitted = 0, waited = 0;       // tickets: batches [waited, submitted) are in flight
+  int host_slot = 0;                                  // input slot / chunk set of the next host chunk (alternates across batches)
 
   std::map<isx::RoadKey, std::vector<float>> road_cache;
   isx_road single_road{0, 0.f, 0.f, 0.f};
@@ -568,6 +584,18 @@ int isx_finish(isx_handle h) {
   cudaFreeHost(h->h_inst);
   cudaFreeHost(h->h_inst_count);
   cudaFreeHost(h->h_error);
+  if (h->other_results_allocated) {
+    cudaFreeHost(h->other_results.h_inst);
+    cudaFreeHost(h->other_results.h_inst_count);
+    cudaFreeHost(h->other_results.h_error);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(h->ev_batch_done[i]);
+    h->other_results = isx_context::ResultSet();
+    h->other_results_allocated = false;
+  }
+  h->submitted = h->waited = 0;
+  h->host_slot = 0;
+  h->batch_n[0] = h->batch_n[1] = 0;
+  h->emit_join_pending = false;
   for (int i = 0; i < 2; i++) {
     cudaEventDestroy(h->ev_in_ready[i]);
     cudaEventDestroy(h->ev_in_free[i]);
@@ -644,6 +672,9 @@ int isx_set_road_parameters(isx_handle h, int vhor, float camera_tilt, float cam
   return ISX_OK;
 }
 
+static int deliver_instances(isx_handle h, int n, isx_instance *instances, int instances_capacity,
+                             int32_t *instance_offsets);
+static int no_batches_in_flight(isx_handle h);
 static int fetch_results(isx_handle h, int n, isx_section *sections, isx_instance *instances, int instances_capacity,
                          int32_t *instance_offsets, cudaStream_t s) {
   const size_t C = h->kp.realcols;
@@ -666,33 +697,14 @@ static int fetch_results(isx_handle h, int n, isx_section *sections, isx_instanc
       ISX_TRY(h, cudaStreamSynchronize(s));
     }
   }
-  if (*h->h_error & kErrOffsetRange)
-    return fail(h, ISX_ERR_UNSUPPORTED,
-                "instance offsets out of range: |sum of instance means| of a column must stay below 2^24");
-  if (*h->h_error) return fail(h, ISX_ERR_CAPACITY, "a column produced >= 200 stixels (MAX_STIXELS_PER_COLUMN)");
-  if (instances || instance_offsets) {
-    int total = 0;
-    for (int f = 0; f < n; f++) {
-      if (instance_offsets) instance_offsets[f] = total;
-      const int cnt = h->h_inst_count[f] < h->inst_cap ? h->h_inst_count[f] : h->inst_cap;
-      if (h->h_inst_count[f] > h->inst_cap)
-        return fail(h, ISX_ERR_CAPACITY, "more instance stixels in one frame than the packed result can hold");
-      if (instances) {
-        const int room = instances_capacity - total;
-        const int take = cnt < room ? cnt : (room > 0 ? room : 0);
-        std::memcpy(instances + total, h->h_inst + (size_t)f * h->inst_cap, sizeof(isx_instance) * take);
-      }
-      total += cnt;
-    }
-    if (instance_offsets) instance_offsets[n] = total;
-  }
-  return ISX_OK;
+  return deliver_instances(h, n, instances, instances_capacity, instance_offsets);
 }
 
 int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_meta *meta,
                 const int32_t *d_segmentation_local) {
   if (int rc = check_ready(h)) return rc;
   if (!h->single_has_road) return fail(h, ISX_ERR_INVALID_ARGUMENT, "SetRoadParameters has not been called");
+  if (int rc = no_batches_in_flight(h)) return rc;
   const int32_t *seg = d_segmentation_local ? d_segmentation_local : h->d_single_seg;
   if (int rc = enqueue_chunk(h, pairwise != 0, 0, 1, h->d_single_disp, seg, &h->single_road, 0)) return rc;
   if (int rc = join_emit_stream(h)) return rc;
@@ -732,10 +744,11 @@ int isx_get_instance_stixels(isx_handle h, isx_instance *out, int capacity, int 
 int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_disparity,
                              const int32_t *d_segmentation, const isx_road *roads) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = no_batches_in_flight(h)) return rc;
   if (n < 1 || n > h->max_batch) return fail(h, ISX_ERR_CAPACITY, "batch size exceeds isx_initialize(max_batch)");
   if (!d_disparity || !d_segmentation || !roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
   const size_t hw = (size_t)h->kp.rows * h->kp.cols, se = seg_elems(h);
-  int slot = 0;
+  int slot = h->host_slot;  // keeps alternating across batches (see enqueue_host_batch)
   for (int first = 0; first < n; first += h->chunk) {
     const int cn = (n - first) < h->chunk ? (n - first) : h->chunk;
     // the pinned ground staging half must not be rewritten while its copy is in flight
@@ -746,6 +759,7 @@ int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_d
     ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_compute));
     slot ^= 1;
   }
+  h->host_slot = slot;
   h->emit_join_pending = true;  // joined lazily: isx_flush / isx_synchronize / any result access
   h->last_batch = n;
   h->last_roads.assign(roads, roads + n);
@@ -771,20 +785,21 @@ int isx_fetch_batch_results(isx_handle h, int n, isx_section *sections, isx_inst
   return fetch_results(h, n, sections, instances, instances_capacity, instance_offsets, h->s_compute);
 }
 
-int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
-                           const isx_road *roads, isx_section *sections, isx_instance *instances,
-                           int instances_capacity, int32_t *instance_offsets) {
-  if (int rc = check_ready(h)) return rc;
-  if (n < 1 || n > h->max_batch) return fail(h, ISX_ERR_CAPACITY, "batch size exceeds isx_initialize(max_batch)");
-  if (!disparity || !segmentation || !roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+// The copy/kernel pipeline of one host batch: H2D on s_h2d, kernels on s_compute / s_emit, D2H of the sections
+// chunk by chunk on s_d2h.  Blocks the caller only for the reuse of an input slot (two chunks behind).
+static int enqueue_host_batch(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
+                              const isx_road *roads, isx_section *sections) {
   const size_t hw = (size_t)h->kp.rows * h->kp.cols, se = seg_elems(h);
   const size_t C = h->kp.realcols;
-  int slot = 0;
+  // The slots keep alternating across batches, so that the first copy of a pipelined batch only waits for the
+  // second-to-last chunk of the batch before it.
+  int slot = h->host_slot;
   int cn = 0;
+  const bool pipeline_idle = h->submitted == h->waited;
   for (int first = 0; first < n; first += cn) {
     cn = (n - first) < h->chunk ? (n - first) : h->chunk;
-    // a short first chunk: its copy is the only one that no kernel hides
-    if (first == 0 && n > h->chunk && h->chunk >= 8) cn = h->chunk / 4;
+    // a short first chunk when nothing is running: its copy is the only one that no kernel hides
+    if (first == 0 && pipeline_idle && n > h->chunk && h->chunk >= 8) cn = h->chunk / 4;
     // H2D of this chunk on the copy stream, once the kernels that last read this slot are done
     ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_in_free[slot], 0));
     ISX_TRY(h, cudaMemcpyAsync(h->d_in_disp[slot], disparity + first * hw, sizeof(float) * hw * cn,
@@ -807,12 +822,123 @@ int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *dispa
     }
     slot ^= 1;
   }
-  if (int rc = join_emit_stream(h)) return rc;
+  h->host_slot = slot;
   h->last_batch = n;
   h->last_roads.assign(roads, roads + n);
+  return ISX_OK;
+}
+
+// Error flag + packed instance records of n frames from the pinned copies (h_error, h_inst_count, h_inst).
+static int deliver_instances(isx_handle h, int n, isx_instance *instances, int instances_capacity,
+                             int32_t *instance_offsets) {
+  if (*h->h_error & kErrOffsetRange)
+    return fail(h, ISX_ERR_UNSUPPORTED,
+                "instance offsets out of range: |sum of instance means| of a column must stay below 2^24");
+  if (*h->h_error) return fail(h, ISX_ERR_CAPACITY, "a column produced >= 200 stixels (MAX_STIXELS_PER_COLUMN)");
+  if (instances || instance_offsets) {
+    int total = 0;
+    for (int f = 0; f < n; f++) {
+      if (instance_offsets) instance_offsets[f] = total;
+      const int cnt = h->h_inst_count[f] < h->inst_cap ? h->h_inst_count[f] : h->inst_cap;
+      if (h->h_inst_count[f] > h->inst_cap)
+        return fail(h, ISX_ERR_CAPACITY, "more instance stixels in one frame than the packed result can hold");
+      if (instances) {
+        const int room = instances_capacity - total;
+        const int take = cnt < room ? cnt : (room > 0 ? room : 0);
+        std::memcpy(instances + total, h->h_inst + (size_t)f * h->inst_cap, sizeof(isx_instance) * take);
+      }
+      total += cnt;
+    }
+    if (instance_offsets) instance_offsets[n] = total;
+  }
+  return ISX_OK;
+}
+
+static int no_batches_in_flight(isx_handle h) {
+  if (h->submitted != h->waited)
+    return fail(h, ISX_ERR_INVALID_ARGUMENT, "submitted batches are in flight: call isx_wait_batch_host first");
+  return ISX_OK;
+}
+
+int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
+                           const isx_road *roads, isx_section *sections, isx_instance *instances,
+                           int instances_capacity, int32_t *instance_offsets) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = no_batches_in_flight(h)) return rc;
+  if (n < 1 || n > h->max_batch) return fail(h, ISX_ERR_CAPACITY, "batch size exceeds isx_initialize(max_batch)");
+  if (!disparity || !segmentation || !roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  if (int rc = enqueue_host_batch(h, pairwise, n, disparity, segmentation, roads, sections)) return rc;
+  if (int rc = join_emit_stream(h)) return rc;
   if (int rc = fetch_results(h, n, nullptr, instances, instances_capacity, instance_offsets, h->s_compute)) return rc;
   ISX_TRY(h, cudaStreamSynchronize(h->s_d2h));
   return ISX_OK;
+}
+
+// Swap the current result arrays with the other set (allocated on first use).
+static int swap_result_sets(isx_handle h) {
+  isx_context::ResultSet &o = h->other_results;
+  if (!h->other_results_allocated) {
+    const size_t C = h->kp.realcols, MB = h->max_batch;
+    ISX_TRY(h, dev_alloc(h, &o.d_sections, MB * C * kMaxSections));
+    ISX_TRY(h, cudaMemset(o.d_sections, 0, MB * C * kMaxSections * sizeof(isx_section)));
+    ISX_TRY(h, dev_alloc(h, &o.d_nsections, MB * C));
+    ISX_TRY(h, dev_alloc(h, &o.d_inst, MB * (size_t)h->inst_cap));
+    ISX_TRY(h, dev_alloc(h, &o.d_inst_count, MB));
+    ISX_TRY(h, cudaMallocHost(&o.h_inst, sizeof(isx_instance) * MB * h->inst_cap));
+    ISX_TRY(h, cudaMallocHost(&o.h_inst_count, sizeof(int) * MB));
+    ISX_TRY(h, cudaMallocHost(&o.h_error, sizeof(int)));
+    for (int i = 0; i < 2; i++) ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_batch_done[i], cudaEventDisableTiming));
+    h->other_results_allocated = true;
+  }
+  std::swap(o.d_sections, h->d_sections_all);
+  std::swap(o.d_nsections, h->d_nsections_all);
+  std::swap(o.d_inst, h->d_inst_all);
+  std::swap(o.d_inst_count, h->d_inst_count_all);
+  std::swap(o.h_inst, h->h_inst);
+  std::swap(o.h_inst_count, h->h_inst_count);
+  std::swap(o.h_error, h->h_error);
+  return ISX_OK;
+}
+
+int isx_submit_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
+                          const isx_road *roads, isx_section *sections) {
+  if (int rc = check_ready(h)) return rc;
+  if (n < 1 || n > h->max_batch) return fail(h, ISX_ERR_CAPACITY, "batch size exceeds isx_initialize(max_batch)");
+  if (!disparity || !segmentation || !roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  if (h->submitted - h->waited >= 2)
+    return fail(h, ISX_ERR_CAPACITY, "two batches are already in flight: call isx_wait_batch_host first");
+  // the set that becomes current was delivered by the wait before last (or never used)
+  if (int rc = swap_result_sets(h)) return rc;
+  if (int rc = enqueue_host_batch(h, pairwise, n, disparity, segmentation, roads, sections)) return rc;
+  // everything the wait delivers, on the copy-out stream behind the last emission: counts, error flag and the
+  // whole record array of every frame (the used part is only known on the device)
+  const int par = (int)(h->submitted & 1);
+  ISX_TRY(h, cudaStreamWaitEvent(h->s_d2h, h->ev_emit_done[h->last_set], 0));
+  ISX_TRY(h, cudaMemcpyAsync(h->h_inst_count, h->d_inst_count_all, sizeof(int) * n, cudaMemcpyDeviceToHost, h->s_d2h));
+  ISX_TRY(h, cudaMemcpyAsync(h->h_error, h->buf.error_flag, sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
+  ISX_TRY(h, cudaMemcpyAsync(h->h_inst, h->d_inst_all, sizeof(isx_instance) * (size_t)n * h->inst_cap,
+                             cudaMemcpyDeviceToHost, h->s_d2h));
+  ISX_TRY(h, cudaEventRecord(h->ev_batch_done[par], h->s_d2h));
+  h->batch_n[par] = n;
+  h->submitted++;
+  h->emit_join_pending = true;  // s_compute itself has not been ordered behind the emission stream
+  return ISX_OK;
+}
+
+int isx_wait_batch_host(isx_handle h, isx_instance *instances, int instances_capacity, int32_t *instance_offsets) {
+  if (int rc = check_ready(h)) return rc;
+  if (h->submitted == h->waited) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no submitted batch is in flight");
+  const int par = (int)(h->waited & 1);
+  ISX_TRY(h, cudaEventSynchronize(h->ev_batch_done[par]));
+  const int n = h->batch_n[par];
+  h->batch_n[par] = 0;
+  h->waited++;
+  // the oldest batch's pinned copies are the current set's when it is the only one in flight, else the other set's
+  const bool in_other = h->submitted != h->waited;
+  if (in_other) swap_result_sets(h);
+  const int rc = deliver_instances(h, n, instances, instances_capacity, instance_offsets);
+  if (in_other) swap_result_sets(h);
+  return rc;
 }
 
 int isx_rasterize_batch_device(isx_handle h, int first, int n, uint8_t *d_label_ids, int32_t *d_instance_ids,
@@ -937,5 +1063,6 @@ int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, in
 }
 
 int isx_chunk_frames(isx_handle h) { return (h && h->initialized) ? h->chunk : 0; }
+int isx_instance_capacity(isx_handle h) { return (h && h->initialized) ? h->inst_cap : 0; }
 
 }  // extern "C"

@@ -196,6 +196,53 @@ def test_device_resident_entry_point_matches_host_entry_point():
     st.Finish()
 
 
+def test_submit_wait_pipeline_equals_synchronous_batches():
+    """isx_submit_batch_host / isx_wait_batch_host: two batches in flight, results in submission order and
+    identical to the synchronous entry point; misuse is refused."""
+    rows, cols, n = 128, 256, 5
+    pre = _preset("pairwise", rows, cols, 8, 0.0, False)
+    import os
+    os.environ["ISX_CHUNK"] = "2"      # several chunks per batch, short first chunk logic aside
+    try:
+        st = api.make_stixels(pre, max_batch=8)
+    finally:
+        del os.environ["ISX_CHUNK"]
+    batches = [synth.make_batch(n, start=s0, rows=rows, cols=cols) for s0 in (0, 7, 14, 21)]
+    want = []
+    for disp, seg, roads in batches:
+        sec, inst, offs = st.ComputeBatch(True, disp, seg, roads)
+        want.append((sec.copy(), inst.copy(), offs.copy()))
+    C_, S = st.GetRealCols(), st.GetMaxSections()
+    outs = [np.zeros((n, C_, S), dtype=api.L.SECTION_DTYPE) for _ in batches]
+    got = []
+    with pytest.raises(api.InvalidArgument):
+        st.WaitBatch()
+    for rep in range(2):                # the second round reuses both result sets
+        got.clear()
+        for i, (disp, seg, roads) in enumerate(batches):
+            st.SubmitBatch(True, disp, seg, roads, outs[i])
+            if i == 1:
+                with pytest.raises(api.StixelsError):   # a third batch in flight
+                    st.SubmitBatch(True, disp, seg, roads, outs[i])
+                with pytest.raises(api.InvalidArgument):  # synchronous call while batches are in flight
+                    st.ComputeBatch(True, disp, seg, roads)
+            if i >= 1:
+                sec, inst, offs = st.WaitBatch()
+                got.append((sec.copy(), inst, offs))
+        sec, inst, offs = st.WaitBatch()
+        got.append((sec.copy(), inst, offs))
+        assert len(got) == len(batches)
+        for i, ((ws, wi, wo), (gs, gi, go)) in enumerate(zip(want, got)):
+            assert all(parity.same_used_sections(ws[f], gs[f]) for f in range(n)), (rep, i)
+            assert np.array_equal(wo, go) and np.array_equal(wi.view(np.uint8), gi.view(np.uint8)), (rep, i)
+    # back to the synchronous calls once nothing is in flight
+    sec, inst, offs = st.ComputeBatch(True, *batches[2])
+    assert np.array_equal(inst.view(np.uint8), want[2][1].view(np.uint8))
+    st.SetDisparityImage(batches[0][0][0]); st.SetSegmentation(batches[0][1][0]); st.SetRoadParameters(**batches[0][2][0])
+    assert parity.same_used_sections(st.Compute(True).sections, want[0][0][0])
+    st.Finish()
+
+
 def test_fewer_rows_than_disparities_against_cpu_oracle():
     """rows < max_dis: the reference kernel only fills object_disparity_range[0..rows) of its shared
     copy (StixelsKernels.cu:378-380, one thread per row), so its own results depend on uninitialised
