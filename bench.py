@@ -360,19 +360,26 @@ def main():
             stage_ms_per_step={k: v[0] / args.steps for k, v in stages.items()},
         )
         if not args.no_extra and world == 1:
-            # p50 latency of one frame through the reference call sequence (host in -> host out)
-            lat = []
+            # p50 latency of one frame through the reference call sequence (host in -> host out), with the
+            # caller's buffers in pinned memory and -- like the reference's callers -- in pageable memory
             fr = synth.make_frame(0, rows=ROWS, cols=COLS, column_step=wl["step"])
-            for i in range(25):
+            pin = [torch.from_numpy(fr.disparity).pin_memory(), torch.from_numpy(fr.segmentation).pin_memory(),
+                   torch.empty(C_ * 200 * 32, dtype=torch.uint8).pin_memory()]
+
+            def one_frame(disp, seg, out):
                 t0 = time.perf_counter()
-                st.SetDisparityImage(fr.disparity)
-                st.SetSegmentation(fr.segmentation)
+                st.SetDisparityImage(disp)
+                st.SetSegmentation(seg)
                 st.SetRoadParameters(**fr.road)
-                st.Compute(pairwise)
+                st.Compute(pairwise, sections_out=out)
                 st.GetInstanceStixels()
-                lat.append(1e3 * (time.perf_counter() - t0))
-            lat = sorted(lat[3:])
-            line["latency_ms_batch1"] = dict(p50=lat[len(lat) // 2], p99=lat[-1])
+                return 1e3 * (time.perf_counter() - t0)
+
+            lat = sorted([one_frame(pin[0].numpy(), pin[1].numpy(), pin[2].numpy().view(api.L.SECTION_DTYPE))
+                          for _ in range(43)][3:])
+            lat_pageable = sorted([one_frame(fr.disparity, fr.segmentation, None) for _ in range(23)][3:])
+            line["latency_ms_batch1"] = dict(p50=lat[len(lat) // 2], p99=lat[-1], buffers="pinned",
+                                             p50_pageable=lat_pageable[len(lat_pageable) // 2])
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl, 24)
         print(json.dumps(line), flush=True)

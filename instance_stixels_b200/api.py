@@ -161,10 +161,17 @@ class Stixels:
         self._check(self._lib.isx_set_model_parameters(self._h, column_step, int(median_join), epsilon,
                                                        range_objects_z, width_margin))
 
-    def Compute(self, pairwise: bool, d_segmentation_local: Optional[int] = None) -> StixelsData:
-        """Returns the StixelsData the reference fills through its out-parameter."""
+    def Compute(self, pairwise: bool, d_segmentation_local: Optional[int] = None,
+                sections_out: Optional[np.ndarray] = None) -> StixelsData:
+        """Returns the StixelsData the reference fills through its out-parameter.  `sections_out`: an optional
+        caller-owned buffer of realcols*max_sections Sections (e.g. pinned) to fill instead of a new array."""
         n = self.GetRealCols() * self.GetMaxSections()
-        sections = np.zeros(n, dtype=L.SECTION_DTYPE)
+        if sections_out is not None:
+            sections = sections_out.reshape(-1)
+            if sections.dtype != L.SECTION_DTYPE or sections.size != n or not sections.flags.c_contiguous:
+                raise InvalidArgument("sections_out must hold realcols*max_sections contiguous Sections")
+        else:
+            sections = np.zeros(n, dtype=L.SECTION_DTYPE)
         meta = L.FrameMeta()
         self._check(self._lib.isx_compute(self._h, int(pairwise), sections.ctypes.data, C.byref(meta),
                                           d_segmentation_local))

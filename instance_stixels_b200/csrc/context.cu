@@ -727,7 +727,9 @@ int isx_dbscan_fit_host(int device, const float *xy, int n, float eps, int min_p
   if (n < 0 || (n > 0 && (!xy || !core_candidates || !labels)))
     return fail(nullptr, ISX_ERR_INVALID_ARGUMENT, "isx_dbscan_fit_host: null argument");
   if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, ISX_ERR_CUDA, "isx_dbscan_fit_host: no such CUDA device");
-  if (isx::dbscan_fit_host(xy, n, eps, min_pts, core_candidates, labels) != 0)
+  // both launch shapes of the kernel (ISX_GROUP_THREADS=256: the batch shape; default: the single-frame shape)
+  const char *e = std::getenv("ISX_GROUP_THREADS");
+  if (isx::dbscan_fit_host(xy, n, eps, min_pts, core_candidates, labels, e ? std::atoi(e) : 1024) != 0)
     return fail(nullptr, ISX_ERR_CUDA, "isx_dbscan_fit_host: CUDA error");
   return ISX_OK;
 }

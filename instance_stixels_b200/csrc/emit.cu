@@ -20,11 +20,18 @@ struct Rec {
   uint32_t w[kRecWords];
 };
 
-// rec = records of this column, word-major with row stride Hp (common.cuh)
-__device__ __forceinline__ Rec load_rec(const uint32_t *rec, int Hp, int v) {
+// rec = row-major records of this column (records_b, common.cuh): one 128-byte line per row
+__device__ __forceinline__ Rec load_rec(const uint32_t *rec, int v) {
   Rec r;
+  const uint4 *row = reinterpret_cast<const uint4 *>(rec + (size_t)v * kRecBWords);
 #pragma unroll
-  for (int k = 0; k < kRecWords; k++) r.w[k] = __ldg(rec + (size_t)k * Hp + v);
+  for (int g = 0; g < (kRecWords + 3) / 4; g++) {
+    const uint4 t = __ldg(row + g);
+    r.w[4 * g] = t.x;
+    r.w[4 * g + 1] = t.y;
+    if (4 * g + 2 < kRecWords) r.w[4 * g + 2] = t.z;
+    if (4 * g + 3 < kRecWords) r.w[4 * g + 3] = t.w;
+  }
   return r;
 }
 
@@ -85,8 +92,12 @@ __device__ int predecessor_type(int type, int vB, float fn_clamped, const float4
   }
 }
 
+// One thread per column, 32 columns per CTA: the per-stixel record loads of a warp touch 32 different lines, so the
+// columns are spread over as many SMs as possible instead of sharing the load/store unit of a few.
+constexpr int kBacktrackThreads = 32;
+
 template <bool PAIRWISE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kBacktrackThreads)
 backtrack_kernel(const uint32_t *__restrict__ records, const float4 *__restrict__ dp, const float *__restrict__ stat,
                  const float *__restrict__ pm, const int *__restrict__ vhor_arr,
                  const float *__restrict__ object_disparity_range, isx_section *__restrict__ sections,
@@ -98,7 +109,7 @@ backtrack_kernel(const uint32_t *__restrict__ records, const float4 *__restrict_
   const int vhor = vhor_arr[f];
   const bool has_invalid = p.invalid_disparity >= 0.0f;
   const int Hp = p.rec_stride;
-  const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
+  const uint32_t *rec = records + (size_t)gcol * Hp * kRecBWords;
   const float4 *dp_col = dp + (size_t)gcol * H;
   const float *S = stat + (size_t)f * H * kStatWords;
   const float *pm_col = pm + (size_t)gcol * H;
@@ -119,7 +130,7 @@ backtrack_kernel(const uint32_t *__restrict__ records, const float4 *__restrict_
     const float4 row = dp_col[vT];
     const int vB = (type == OBJECT) ? __float_as_int(row.w) : __float_as_int(row.z);
     const float cost = (type == OBJECT) ? row.y : row.x;
-    const Rec hi = load_rec(rec, Hp, vT + 1), lo = load_rec(rec, Hp, vB);
+    const Rec hi = load_rec(rec, vT + 1), lo = load_rec(rec, vB);
     const int n = vT + 1 - vB;
 
     isx_section sec;
@@ -269,7 +280,7 @@ __global__ void export_tables_kernel(const uint32_t *__restrict__ records, const
   const int vhor = vhor_arr[frame];
   const bool has_invalid = p.invalid_disparity >= 0.0f;
   const int Hp = p.rec_stride;
-  const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
+  const uint32_t *rec = records + (size_t)gcol * Hp * kRecBWords;
   const float4 *dp_col = dp + (size_t)gcol * H;
   const float *S = stat + (size_t)frame * H * kStatWords;
   const float *pm_col = pm + (size_t)gcol * H;
@@ -291,7 +302,7 @@ __global__ void export_tables_kernel(const uint32_t *__restrict__ records, const
       it[type] = type == GROUND ? GROUND : OBJECT;  // (:564, 592)
       continue;
     }
-    const Rec hi = load_rec(rec, Hp, vT + 1), lo = load_rec(rec, Hp, vB);
+    const Rec hi = load_rec(rec, vT + 1), lo = load_rec(rec, vB);
     const float fn = segment_mean(__uint_as_float(hi.w[kRecDisp]), __uint_as_float(lo.w[kRecDisp]),
                                   __uint_as_float(hi.w[kRecValid]), __uint_as_float(lo.w[kRecValid]),
                                   vT + 1 - vB, has_invalid);
@@ -303,13 +314,13 @@ __global__ void export_tables_kernel(const uint32_t *__restrict__ records, const
 
 void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s) {
   const int ncolumns = nframes * p.realcols;
-  const int grid = (ncolumns + 127) / 128;
-  const uint32_t *rec = b.records;
+  const int grid = (ncolumns + kBacktrackThreads - 1) / kBacktrackThreads;
+  const uint32_t *rec = b.records_b;
   if (pairwise)
-    backtrack_kernel<true><<<grid, 128, 0, s>>>(rec, b.dp, b.stat, b.pm, b.vhor, b.object_disparity_range,
+    backtrack_kernel<true><<<grid, kBacktrackThreads, 0, s>>>(rec, b.dp, b.stat, b.pm, b.vhor, b.object_disparity_range,
                                                 b.sections, b.n_sections, b.error_flag, ncolumns, p);
   else
-    backtrack_kernel<false><<<grid, 128, 0, s>>>(rec, b.dp, b.stat, b.pm, b.vhor, b.object_disparity_range,
+    backtrack_kernel<false><<<grid, kBacktrackThreads, 0, s>>>(rec, b.dp, b.stat, b.pm, b.vhor, b.object_disparity_range,
                                                  b.sections, b.n_sections, b.error_flag, ncolumns, p);
   collect_candidates_kernel<<<nframes, 256, 0, s>>>(b.sections, b.n_sections, b.cand_count, b.cand_offset, b.cand_xy,
                                                      b.cand_idx, b.cand_core, p);
@@ -319,7 +330,7 @@ void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pair
 void launch_export_tables(const KParams &p, const BatchBuffers &b, int frame, bool pairwise, float *cost_table,
                           int *index_table, cudaStream_t s) {
   const int n = p.realcols * p.rows;
-  const uint32_t *rec = b.records;
+  const uint32_t *rec = b.records_b;
   if (pairwise)
     export_tables_kernel<true><<<(n + 127) / 128, 128, 0, s>>>(rec, b.dp, b.stat, b.pm, b.vhor,
                                                                b.object_disparity_range, frame, cost_table,

@@ -24,7 +24,10 @@ namespace isx {
 
 namespace {
 
+// threads per CTA: 256 for batches (one CTA per frame and class fits beside the DP), 1024 when only a few
+// frames are in flight and the latency of the largest class is what the caller waits for
 constexpr int kGroupThreads = 256;
+constexpr int kGroupThreadsLatency = 1024;
 constexpr int kGroupSmemPts = 4096;
 constexpr size_t kGroupSmemBytes = (size_t)kGroupSmemPts * (sizeof(float2) + sizeof(int));
 
@@ -60,13 +63,14 @@ __device__ __forceinline__ void group_points(float2 *P, const float2 *__restrict
                                              const uint8_t *__restrict__ cand, int *__restrict__ label, int n,
                                              float eps2, int min_pts, int *warp_sum, int *carry) {
   const int tid = threadIdx.x;
+  const int nthreads = blockDim.x;
   const float inf = inf_f();
   if (SMEM) {
-    for (int i = tid; i < n; i += kGroupThreads) P[i] = xy[i];
+    for (int i = tid; i < n; i += nthreads) P[i] = xy[i];
     __syncthreads();
   }
   // 1. core points (every point counts as a neighbour, core or not)
-  for (int i = tid; i < n; i += kGroupThreads) {
+  for (int i = tid; i < n; i += nthreads) {
     const float2 pi = P[i];
     int deg = 0;
 #pragma unroll 4
@@ -75,13 +79,13 @@ __device__ __forceinline__ void group_points(float2 *P, const float2 *__restrict
   }
   __syncthreads();
   if (SMEM) {
-    for (int i = tid; i < n; i += kGroupThreads)
+    for (int i = tid; i < n; i += nthreads)
       if (comp[i] < 0) P[i].x = inf;
     __syncthreads();
   }
   // 2. connected components of the core points: unite every near pair j < i.  Rows i and n-1-i go to the
   //    same thread so that the triangular sweep is balanced.
-  for (int h = tid; 2 * h < n; h += kGroupThreads) {
+  for (int h = tid; 2 * h < n; h += nthreads) {
     for (int side = 0; side < 2; side++) {
       const int i = side == 0 ? h : n - 1 - h;
       if (side == 1 && i == h) break;
@@ -100,7 +104,7 @@ __device__ __forceinline__ void group_points(float2 *P, const float2 *__restrict
   }
   __syncthreads();
   // every core point -> its root (read-only chase, then a private write: ancestors stay ancestors)
-  for (int i = tid; i < n; i += kGroupThreads) {
+  for (int i = tid; i < n; i += nthreads) {
     if (ld_link(comp, i) < 0) continue;
     const int r = find_root(comp, i);
     if (r != i) atomicMin(comp + i, r);
@@ -109,7 +113,7 @@ __device__ __forceinline__ void group_points(float2 *P, const float2 *__restrict
   // 3. rank the roots (comp[i] == i) by index -> cluster ids 0..k-1
   if (tid == 0) *carry = 0;
   __syncthreads();
-  for (int start = 0; start < n; start += kGroupThreads) {
+  for (int start = 0; start < n; start += nthreads) {
     const int i = start + tid;
     const int is_rep = (i < n && ld_link(comp, i) == i) ? 1 : 0;
     int incl = is_rep;
@@ -126,14 +130,14 @@ __device__ __forceinline__ void group_points(float2 *P, const float2 *__restrict
     __syncthreads();
     if (tid == 0) {
       int t = *carry;
-      for (int w = 0; w < kGroupThreads / 32; w++) t += warp_sum[w];
+      for (int w = 0; w < nthreads / 32; w++) t += warp_sum[w];
       *carry = t;
     }
     __syncthreads();
   }
   // 4. core members take their root's id; border points the id of their lowest-index core neighbour;
   //    the rest is noise (-1).
-  for (int i = tid; i < n; i += kGroupThreads) {
+  for (int i = tid; i < n; i += nthreads) {
     const int c = ld_link(comp, i);
     if (c == i) continue;  // root, labelled in step 3
     if (c >= 0) {
@@ -152,12 +156,12 @@ __device__ __forceinline__ void group_points(float2 *P, const float2 *__restrict
   }
 }
 
-__global__ void __launch_bounds__(kGroupThreads)
+__global__ void __launch_bounds__(kGroupThreadsLatency)
 grouping_kernel(const int *__restrict__ cand_count, const float2 *__restrict__ cand_xy,
                 const uint8_t *__restrict__ cand_core, int *__restrict__ cand_label, int *__restrict__ scratch,
                 KParams p) {
   extern __shared__ __align__(16) unsigned char group_smem[];
-  __shared__ int warp_sum[kGroupThreads / 32];
+  __shared__ int warp_sum[kGroupThreadsLatency / 32];
   __shared__ int carry;
   const int k = blockIdx.x, f = blockIdx.y;
   const int n = cand_count[f * kInstanceClasses + k];
@@ -188,15 +192,18 @@ void launch_grouping(const KParams &p, const BatchBuffers &b, int nframes, cudaS
     configured = true;
   }
   dim3 grid(kInstanceClasses, nframes);
-  grouping_kernel<<<grid, kGroupThreads, kGroupSmemBytes, s>>>(b.cand_count, b.cand_xy, b.cand_core, b.cand_label,
+  const int threads = nframes <= 4 ? kGroupThreadsLatency : kGroupThreads;
+  grouping_kernel<<<grid, threads, kGroupSmemBytes, s>>>(b.cand_count, b.cand_xy, b.cand_core, b.cand_label,
                                                                b.cand_scratch, p);
   g_launch_count++;
 }
 
 // Stand-alone grouping of one point set (the reference's ML::dbscanFit call, Stixels.cu:660-666): host buffers in,
 // labels out.  Uses the same kernel as the path (grid 1 x 1).
-int dbscan_fit_host(const float *xy, int n, float eps, int min_pts, const uint8_t *core_candidates, int *labels) {
+int dbscan_fit_host(const float *xy, int n, float eps, int min_pts, const uint8_t *core_candidates, int *labels,
+                    int threads) {
   if (n == 0) return 0;
+  if (threads != kGroupThreads) threads = kGroupThreadsLatency;
   float2 *d_xy = nullptr;
   uint8_t *d_core = nullptr;
   int *d_label = nullptr, *d_scratch = nullptr, *d_count = nullptr;
@@ -218,7 +225,7 @@ int dbscan_fit_host(const float *xy, int n, float eps, int min_pts, const uint8_
         cudaFuncSetAttribute(grouping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGroupSmemBytes);
         configured = true;
       }
-      grouping_kernel<<<dim3(1, 1), kGroupThreads, kGroupSmemBytes>>>(d_count, d_xy, d_core, d_label, d_scratch, p);
+      grouping_kernel<<<dim3(1, 1), threads, kGroupSmemBytes>>>(d_count, d_xy, d_core, d_label, d_scratch, p);
       g_launch_count++;
       ok(cudaGetLastError());
       ok(cudaDeviceSynchronize());

@@ -57,7 +57,8 @@ void launch_rasterize(const KParams &p, const isx_section *sections, const int *
                       int32_t *instance_img, float *disparity_img, cudaStream_t s);
 void launch_grouping(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
 // one point set through the grouping kernel, host buffers; 0 or a cudaError_t
-int dbscan_fit_host(const float *xy, int n, float eps, int min_pts, const uint8_t *core_candidates, int *labels);
+int dbscan_fit_host(const float *xy, int n, float eps, int min_pts, const uint8_t *core_candidates, int *labels,
+                    int threads);
 // reference-format views for the parity tests
 void launch_export_tables(const KParams &p, const BatchBuffers &b, int frame, bool pairwise, float *cost_table,
                           int *index_table, cudaStream_t s);

@@ -29,7 +29,9 @@ def _blobs(rng, n, k, spread, extent=2000.0):
     (6000, 5, 30.0, 12.0, 5, 0.3),      # global-memory path, chains of border points
     (800, 800, 0.0, 5.0, 2, 1.0),       # isolated points: everything is noise
 ])
-def test_labels_equal_the_definition(n, k, spread, eps, min_pts, p_cand):
+@pytest.mark.parametrize("threads", ["256", "1024"])   # the batch and the single-frame launch shape
+def test_labels_equal_the_definition(n, k, spread, eps, min_pts, p_cand, threads, monkeypatch):
+    monkeypatch.setenv("ISX_GROUP_THREADS", threads)
     rng = np.random.default_rng(n * 7919 + k)
     xy = _blobs(rng, n, k, spread)
     cand = (rng.random(n) < p_cand).astype(np.uint8)
