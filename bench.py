@@ -40,6 +40,15 @@ WORKLOADS = {
 }
 ROWS, COLS = 1024, 2048
 OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of a 16-frame chunk, from the `ncu --set full` captures
+# summarised in profiles/r1g_{unary,pairwise}_b16.txt (width 8; no capture exists for width 4).
+# "tables" = join_columns + column_tables + object_lut kernels.
+NCU_TRAFFIC = {
+    ("unary", 8): dict(dp=3.970442e9 + 0.305009e9,
+                       tables=(0.134252 + 0.009444 + 0.078595 + 1.022638 + 0.017293 + 2.088306) * 1e9),
+    ("pairwise", 8): dict(dp=2.358252e9 + 0.124019e9,
+                          tables=(0.134254 + 0.009981 + 0.078436 + 1.023258 + 0.016962 + 2.090570) * 1e9),
+}
 
 
 def measured_peaks():
@@ -329,6 +338,9 @@ def main():
         tab_bytes = (in_bytes + table_bytes) * chunk
         tab_ms = stages["join"][0] + stages["column_tables"][0]
         tab_launches = max(stages["join"][1], 1)
+        ncu = NCU_TRAFFIC.get((wl["mode"], wl["step"])) if chunk == 16 else None
+        # DRAM bytes one DP launch has to move once: object LUT + records in both layouts + the (cost, vB) rows
+        dp_alg_bytes = (C_ * 128 * H * 4 + C_ * (30 + 32) * rec_stride * 4 + C_ * H * 16) * chunk
         line = dict(
             metric="stixel frames/sec @1024x2048", value=world * B * args.steps / (ms_max * 1e-3), unit="frames/s",
             n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_max / args.steps,
@@ -345,7 +357,9 @@ def main():
             gpu_launches=int(launches),
             clocks=clk.summary(),
             roofline=dict(bound="alu", kernel="dp_kernel", achieved=achieved, peak=peak, unit="Tlane-op/s",
-                          frac=achieved / peak, traffic=None,
+                          frac=achieved / peak, traffic=ncu["dp"] if ncu else None,
+                          traffic_note=f"DRAM bytes per launch (ncu, profiles/r1g_*_b16.txt); the tables one launch reads "
+                                       f"once are {dp_alg_bytes} bytes",
                           note=f"{OPS_PER_CELL[wl['mode']]} lane-ops per DP cell x {cells_per_frame} cells/frame x "
                                f"{chunk} frames per launch / {dp_avg_s * 1e3:.2f} ms avg launch (CUDA events, "
                                f"{dp_launches} launches); peak = 148 SM x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz "
@@ -354,8 +368,8 @@ def main():
                                  achieved=tab_bytes / (tab_ms * 1e-3 / tab_launches) / 1e9,
                                  peak=peaks["hbm_gbs"], unit="GB/s",
                                  frac=tab_bytes / (tab_ms * 1e-3 / tab_launches) / 1e9 / peaks["hbm_gbs"],
-                                 traffic=None,
-                                 note=f"bytes per frame: inputs {in_bytes} + joined/records/object LUT {table_bytes}; "
+                                 traffic=ncu["tables"] if ncu else None,
+                                 note=f"bytes per launch {tab_bytes}; per frame: inputs {in_bytes} + joined/records/object LUT {table_bytes}; "
                                       f"inputs alone are {in_bytes * chunk / (tab_ms * 1e-3 / tab_launches) / 1e9:.0f} GB/s"),
             stage_ms_per_step={k: v[0] / args.steps for k, v in stages.items()},
         )
