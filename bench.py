@@ -40,14 +40,15 @@ WORKLOADS = {
 }
 ROWS, COLS = 1024, 2048
 OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of a 16-frame chunk, from the `ncu --set full` captures
-# summarised in profiles/r1g_{unary,pairwise}_b16.txt (width 8; no capture exists for width 4).
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of a 32-frame chunk, from the `ncu --set full` captures
+# summarised in profiles/r1h_{unary,pairwise}_b32.txt (width 8; no capture exists for width 4).
 # "tables" = join_columns + column_tables + object_lut kernels.
+NCU_CHUNK = 32
 NCU_TRAFFIC = {
-    ("unary", 8): dict(dp=3.970442e9 + 0.305009e9,
-                       tables=(0.134252 + 0.009444 + 0.078595 + 1.022638 + 0.017293 + 2.088306) * 1e9),
-    ("pairwise", 8): dict(dp=2.358252e9 + 0.124019e9,
-                          tables=(0.134254 + 0.009981 + 0.078436 + 1.023258 + 0.016962 + 2.090570) * 1e9),
+    ("unary", 8): dict(dp=(7.6478 + 0.6030) * 1e9,
+                       tables=(0.2685 + 0.0261 + 0.1554 + 2.1010 + 0.0337 + 4.2364) * 1e9),
+    ("pairwise", 8): dict(dp=(4.5367 + 0.2267) * 1e9,
+                          tables=(0.2685 + 0.0273 + 0.1559 + 2.1009 + 0.0338 + 4.2363) * 1e9),
 }
 
 
@@ -338,7 +339,7 @@ def main():
         tab_bytes = (in_bytes + table_bytes) * chunk
         tab_ms = stages["join"][0] + stages["column_tables"][0]
         tab_launches = max(stages["join"][1], 1)
-        ncu = NCU_TRAFFIC.get((wl["mode"], wl["step"])) if chunk == 16 else None
+        ncu = NCU_TRAFFIC.get((wl["mode"], wl["step"])) if chunk == NCU_CHUNK else None
         # DRAM bytes one DP launch has to move once: object LUT + records in both layouts + the (cost, vB) rows
         dp_alg_bytes = (C_ * 128 * H * 4 + C_ * (30 + 32) * rec_stride * 4 + C_ * H * 16) * chunk
         line = dict(
@@ -358,7 +359,7 @@ def main():
             clocks=clk.summary(),
             roofline=dict(bound="alu", kernel="dp_kernel", achieved=achieved, peak=peak, unit="Tlane-op/s",
                           frac=achieved / peak, traffic=ncu["dp"] if ncu else None,
-                          traffic_note=f"DRAM bytes per launch (ncu, profiles/r1g_*_b16.txt); the tables one launch reads "
+                          traffic_note=f"DRAM bytes per launch (ncu, profiles/r1h_*_b32.txt); the tables one launch reads "
                                        f"once are {dp_alg_bytes} bytes",
                           note=f"{OPS_PER_CELL[wl['mode']]} lane-ops per DP cell x {cells_per_frame} cells/frame x "
                                f"{chunk} frames per launch / {dp_avg_s * 1e3:.2f} ms avg launch (CUDA events, "

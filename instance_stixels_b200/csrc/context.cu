@@ -473,8 +473,12 @@ int isx_initialize(isx_handle h, int max_batch) {
   const size_t H = kp.rows, W = kp.cols, C = kp.realcols, D = kp.max_dis;
   if (C == 0) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no stixel columns");
   h->max_batch = max_batch;
-  int chunk = 16;  // frames per launch: 4096 column CTAs = 14 waves of the DP on 148 SMs x 2 CTAs; small enough
-                   // for the copies of one chunk to hide behind the kernels of its neighbours
+  // Frames per launch.  32 frames = 8192 column CTAs = 11-14 waves of the DP: every launch ends with a partly
+  // filled wave, and the next kernel of the stream only starts when the last CTA is done, so few large launches
+  // beat many small ones (resident: 16 -> 32 -> 64 frames = 1997 -> 2049 -> 2092 frames/s unary); but the
+  // copies of a host batch only overlap kernels of OTHER chunks, and at 64 the streaming path loses more than the
+  // launches gain (e2e 1954 -> 1971 -> 1907).  Intermediates take about 7 GB at 32 frames, width 8.
+  int chunk = 32;
   if (const char *e = std::getenv("ISX_CHUNK")) chunk = std::atoi(e) > 0 ? std::atoi(e) : chunk;
   h->chunk = chunk < max_batch ? chunk : max_batch;
   h->kp.lut_cols = h->chunk * (int)C;

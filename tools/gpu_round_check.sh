@@ -11,7 +11,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/${tag}_launches_bench.log 2>&1
 for mode in unary pairwise; do
   timeout 900 ncu --set full --clock-control none --import-source on -c 12 -f -o gpurun_out/prof_${tag}_${mode} \
-    python tools/profile_run.py --mode $mode --batch 16 --steps 1 > gpurun_out/prof_${tag}_${mode}.log 2>&1
+    python tools/profile_run.py --mode $mode --batch 32 --steps 1 > gpurun_out/prof_${tag}_${mode}.log 2>&1
 done
 cat gpurun_out/${tag}_pytest.log; tail -c 1500 gpurun_out/${tag}_bench_unary.json; tail -c 600 gpurun_out/${tag}_bench_unary.err
 ls -la gpurun_out
