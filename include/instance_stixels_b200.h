@@ -268,6 +268,9 @@ typedef enum isx_tensor {
 int isx_set_profiling(isx_handle h, int enable);
 int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, int reset);
 /* Frames per kernel launch (batches are cut into chunks of this many frames). */
+/* DP work since isx_initialize in units of 32 x 32 cells: `total` = every (tile, chunk) pair of every column,
+ * `evaluated` = those the kernels actually walked (the unary DP prunes chunks that provably cannot win). */
+int isx_get_dp_units(isx_handle h, unsigned long long *evaluated, unsigned long long *total);
 int isx_chunk_frames(isx_handle h);
 /* instance records per frame the packed result arrays hold (isx_submit_batch_host copies that many per frame) */
 int isx_instance_capacity(isx_handle h);

@@ -23,7 +23,7 @@ EXPORTS = [
     "isx_set_camera_parameters", "isx_set_model_parameters", "isx_initialize", "isx_finish",
     "isx_is_initialized", "isx_real_cols", "isx_max_sections", "isx_segmentation_elems",
     "isx_set_disparity_image", "isx_input_disparity_device", "isx_set_segmentation",
-    "isx_set_road_parameters", "isx_compute", "isx_cluster_instances", "isx_dbscan_fit_host", "isx_instance_capacity", "isx_flush",
+    "isx_set_road_parameters", "isx_compute", "isx_cluster_instances", "isx_dbscan_fit_host", "isx_instance_capacity", "isx_get_dp_units", "isx_flush",
     "isx_get_instance_stixels",
     "isx_compute_batch_host", "isx_submit_batch_host", "isx_wait_batch_host", "isx_compute_batch_device", "isx_synchronize", "isx_fetch_batch_results",
     "isx_stream", "isx_tensor_elems", "isx_read_tensor", "isx_set_profiling", "isx_get_stage_times",
@@ -142,6 +142,7 @@ def _declare(lib):
     lib.isx_set_profiling.argtypes = [H, i]
     lib.isx_get_stage_times.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_long), i, i]
     lib.isx_chunk_frames.argtypes = [H]
+    lib.isx_get_dp_units.argtypes = [H, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     lib.isx_instance_capacity.argtypes = [H]
     lib.isx_set_segmentation_from_cnn_device.argtypes = [H, C.c_void_p, i, i]
     lib.isx_flip_and_pad_batch_device.argtypes = [H, i, C.c_void_p, i, i, C.c_void_p]

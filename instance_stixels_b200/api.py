@@ -286,6 +286,12 @@ class Stixels:
     def chunk_frames(self) -> int:
         return self._lib.isx_chunk_frames(self._h)
 
+    def dp_units(self):
+        """(evaluated, total) 32 x 32-cell units of the DP since Initialize (the unary DP prunes)."""
+        ev, tot = C.c_ulonglong(0), C.c_ulonglong(0)
+        self._check(self._lib.isx_get_dp_units(self._h, C.byref(ev), C.byref(tot)))
+        return ev.value, tot.value
+
     def instance_capacity(self) -> int:
         return self._lib.isx_instance_capacity(self._h)
 

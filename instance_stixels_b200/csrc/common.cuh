@@ -94,6 +94,9 @@ struct KParams {
   int rec_stride;    // entries per (column, word) row of the records: always kRecStride
   int lut_stride;    // floats per fn row of the object LUT (>= H, multiple of 32)
   int lut_cols;      // column slots of the object-LUT buffer (chunk * C), see lut_column_address
+  // unary branch and bound (dp.cu)
+  float obj_cost_min;  // smallest entry of obj_cost_lut
+  int prune_unary;     // 0: walk every chunk (debug / A-B runs, ISX_UNARY_PRUNE=0)
 };
 
 // ---- pinned float ops (all .ftz through -ftz=true) ----

@@ -102,6 +102,8 @@ struct isx_context {
   cudaEvent_t ev_batch_done[2] = {nullptr, nullptr};  // by ticket parity
   int batch_n[2] = {0, 0};                            // frames of the batch in flight with that parity, 0 = none
   unsigned long long submitted = 0, waited = 0;       // tickets: batches [waited, submitted) are in flight
+  unsigned long long dp_units_pairwise = 0;           // ... of which in pairwise mode (never pruned)
+  unsigned long long dp_units_total = 0;              // 32 x 32-cell units of all DP launches so far
   int host_slot = 0;                                  // input slot / chunk set of the next host chunk (alternates across batches)
 
   std::map<isx::RoadKey, std::vector<float>> road_cache;
@@ -199,6 +201,11 @@ static void fill_kparams(isx_context *c) {
   k.instance_weight = m.instance_weight;
   k.rec_stride = kRecStride;  // constant whatever the height (rows <= 1024 is checked in isx_initialize)
   k.lut_stride = (m.rows + 31) & ~31;
+  float mn = m.obj_cost_lut.empty() ? 0.0f : m.obj_cost_lut[0];
+  for (float v : m.obj_cost_lut) mn = v < mn ? v : mn;
+  k.obj_cost_min = mn;
+  const char *e = std::getenv("ISX_UNARY_PRUNE");
+  k.prune_unary = (e && std::atoi(e) == 0) ? 0 : 1;
 }
 
 // Compacts the grouping result of every frame into isx_instance records
@@ -290,6 +297,13 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
   launch_column_tables(kp, b, n, s);
   mark(s);
   launch_dp(kp, b, n, pairwise, s);
+  {
+    const unsigned long long nt = (unsigned long long)(H + 31) / 32;
+    c->dp_units_total += (unsigned long long)n * C * (nt * (nt + 1) / 2);
+    const char *ex = std::getenv("ISX_UNARY_EXHAUSTIVE");
+    const bool walks_all = pairwise || (ex && std::atoi(ex) != 0);  // only the pruned unary kernel counts on the device
+    c->dp_units_pairwise += walks_all ? (unsigned long long)n * C * (nt * (nt + 1) / 2) : 0;
+  }
   mark(s);
   ISX_TRY(c, cudaEventRecord(c->ev_dp_done[slot], s));
   ISX_TRY(c, cudaStreamWaitEvent(se, c->ev_dp_done[slot], 0));
@@ -533,6 +547,8 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &b.cand_label, ch * kInstanceClasses * cap));
   ISX_TRY(h, dev_alloc(h, &b.cand_scratch, ch * kInstanceClasses * cap));
   ISX_TRY(h, dev_alloc(h, &b.error_flag, 1));
+  ISX_TRY(h, dev_alloc(h, &b.dp_units, 1));
+  ISX_TRY(h, cudaMemset(b.dp_units, 0, sizeof(unsigned long long)));
   ISX_TRY(h, cudaMemset(b.error_flag, 0, sizeof(int)));
   ISX_TRY(h, dev_alloc(h, &h->d_sections_all, MB * C * kMaxSections));
   // entries after a column's terminator are never written: start them from zero
@@ -598,6 +614,7 @@ int isx_finish(isx_handle h) {
   }
   h->submitted = h->waited = 0;
   h->host_slot = 0;
+  h->dp_units_total = h->dp_units_pairwise = 0;
   h->batch_n[0] = h->batch_n[1] = 0;
   h->emit_join_pending = false;
   for (int i = 0; i < 2; i++) {
@@ -1068,6 +1085,15 @@ int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, in
   return ISX_OK;
 }
 
+int isx_get_dp_units(isx_handle h, unsigned long long *evaluated, unsigned long long *total) {
+  if (int rc = check_ready(h)) return rc;
+  unsigned long long dev = 0;
+  ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
+  ISX_TRY(h, cudaMemcpy(&dev, h->buf.dp_units, sizeof dev, cudaMemcpyDeviceToHost));
+  if (evaluated) *evaluated = dev + h->dp_units_pairwise;
+  if (total) *total = h->dp_units_total;
+  return ISX_OK;
+}
 int isx_chunk_frames(isx_handle h) { return (h && h->initialized) ? h->chunk : 0; }
 int isx_instance_capacity(isx_handle h) { return (h && h->initialized) ? h->inst_cap : 0; }
 

@@ -684,6 +684,249 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Unary mode with exact pruning (branch and bound over the vB chunks of a tile).
+//
+// In unary mode a cell's cost is a function of its own segment only (previous costs are not accumulated,
+// StixelsKernels.cu:713-720, 758-766, 815-824): cost = sw*seg + pw/n + dw*data, where seg is a sum of
+// non-negative integers over the rows of the segment.  So every cell of a far unit is bounded from below
+// by what its shortest segment must cost at least, and once the rows of a tile have found a cheap
+// segment in the chunks next to the diagonal, the chunks further down cannot win any more -- with the
+// tuned weights (pw = 1e4) the best segment of a row is a few dozen rows long.
+//
+// One warp owns a tile and walks its chunks DOWNWARDS from the diagonal (j = t, t-1, ...):
+//   * inside a unit the steps ascend with strict '<' as before; a unit's minima replace the carried ones
+//     when they are '<=', so that among equal costs the lowest vB still wins (the reference's tie rule);
+//   * before chunk j-1 every lane evaluates a lower bound of all its cells still to come (vB <= last row of
+//     chunk j-1, its own vT):
+//         seg_c(vB, vT) >= P_c(vT + 1) - P_c(last row of chunk j-1)                          (prefixes are monotone)
+//         instance term >= -2^-19 * iw * (sum of squared means up to the tile)               (float error of the variance)
+//         data terms    >= rows * min(0, smallest per-row cost)                              (over the longest segment)
+//     combined with the same monotone float operations as the cell itself, minus 1.0 of slack for the
+//     rounding of the float prefix sums; the bound only grows further down, so the walk stops as soon as
+//     it exceeds the carried cost of both slots in every row of the tile.
+// The result is bit-identical to the exhaustive scan (same cells win, same ties); tests run both.
+// B records travel global -> shared memory per warp (two 4 KB buffers, cp.async.bulk + mbarrier), the next
+// chunk speculatively while the current one is evaluated.
+// ---------------------------------------------------------------------------
+#ifndef ISX_UNARY_PRUNE
+#define ISX_UNARY_PRUNE 1
+#endif
+#ifndef ISX_PRUNED_CTAS
+#define ISX_PRUNED_CTAS 4  // 128 registers: carried + local minima and the bound ingredients beside the 30 A words
+#endif
+
+struct PruneLayout {
+  size_t off_stage, off_bars, off_ih, off_misc, total;
+  __host__ __device__ PruneLayout(int H, int warps) {
+    size_t o = 0;
+    off_stage = o; o += (size_t)warps * 2 * kSlotBytes;
+    off_bars = o; o += (size_t)warps * 2 * 8;
+    off_ih = o; o += (size_t)(H + 1) * 4;
+    o = (o + 15) & ~(size_t)15;
+    off_misc = o; o += 16;
+    total = (o + 15) & ~(size_t)15;
+  }
+};
+
+template <bool HAS_INVALID, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == kDpWarps ? ISX_PRUNED_CTAS : 2)
+dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
+                       const float *__restrict__ object_lut, const float *__restrict__ ground,
+                       const int *__restrict__ vhor_arr, const float *__restrict__ inverse_height, float4 *dp_out,
+                       unsigned long long *__restrict__ units_evaluated, KParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kThreads = WARPS * 32;
+  const unsigned full_mask = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gcol = blockIdx.x;  // frame * C + column
+  const int H = p.rows, C = p.realcols;
+  constexpr int Hp = kRecStride;
+  const int f = gcol / C;
+  const int vhor = vhor_arr[f];
+  const float inf = inf_f();
+  const PruneLayout L(H, WARPS);
+  const int nt = (H + kChunk - 1) / kChunk;
+
+  uint32_t *stage_w = reinterpret_cast<uint32_t *>(smem_raw + L.off_stage) + (size_t)warp * 2 * kSlotWords;
+  uint64_t *bars_w = reinterpret_cast<uint64_t *>(smem_raw + L.off_bars) + warp * 2;
+  float *ihs = reinterpret_cast<float *>(smem_raw + L.off_ih);
+  int *tile_next = reinterpret_cast<int *>(smem_raw + L.off_misc);
+  float *norm_g_min_s = reinterpret_cast<float *>(smem_raw + L.off_misc + 4);
+
+  DpConsts c;
+  c.pw = p.prior_weight; c.dw = p.disparity_weight; c.sw = p.segmentation_weight; c.iw = p.instance_weight;
+  c.dm1f = (float)(p.max_dis - 1);
+  c.lut_stride4 = (unsigned)p.lut_stride * 4u;
+  c.epsilon = p.epsilon;
+  const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
+  const uint32_t *recb = records_b + (size_t)gcol * Hp * kRecBWords;
+  const unsigned long long lut_addr = lut_column_address((unsigned long long)object_lut, (size_t)gcol, p.lut_cols,
+                                                         (size_t)p.max_dis * p.lut_stride * 4);
+  c.lut_hi = (unsigned)(lut_addr >> 32);
+  const unsigned lutb = (unsigned)lut_addr - 0x4B000000u * c.lut_stride4;
+  float4 *out = dp_out + (size_t)gcol * H;
+
+  // ---- one-time setup ----
+  if (tid == 0) {
+    uint64_t *bars_all = reinterpret_cast<uint64_t *>(smem_raw + L.off_bars);
+    for (int i = 0; i < 2 * WARPS; i++) mbar_init(&bars_all[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *tile_next = nt;
+  }
+  for (int i = tid; i <= H; i += kThreads) ihs[i] = __ldg(inverse_height + i);
+  if (warp == 0) {
+    // smallest normalization_ground of the frame: per-row ground cost >= min(puniform, it) + ... (:217-234)
+    const float *norm_g = ground + (size_t)f * 3 * H + H;
+    float m = inf;
+    for (int v = lane; v < H; v += 32) m = fminf(m, __ldg(norm_g + v));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(full_mask, m, d));
+    if (lane == 0) *norm_g_min_s = m;
+  }
+  __syncthreads();
+  // smallest possible per-row data cost of the three models (StixelsKernels.cu:201-234, Stixels.cu:842-854):
+  // the squared term is >= 0, fmin / fadd are monotone
+  const float lb_g = fminf(p.pnexists_given_ground_log,
+                           fadd(fminf(p.puniform, *norm_g_min_s), p.nopnexists_given_ground_log));
+  const float lb_s = fminf(p.pnexists_given_sky_log,
+                           fadd(fminf(p.puniform_sky, p.normalization_sky), p.nopnexists_given_sky_log));
+  const float lb_o = p.obj_cost_min;
+  // the bounds assume non-negative weights (NaN fails the test too): otherwise every chunk is evaluated
+  const bool prune_ok = ISX_UNARY_PRUNE && c.sw >= 0.0f && c.dw >= 0.0f && c.pw >= 0.0f && c.iw >= 0.0f &&
+                        p.prune_unary != 0;
+
+  unsigned ph0 = 0, ph1 = 0;  // phase parity of this warp's two buffers
+  auto stage = [&](int ch, int b) {
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive_expect_tx(&bars_w[b], kSlotBytes);
+      bulk_g2s(stage_w + (size_t)b * kSlotWords, recb + (size_t)ch * kSlotWords, kSlotBytes, &bars_w[b]);
+    }
+  };
+  auto wait = [&](int b) {
+    if (b) { mbar_wait(&bars_w[1], ph1); ph1 ^= 1u; }
+    else { mbar_wait(&bars_w[0], ph0); ph0 ^= 1u; }
+  };
+  unsigned long long my_units = 0;
+
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = atomicSub(tile_next, 1) - 1;
+    t = __shfl_sync(full_mask, t, 0);
+    if (t < 0) break;
+    const int vT = t * kChunk + lane;
+    const bool row_ok = vT < H;
+    const int vTc = row_ok ? vT : H - 1;
+    stage(t, 0);
+
+    uint32_t A[kRecWords];
+#pragma unroll
+    for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
+    const unsigned ca = lutb + 4u * (unsigned)vTc;
+    // ---- what the bounds of this tile are made of ----
+    const int vTmaxc = min(t * kChunk + kChunk - 1, H - 1);
+    float sq = 0.0f;
+    if (lane == 0) {
+      const uint32_t *r1 = rec + vTmaxc + 1;
+      sq = fadd(fadd(f_(__ldg(r1 + (size_t)kRecMx2Hi * Hp)), f_(__ldg(r1 + (size_t)kRecMx2Lo * Hp))),
+                fadd(f_(__ldg(r1 + (size_t)kRecMy2Hi * Hp)), f_(__ldg(r1 + (size_t)kRecMy2Lo * Hp))));
+    }
+    sq = __shfl_sync(full_mask, sq, 0);
+    const float ic_lb = -fmul(fmul(sq, c.iw), 1.9073486328125e-06f);  // 2^-19: > 5 roundings + MUFU.RCP, relative
+    const float nmaxf = (float)(vTmaxc + 1);
+    const float dneg_o = fmul(c.dw, fmul(nmaxf, fminf(lb_o, 0.0f)));
+    const float dneg_gs = fmul(c.dw, fmul(nmaxf, fminf(vTc < vhor ? lb_g : lb_s, 0.0f)));
+
+    Best carried{inf, inf, 0, 0};
+    int buf = 0;
+    wait(0);
+    for (int j = t;; j--) {
+      if (j > 0) stage(j - 1, buf ^ 1);  // needed for the bound below, and for the next unit if the walk goes on
+      const uint32_t *bchunk = stage_w + (size_t)buf * kSlotWords;
+      const int vb0 = j * kChunk;
+      const int nsteps = min(kChunk, H - vb0);
+      const int kg = max(0, min(nsteps, vhor + 1 - vb0));  // steps with vB <= vhor are on the ground side
+      const unsigned cb0 = lutb + 4u * (unsigned)(vb0 - 1);
+      const int n0 = vTc + 1 - vb0;
+      Best local{inf, inf, 0, 0};
+      int k0 = 0;
+      if (j == 0) {
+        // first segment, vB = 0 (:481-594)
+        const CellBase b = cell_base<true, 1, HAS_INVALID>(A, bchunk, ca, lutb, (float)n0, c);
+        RowInfo q{};
+        float cost_gs, cost_o;
+        cell_finish<false, true, 1>(b, ihs[n0], q, 0.0f, 0.0f, c, cost_gs, cost_o);
+        if (cost_gs < local.gs) { local.gs = cost_gs; local.vb_gs = 0; }
+        if (cost_o < local.o) { local.o = cost_o; local.vb_o = 0; }
+        k0 = 1;
+      }
+      if (j == t) {
+        dp_steps<false, 1, true, HAS_INVALID>(A, bchunk, cb0, ca, ihs, nullptr, vb0, k0, max(k0, kg), n0, lane, c,
+                                              local);
+        dp_steps<false, 0, true, HAS_INVALID>(A, bchunk, cb0, ca, ihs, nullptr, vb0, max(k0, kg), nsteps, n0, lane, c,
+                                              local);
+      } else {
+        if (t * kChunk >= vhor)
+          dp_steps<false, 3, false, HAS_INVALID>(A, bchunk, cb0, ca, ihs, nullptr, vb0, k0, max(k0, kg), n0, lane, c,
+                                                 local);
+        else
+          dp_steps<false, 1, false, HAS_INVALID>(A, bchunk, cb0, ca, ihs, nullptr, vb0, k0, max(k0, kg), n0, lane, c,
+                                                 local);
+        dp_steps<false, 0, false, HAS_INVALID>(A, bchunk, cb0, ca, ihs, nullptr, vb0, max(k0, kg), nsteps, n0, lane, c,
+                                               local);
+      }
+      // this chunk lies below the ones seen so far: it wins ties
+      if (local.gs <= carried.gs) { carried.gs = local.gs; carried.vb_gs = local.vb_gs; }
+      if (local.o <= carried.o) { carried.o = local.o; carried.vb_o = local.vb_o; }
+      my_units++;
+      __syncwarp();
+      if (j == 0) break;
+      // ---- can a segment that starts in chunk j-1 or below still win a row of this tile? ----
+      wait(buf ^ 1);
+      bool stop = false;
+      if (prune_ok) {
+        // Row vT against the LAST row of chunk j-1 (all of them are full chunks): the class sums of the shortest
+        // segment that is still to come; every other one contains it, and the sums only grow (non-negative terms).
+        const int vbm = (j - 1) * kChunk + kChunk - 1;
+        const uint32_t *blast = stage_w + (size_t)(buf ^ 1) * kSlotWords + (kChunk - 1) * kRecBWords;
+        uint32_t Bl[20];
+        {
+          const uint4 *b4 = reinterpret_cast<const uint4 *>(blast);
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            const uint4 q4 = b4[k];
+            Bl[4 * k] = q4.x; Bl[4 * k + 1] = q4.y; Bl[4 * k + 2] = q4.z; Bl[4 * k + 3] = q4.w;
+          }
+        }
+        int l_ni = (int)(A[2] - Bl[2]);
+#pragma unroll
+        for (int k = 3; k < 10; k++) l_ni = min(l_ni, (int)(A[k] - Bl[k]));
+        int l_in = (int)(A[11] - Bl[11]);
+#pragma unroll
+        for (int k = 12; k < 19; k++) l_in = min(l_in, (int)(A[k] - Bl[k]));
+        const int l_g = min((int)(A[0] - Bl[0]), (int)(A[1] - Bl[1]));
+        const int l_s = (int)(A[kSkyClass] - Bl[kSkyClass]);
+        // object slot: seg_o >= min(0 + S_ni, ic + S_in), prior >= 0
+        const float seg_o_lb = fminf((float)l_ni, fadd(ic_lb, (float)l_in));
+        const float lbo = fadd(ffma(seg_o_lb, c.sw, dneg_o), -1.0f);
+        // ground / sky slot of this lane's row; sky cells need vB > vhor, ground rows always have candidates
+        const bool gs_possible = vTc < vhor || vbm > vhor;
+        const float seg_gs_lb = (float)(vTc < vhor ? l_g : l_s);
+        const float lbgs = fadd(ffma(seg_gs_lb, c.sw, dneg_gs), -1.0f);
+        const bool lane_done = !row_ok || (lbo > carried.o && (!gs_possible || lbgs > carried.gs));
+        stop = __all_sync(full_mask, lane_done);
+      }
+      if (stop) break;
+      buf ^= 1;
+    }
+    if (row_ok) store_best(out + vT, carried);
+    __syncwarp();
+  }
+  if (lane == 0 && my_units) atomicAdd(units_evaluated, my_units);
+}
+
 }  // namespace
 
 size_t dp_smem_bytes(const KParams &p, bool pairwise) {
@@ -719,13 +962,49 @@ static void launch_dp_variant(const KParams &p, const BatchBuffers &b, int ncolu
   else launch_dp_warps<PAIRWISE, HAS_INVALID, kDpWarps>(p, b, ncolumns, smem, s);
 }
 
+template <bool HAS_INVALID, int WARPS>
+static void launch_unary_pruned_warps(const KParams &p, const BatchBuffers &b, int ncolumns, cudaStream_t s) {
+  const size_t smem = PruneLayout(p.rows, WARPS).total;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(dp_unary_pruned_kernel<HAS_INVALID, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    configured = smem;
+  }
+  dp_unary_pruned_kernel<HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
+      b.records, b.records_b, b.object_lut, b.ground, b.vhor, b.inverse_height, b.dp, b.dp_units, p);
+}
+
+template <bool HAS_INVALID>
+static void launch_unary_pruned(const KParams &p, const BatchBuffers &b, int ncolumns, cudaStream_t s) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  bool latency = ncolumns < 2 * sms;
+  if (const char *e = std::getenv("ISX_DP_WARPS")) {  // tests pin the variant
+    if (std::atoi(e) == kDpWarps) latency = false;
+    if (std::atoi(e) == kDpWarpsLatency) latency = true;
+  }
+  if (latency) launch_unary_pruned_warps<HAS_INVALID, kDpWarpsLatency>(p, b, ncolumns, s);
+  else launch_unary_pruned_warps<HAS_INVALID, kDpWarps>(p, b, ncolumns, s);
+}
+
 void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s) {
   const int ncolumns = nframes * p.realcols;
   const size_t smem = dp_smem_bytes(p, pairwise);
   const bool has_invalid = p.invalid_disparity >= 0.0f;  // ComputeMean's two modes (StixelsKernels.cu:47-60)
+  // ISX_UNARY_EXHAUSTIVE=1: the unary DP without the walk from the diagonal (every unit of every tile)
+  const char *ex = std::getenv("ISX_UNARY_EXHAUSTIVE");
+  const bool exhaustive = ex && std::atoi(ex) != 0;
   if (pairwise) {
     if (has_invalid) launch_dp_variant<true, true>(p, b, ncolumns, smem, s);
     else launch_dp_variant<true, false>(p, b, ncolumns, smem, s);
+  } else if (!exhaustive) {
+    if (has_invalid) launch_unary_pruned<true>(p, b, ncolumns, s);
+    else launch_unary_pruned<false>(p, b, ncolumns, s);
   } else {
     if (has_invalid) launch_dp_variant<false, true>(p, b, ncolumns, smem, s);
     else launch_dp_variant<false, false>(p, b, ncolumns, smem, s);

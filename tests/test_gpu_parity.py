@@ -82,6 +82,65 @@ def test_bit_exact_against_reference_cuda_build(case, dp_warps):
     st.Finish()
 
 
+UNARY_WALKS = {  # how the unary DP visits the chunks of a tile
+    "pruned": {},                                   # from the diagonal downwards until no chunk below can win
+    "all_chunks": {"ISX_UNARY_PRUNE": "0"},         # the same walk without the bound test
+    "exhaustive": {"ISX_UNARY_EXHAUSTIVE": "1"},    # chunk-major over every unit (the pairwise kernel's schedule)
+}
+
+
+@pytest.mark.parametrize("shape", [(256, 512, 8, -1.0), (200, 328, 8, 0.0), (784, 1792, 8, 0.0), (1024, 2048, 8, 0.0),
+                                   (1024, 2048, 4, 0.0), (1024, 640, 8, -1.0)],
+                         ids=lambda s: f"{s[0]}x{s[1]}w{s[2]}inv{s[3]:g}")
+def test_unary_branch_and_bound_is_exact(shape, dp_warps, monkeypatch):
+    """The pruned unary DP returns byte-identical Sections and instance records to the exhaustive scan (and to
+    the reference CUDA build), and at full size it really skips most of the (tile, chunk) units."""
+    rows, cols, step, invalid = shape
+    pre = _preset("unary", rows, cols, step, invalid, False)
+    frames = [synth.make_frame(f, rows=rows, cols=cols, column_step=step) for f in (0, 5)]
+    results, work = {}, {}
+    for walk, env in UNARY_WALKS.items():
+        for k in ("ISX_UNARY_PRUNE", "ISX_UNARY_EXHAUSTIVE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        st = api.make_stixels(pre, max_batch=2)
+        out = []
+        for fr in frames:
+            st.SetDisparityImage(fr.disparity)
+            st.SetSegmentation(fr.segmentation)
+            st.SetRoadParameters(**fr.road)
+            data = st.Compute(False)
+            out.append((data.sections.copy(), st.instance_records().copy(),
+                        st.read_tensor(L.T_COST_TABLE).copy(), st.read_tensor(L.T_INDEX_TABLE).copy()))
+        sec_b, inst_b, _ = st.ComputeBatch(False, np.stack([f.disparity for f in frames]),
+                                           np.stack([f.segmentation for f in frames]), [f.road for f in frames])
+        for i in range(len(frames)):
+            assert parity.same_used_sections(sec_b[i], out[i][0])
+        results[walk], work[walk] = out, st.dp_units()
+        st.Finish()
+    for walk in ("all_chunks", "exhaustive"):
+        for (s0, i0, c0, x0), (s1, i1, c1, x1) in zip(results["pruned"], results[walk]):
+            assert np.array_equal(s0.view(np.uint8), s1.view(np.uint8)), walk
+            assert np.array_equal(i0.view(np.uint8), i1.view(np.uint8)), walk
+            # the whole (cost, argmin) tables, not just the rows on the optimal path
+            assert np.array_equal(c0.view(np.int32), c1.view(np.int32)), walk
+            assert np.array_equal(x0, x1), walk
+    ev, tot = work["pruned"]
+    assert work["all_chunks"][0] == work["all_chunks"][1] == tot and work["exhaustive"][0] == tot
+    assert 0 < ev <= tot
+    if rows == 1024 and cols == 2048:
+        assert ev < 0.5 * tot, (ev, tot)     # the synthetic Cityscapes-shaped frames: most units cannot win
+    if refbind.available() and rows * cols <= 784 * 1792:
+        ref = refbind.RefStixels(api.StixelConfig(**pre))
+        for fr, (sec, inst, _, _) in zip(frames, results["pruned"]):
+            rsec, rinst, _ = ref.compute(False, fr.disparity, fr.segmentation, fr.road)
+            r = parity.compare_sections(sec, rsec)
+            assert r["exact"] == 1.0 and r["close"] == 1.0 and r["bitwise"] >= 0.995, r
+            assert parity.compare_instances(inst, rinst)["same_partition"]
+        ref.close()
+
+
 def test_against_golden_vectors(golden_files):
     for path in golden_files:
         z = np.load(path)
