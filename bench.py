@@ -259,6 +259,7 @@ def main():
     st.set_profiling(True)
     st.stage_times(reset=True)
     launches0 = st._lib.isx_kernel_launch_count()
+    units0 = st.dp_units()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with ClockSampler(local) as clk:
@@ -271,6 +272,8 @@ def main():
         barrier()
     ms = e0.elapsed_time(e1)
     launches = st._lib.isx_kernel_launch_count() - launches0
+    units1 = st.dp_units()
+    units_eval, units_total = units1[0] - units0[0], units1[1] - units0[1]
     stages = st.stage_times(reset=True)
     st.set_profiling(False)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -325,7 +328,11 @@ def main():
         cells_per_frame = C_ * H * (H + 1) // 2
         dp_ms, dp_launches = stages["dp"]
         chunk = st.chunk_frames()
-        ops_per_launch = cells_per_frame * chunk * OPS_PER_CELL[wl["mode"]]
+        # The unary DP prunes (tile, chunk) units that provably cannot win (exact branch and bound): the roofline
+        # counts the cells the kernel evaluated (32 x 32 per unit), not the cells of the exhaustive scan.
+        eval_frac = units_eval / max(units_total, 1)
+        cells_eval_per_launch = units_eval * 1024 / max(dp_launches, 1)
+        ops_per_launch = cells_eval_per_launch * OPS_PER_CELL[wl["mode"]]
         dp_avg_s = dp_ms * 1e-3 / max(dp_launches, 1)
         achieved = ops_per_launch / dp_avg_s / 1e12
         peak = 148 * 128 * peaks["sm_max_mhz"] * 1e6 / 1e12
@@ -350,7 +357,9 @@ def main():
                         frames_per_step_per_gpu=B, chunk_frames=chunk,
                         l2="inputs (890 MB/step) and tables (>2 GB/chunk) exceed the 126 MB L2"),
             e2e=dict(value=world * B * args.steps / e2e_s, unit="frames/s",
-                     h2d_bytes_per_step=int(h_disp.numel() * 4 + h_seg.numel() * 4),
+                     # the zero padding of the segmentation tensor (rows/8 of rows_power2_segmentation entries
+                     # per channel are used) does not travel
+                     h2d_bytes_per_step=int(h_disp.numel() * 4 + h_seg.numel() * 4 * ((ROWS + 7) // 8) // h_seg.shape[-1]),
                      d2h_bytes_per_step=int(sections_host[0].numel() + B * st.instance_capacity() * 16 + B * 4 + 4),
                      pipeline="1 host thread, isx_submit_batch_host / isx_wait_batch_host, 2 batches in flight"),
             e2e_single=dict(value=world * B * args.steps / e2e_single_s, unit="frames/s",
@@ -361,10 +370,12 @@ def main():
                           frac=achieved / peak, traffic=ncu["dp"] if ncu else None,
                           traffic_note=f"DRAM bytes per launch (ncu, profiles/r1h_*_b32.txt); the tables one launch reads "
                                        f"once are {dp_alg_bytes} bytes",
-                          note=f"{OPS_PER_CELL[wl['mode']]} lane-ops per DP cell x {cells_per_frame} cells/frame x "
-                               f"{chunk} frames per launch / {dp_avg_s * 1e3:.2f} ms avg launch (CUDA events, "
-                               f"{dp_launches} launches); peak = 148 SM x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz "
-                               f"({peaks['source']})"),
+                          units_evaluated_frac=eval_frac,
+                          note=f"{OPS_PER_CELL[wl['mode']]} lane-ops per DP cell x {cells_eval_per_launch:.0f} cells "
+                               f"evaluated per launch ({100 * eval_frac:.1f} % of the {cells_per_frame} x {chunk} cells "
+                               f"of the exhaustive scan incl. the dead half of the diagonal units) / "
+                               f"{dp_avg_s * 1e3:.2f} ms avg launch (CUDA events, {dp_launches} launches); "
+                               f"peak = 148 SM x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']})"),
             roofline_tables=dict(bound="hbm", kernel="join_columns+column_tables",
                                  achieved=tab_bytes / (tab_ms * 1e-3 / tab_launches) / 1e9,
                                  peak=peaks["hbm_gbs"], unit="GB/s",

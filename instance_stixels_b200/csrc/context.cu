@@ -521,6 +521,7 @@ int isx_initialize(isx_handle h, int max_batch) {
   for (int i = 0; i < 2; i++) {
     ISX_TRY(h, dev_alloc(h, &h->d_in_disp[i], ch * H * W));
     ISX_TRY(h, dev_alloc(h, &h->d_in_seg[i], ch * seg_elems(h)));
+    ISX_TRY(h, cudaMemset(h->d_in_seg[i], 0, ch * seg_elems(h) * sizeof(int32_t)));
   }
   ISX_TRY(h, dev_alloc(h, &h->d_single_disp, H * W));
   ISX_TRY(h, dev_alloc(h, &h->d_single_seg, seg_elems(h)));
@@ -827,8 +828,17 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const float *di
     ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_in_free[slot], 0));
     ISX_TRY(h, cudaMemcpyAsync(h->d_in_disp[slot], disparity + first * hw, sizeof(float) * hw * cn,
                                cudaMemcpyHostToDevice, h->s_h2d));
-    ISX_TRY(h, cudaMemcpyAsync(h->d_in_seg[slot], segmentation + first * se, sizeof(int32_t) * se * cn,
-                               cudaMemcpyHostToDevice, h->s_h2d));
+    {
+      // Only the first rows/8 entries of every [rows_power2_segmentation] channel row are ever read
+      // (StixelsKernels.cu:393-405, 462-468 index v/8 with v < rows); the zero padding of FlipAndPad does not
+      // travel: a 2-D copy of the used part, the rest of the staging buffer stays zero from isx_initialize.
+      const size_t hs2 = (size_t)h->kp.hs2;
+      size_t used = (size_t)(h->kp.rows + kDownsample - 1) / kDownsample;
+      used = used < hs2 ? used : hs2;
+      ISX_TRY(h, cudaMemcpy2DAsync(h->d_in_seg[slot], hs2 * sizeof(int32_t), segmentation + first * se,
+                                   hs2 * sizeof(int32_t), used * sizeof(int32_t), (se / hs2) * cn,
+                                   cudaMemcpyHostToDevice, h->s_h2d));
+    }
     ISX_TRY(h, cudaEventRecord(h->ev_in_ready[slot], h->s_h2d));
     ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[slot]));  // pinned ground staging of this slot is reusable
     ISX_TRY(h, cudaStreamWaitEvent(h->s_compute, h->ev_in_ready[slot], 0));

@@ -703,7 +703,7 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
 //         seg_c(vB, vT) >= P_c(vT + 1) - P_c(last row of chunk j-1)                          (prefixes are monotone)
 //         instance term >= -2^-19 * iw * (sum of squared means up to the tile)               (float error of the variance)
 //         data terms    >= rows * min(0, smallest per-row cost)                              (over the longest segment)
-//     combined with the same monotone float operations as the cell itself, minus 1.0 of slack for the
+//     combined with the same monotone float operations as the cell itself, minus (1 + dw) of slack for the
 //     rounding of the float prefix sums; the bound only grows further down, so the walk stops as soon as
 //     it exceeds the carried cost of both slots in every row of the tile.
 // The result is bit-identical to the exhaustive scan (same cells win, same ties); tests run both.
@@ -836,6 +836,9 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
     sq = __shfl_sync(full_mask, sq, 0);
     const float ic_lb = -fmul(fmul(sq, c.iw), 1.9073486328125e-06f);  // 2^-19: > 5 roundings + MUFU.RCP, relative
     const float nmaxf = (float)(vTmaxc + 1);
+    // rounding of the float prefix sums behind the data terms (two prefixes of <= 37 additions each, entries below
+    // 2^17: < 0.6 absolute, scaled by dw) and of the final FFMAs
+    const float slack = fadd(1.0f, c.dw);
     const float dneg_o = fmul(c.dw, fmul(nmaxf, fminf(lb_o, 0.0f)));
     const float dneg_gs = fmul(c.dw, fmul(nmaxf, fminf(vTc < vhor ? lb_g : lb_s, 0.0f)));
 
@@ -910,11 +913,11 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
         const int l_s = (int)(A[kSkyClass] - Bl[kSkyClass]);
         // object slot: seg_o >= min(0 + S_ni, ic + S_in), prior >= 0
         const float seg_o_lb = fminf((float)l_ni, fadd(ic_lb, (float)l_in));
-        const float lbo = fadd(ffma(seg_o_lb, c.sw, dneg_o), -1.0f);
+        const float lbo = fsub(ffma(seg_o_lb, c.sw, dneg_o), slack);
         // ground / sky slot of this lane's row; sky cells need vB > vhor, ground rows always have candidates
         const bool gs_possible = vTc < vhor || vbm > vhor;
         const float seg_gs_lb = (float)(vTc < vhor ? l_g : l_s);
-        const float lbgs = fadd(ffma(seg_gs_lb, c.sw, dneg_gs), -1.0f);
+        const float lbgs = fsub(ffma(seg_gs_lb, c.sw, dneg_gs), slack);
         const bool lane_done = !row_ok || (lbo > carried.o && (!gs_possible || lbgs > carried.gs));
         stop = __all_sync(full_mask, lane_done);
       }

@@ -202,6 +202,15 @@ def test_batch_equals_single_frame_and_is_deterministic():
         data = st.Compute(True)
         assert parity.same_used_sections(data.sections, sec1[f]), f
         assert np.array_equal(st.instance_records().view(np.uint8), inst1[offs1[f]:offs1[f + 1]].view(np.uint8))
+    # the padding of the segmentation tensor (entries >= rows/8 of every channel row) is never read: the host
+    # batch path does not even copy it
+    seg_junk = seg.copy()
+    seg_junk[..., (rows + 7) // 8:] = np.random.default_rng(3).integers(-1000, 1000, seg_junk[..., (rows + 7) // 8:].shape)
+    sec4, inst4, offs4 = st.ComputeBatch(True, disp, seg_junk, roads)
+    assert all(parity.same_used_sections(sec1[f], sec4[f]) for f in range(n))   # (entries behind a terminator are stale)
+    assert np.array_equal(inst1.view(np.uint8), inst4.view(np.uint8)) and np.array_equal(offs1, offs4)
+    st.SetDisparityImage(disp[1]); st.SetSegmentation(seg_junk[1]); st.SetRoadParameters(**roads[1])
+    assert parity.same_used_sections(st.Compute(True).sections, sec1[1])
     st.Finish()
     # chunked execution (ISX_CHUNK) does not change results
     import os
