@@ -41,12 +41,12 @@ WORKLOADS = {
 ROWS, COLS = 1024, 2048
 OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of a 32-frame chunk, from the `ncu --set full` captures
-# summarised in profiles/r1h_{unary,pairwise}_b32.txt (width 8; no capture exists for width 4).
+# summarised in profiles/r1i_unary_b32.txt and profiles/r1h_pairwise_b32.txt (width 8; no capture for width 4).
 # "tables" = join_columns + column_tables + object_lut kernels.
 NCU_CHUNK = 32
 NCU_TRAFFIC = {
-    ("unary", 8): dict(dp=(7.6478 + 0.6030) * 1e9,
-                       tables=(0.2685 + 0.0261 + 0.1554 + 2.1010 + 0.0337 + 4.2364) * 1e9),
+    ("unary", 8): dict(dp=(3.4238 + 0.1345) * 1e9,   # dp_unary_pruned_kernel (r1i)
+                       tables=(0.2685 + 0.0267 + 0.1555 + 2.1040 + 0.0338 + 4.2369) * 1e9),
     ("pairwise", 8): dict(dp=(4.5367 + 0.2267) * 1e9,
                           tables=(0.2685 + 0.0273 + 0.1559 + 2.1009 + 0.0338 + 4.2363) * 1e9),
 }
@@ -368,7 +368,7 @@ def main():
             clocks=clk.summary(),
             roofline=dict(bound="alu", kernel="dp_kernel", achieved=achieved, peak=peak, unit="Tlane-op/s",
                           frac=achieved / peak, traffic=ncu["dp"] if ncu else None,
-                          traffic_note=f"DRAM bytes per launch (ncu, profiles/r1h_*_b32.txt); the tables one launch reads "
+                          traffic_note=f"DRAM bytes per launch (ncu, profiles/r1i_unary_b32.txt / r1h_pairwise_b32.txt); the tables one launch reads "
                                        f"once are {dp_alg_bytes} bytes",
                           units_evaluated_frac=eval_frac,
                           note=f"{OPS_PER_CELL[wl['mode']]} lane-ops per DP cell x {cells_eval_per_launch:.0f} cells "
