@@ -97,6 +97,7 @@ struct KParams {
   // unary branch and bound (dp.cu)
   float obj_cost_min;  // smallest entry of obj_cost_lut
   int prune_unary;     // 0: walk every chunk (debug / A-B runs, ISX_UNARY_PRUNE=0)
+  int prune_pairwise;  // same for the pairwise tile-major walk (ISX_PAIRWISE_PRUNE=0)
 };
 
 // ---- pinned float ops (all .ftz through -ftz=true) ----

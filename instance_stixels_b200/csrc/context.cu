@@ -206,6 +206,8 @@ static void fill_kparams(isx_context *c) {
   k.obj_cost_min = mn;
   const char *e = std::getenv("ISX_UNARY_PRUNE");
   k.prune_unary = (e && std::atoi(e) == 0) ? 0 : 1;
+  const char *e2 = std::getenv("ISX_PAIRWISE_PRUNE");
+  k.prune_pairwise = (e2 && std::atoi(e2) == 0) ? 0 : 1;
 }
 
 // Compacts the grouping result of every frame into isx_instance records
@@ -301,7 +303,8 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
     const unsigned long long nt = (unsigned long long)(H + 31) / 32;
     c->dp_units_total += (unsigned long long)n * C * (nt * (nt + 1) / 2);
     const char *ex = std::getenv("ISX_UNARY_EXHAUSTIVE");
-    const bool walks_all = pairwise || (ex && std::atoi(ex) != 0);  // only the pruned unary kernel counts on the device
+    // the pruning kernels count on the device
+    const bool walks_all = (pairwise && !(pairwise_walk_enabled() && b.qrows)) || (!pairwise && ex && std::atoi(ex) != 0);
     c->dp_units_pairwise += walks_all ? (unsigned long long)n * C * (nt * (nt + 1) / 2) : 0;
   }
   mark(s);
@@ -549,6 +552,10 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &b.cand_scratch, ch * kInstanceClasses * cap));
   ISX_TRY(h, dev_alloc(h, &b.error_flag, 1));
   ISX_TRY(h, dev_alloc(h, &b.dp_units, 1));
+  if (pairwise_walk_enabled()) {
+    ISX_TRY(h, dev_alloc(h, &b.qrows, ch * C * (size_t)kp.rec_stride * kDynWords));
+    ISX_TRY(h, cudaMemset(b.qrows, 0, ch * C * (size_t)kp.rec_stride * kDynWords * sizeof(float)));
+  }
   ISX_TRY(h, cudaMemset(b.dp_units, 0, sizeof(unsigned long long)));
   ISX_TRY(h, cudaMemset(b.error_flag, 0, sizeof(int)));
   ISX_TRY(h, dev_alloc(h, &h->d_sections_all, MB * C * kMaxSections));

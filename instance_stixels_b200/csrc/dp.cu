@@ -930,6 +930,352 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
   if (lane == 0 && my_units) atomicAdd(units_evaluated, my_units);
 }
 
+
+// ---------------------------------------------------------------------------
+// Pairwise mode, tile-major with exact pruning.
+//
+// The pairwise cost of a cell is  dw*data + pw*min_k(C[vB-1][k] + pw*trans_k) + sw*seg : the best total cost of the
+// rows below plus what the segment itself costs.  A segment that runs across a region of another class pays for
+// every row of it, so most far cells cannot win -- but proving it needs the row's near candidates first, and the
+// chunk-major schedule of dp_kernel evaluates the far chunks first.  Here a column is processed TILE by tile behind
+// the diagonal chain:
+//   for tile t:  (1) the units (t, j), j = t-1 ... 0, interleaved over the warps of the CTA, each unit only if a
+//                    lower bound of its cells does not already exceed the minima carried so far in some row;
+//                (2) the diagonal unit (t, t) -- the wavefront -- by warp 0, which finalises the rows of the tile,
+//                    writes their transition records Q[vB] for all later tiles and the smallest priors of the chunk.
+// Bound of unit (t, j) for row vT (the slots separately):
+//     prior >= smallest prior of any row of chunk j (exactly what the cells use for the ground/sky slot, the
+//              smallest of the candidate priors for the object slot),
+//     seg   >= class sums over the shortest segment (last row of chunk j .. vT), instance term >= -2^-19*iw*sum(means^2),
+//     data  >= rows * min(0, smallest per-row cost),
+// combined with the cell's own monotone float operations, minus (1 + dw) of slack.  Minima are merged
+// lexicographically by (cost, vB): the reference's "lowest vB wins ties" whatever the order of evaluation.
+// ---------------------------------------------------------------------------
+#ifndef ISX_WALK_CTAS
+#define ISX_WALK_CTAS 4
+#endif
+#ifndef ISX_PAIRWISE_WALK_DEFAULT
+#define ISX_PAIRWISE_WALK_DEFAULT 1
+#endif
+
+struct WalkLayout {
+  int nt;
+  size_t off_stage, off_bars, off_q, off_sst, off_odr, off_merge, off_cmin, off_qnext, total;
+  __host__ __device__ WalkLayout(int H, int D, int warps) {
+    nt = (H + kChunk - 1) / kChunk;
+    size_t o = 0;
+    off_stage = o; o += (size_t)warps * kSlotBytes;
+    off_bars = o; o += (size_t)warps * 8;
+    o = (o + 15) & ~(size_t)15;
+    off_q = o; o += (size_t)warps * kChunk * kDynWords * 4;
+    off_sst = o; o += (size_t)kSstWords * 4;
+    off_odr = o; o += (size_t)((D + 3) & ~3) * 4;
+    off_merge = o; o += (size_t)warps * 32 * 16;
+    off_cmin = o; o += (size_t)3 * nt * 4;  // per chunk: smallest object prior | ground prior | sky prior
+    o = (o + 15) & ~(size_t)15;
+    off_qnext = o; o += (size_t)kDynWords * 4;
+    total = (o + 15) & ~(size_t)15;
+  }
+};
+
+// (cost, vB) lexicographic: the lowest vB among equal costs, NaN never wins
+__device__ __forceinline__ void merge_best(Best &c, const Best &l) {
+  if (l.gs < c.gs || (l.gs == c.gs && l.vb_gs < c.vb_gs)) { c.gs = l.gs; c.vb_gs = l.vb_gs; }
+  if (l.o < c.o || (l.o == c.o && l.vb_o < c.vb_o)) { c.o = l.o; c.vb_o = l.vb_o; }
+}
+
+// smallest prior any object cell of row vB can get (object_priors picks one of these), times pw like the cell
+__device__ __forceinline__ float object_prior_floor(const RowInfo &q, bool ground_side, float pw) {
+  float m = fminf(q.p2_hi, fminf(q.p2_lo, q.p2_mid));
+  m = fminf(m, fminf(q.a1, q.a2));
+  if (ground_side) m = fminf(m, q.a3);
+  return fmul(m, pw);
+}
+
+template <bool HAS_INVALID, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 16 : WARPS == kDpWarps ? ISX_WALK_CTAS : 2)
+dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
+                        const float *__restrict__ object_lut, const float *__restrict__ stat,
+                        const float *__restrict__ ground, float *__restrict__ pm_out, float *__restrict__ qrows,
+                        const int *__restrict__ vhor_arr, const float *__restrict__ object_disparity_range,
+                        float4 *dp_out, unsigned long long *__restrict__ units_evaluated, KParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kThreads = WARPS * 32;
+  const unsigned full_mask = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gcol = blockIdx.x;
+  const int H = p.rows, C = p.realcols;
+  constexpr int Hp = kRecStride;
+  const int f = gcol / C;
+  const int vhor = vhor_arr[f];
+  const float inf = inf_f();
+  const WalkLayout L(H, p.max_dis, WARPS);
+  const int nt = L.nt;
+
+  uint32_t *stage_w = reinterpret_cast<uint32_t *>(smem_raw + L.off_stage) + (size_t)warp * kSlotWords;
+  uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem_raw + L.off_bars) + warp;
+  float *q_w = reinterpret_cast<float *>(smem_raw + L.off_q) + (size_t)warp * kChunk * kDynWords;
+  float *sst = reinterpret_cast<float *>(smem_raw + L.off_sst);
+  float *odr = reinterpret_cast<float *>(smem_raw + L.off_odr);
+  float4 *merge = reinterpret_cast<float4 *>(smem_raw + L.off_merge);
+  float *cmin_o = reinterpret_cast<float *>(smem_raw + L.off_cmin);
+  float *cmin_g = cmin_o + nt, *cmin_s = cmin_g + nt;
+  float *qnext = reinterpret_cast<float *>(smem_raw + L.off_qnext);
+
+  DpConsts c;
+  c.pw = p.prior_weight; c.dw = p.disparity_weight; c.sw = p.segmentation_weight; c.iw = p.instance_weight;
+  c.dm1f = (float)(p.max_dis - 1);
+  c.lut_stride4 = (unsigned)p.lut_stride * 4u;
+  c.epsilon = p.epsilon;
+  const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
+  const uint32_t *recb = records_b + (size_t)gcol * Hp * kRecBWords;
+  const unsigned long long lut_addr = lut_column_address((unsigned long long)object_lut, (size_t)gcol, p.lut_cols,
+                                                         (size_t)p.max_dis * p.lut_stride * 4);
+  c.lut_hi = (unsigned)(lut_addr >> 32);
+  const unsigned lutb = (unsigned)lut_addr - 0x4B000000u * c.lut_stride4;
+  const float *S = stat + (size_t)f * H * kStatWords;
+  float *pm_col = pm_out + (size_t)gcol * H;
+  float *qg = qrows + (size_t)gcol * Hp * kDynWords;  // Q[vB] of every row of this column
+  float4 *out = dp_out + (size_t)gcol * H;
+
+  if (tid == 0) {
+    uint64_t *bars_all = reinterpret_cast<uint64_t *>(smem_raw + L.off_bars);
+    for (int i = 0; i < WARPS; i++) mbar_init(&bars_all[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < p.max_dis; i += kThreads) odr[i] = __ldg(object_disparity_range + i);
+  float norm_g_min = inf;
+  {
+    const float *norm_g = ground + (size_t)f * 3 * H + H;
+    for (int v = lane; v < H; v += 32) norm_g_min = fminf(norm_g_min, __ldg(norm_g + v));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) norm_g_min = fminf(norm_g_min, __shfl_xor_sync(full_mask, norm_g_min, d));
+  }
+  __syncthreads();
+  const float lb_g = fminf(p.pnexists_given_ground_log, fadd(fminf(p.puniform, norm_g_min), p.nopnexists_given_ground_log));
+  const float lb_s = fminf(p.pnexists_given_sky_log,
+                           fadd(fminf(p.puniform_sky, p.normalization_sky), p.nopnexists_given_sky_log));
+  const float lb_o = p.obj_cost_min;
+  const bool prune_ok = c.sw >= 0.0f && c.dw >= 0.0f && c.pw >= 0.0f && c.iw >= 0.0f && p.prune_pairwise != 0;
+  const float slack = fadd(1.0f, c.dw);
+  // first-segment priors (:189-199)
+  const float first_k_gs = fmul(ffma(1.0f, kLn2, p.rows_log), c.pw);
+
+  unsigned ph = 0;  // phase parity of this warp's buffer
+  auto stage = [&](int ch) {
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive_expect_tx(bar_w, kSlotBytes);
+      bulk_g2s(stage_w, recb + (size_t)ch * kSlotWords, kSlotBytes, bar_w);
+    }
+  };
+  auto wait = [&]() { mbar_wait(bar_w, ph); ph ^= 1u; };
+  unsigned long long my_units = 0;
+
+  for (int t = 0; t < nt; t++) {
+    const int vT = t * kChunk + lane;
+    const bool row_ok = vT < H;
+    const int vTc = row_ok ? vT : H - 1;
+    uint32_t A[kRecWords];
+#pragma unroll
+    for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
+    const unsigned ca = lutb + 4u * (unsigned)vTc;
+    // bound ingredients of this tile (see dp_unary_pruned_kernel)
+    const int vTmaxc = min(t * kChunk + kChunk - 1, H - 1);
+    float sq = 0.0f;
+    if (lane == 0) {
+      const uint32_t *r1 = rec + vTmaxc + 1;
+      sq = fadd(fadd(f_(__ldg(r1 + (size_t)kRecMx2Hi * Hp)), f_(__ldg(r1 + (size_t)kRecMx2Lo * Hp))),
+                fadd(f_(__ldg(r1 + (size_t)kRecMy2Hi * Hp)), f_(__ldg(r1 + (size_t)kRecMy2Lo * Hp))));
+    }
+    sq = __shfl_sync(full_mask, sq, 0);
+    const float ic_lb = -fmul(fmul(sq, c.iw), 1.9073486328125e-06f);
+    const float nmaxf = (float)(vTmaxc + 1);
+    const float dneg_o = fmul(c.dw, fmul(nmaxf, fminf(lb_o, 0.0f)));
+    const float dneg_gs = fmul(c.dw, fmul(nmaxf, fminf(vTc < vhor ? lb_g : lb_s, 0.0f)));
+
+    // ================= (1) the chunks below the diagonal, nearest first, interleaved over the warps =================
+    Best carried{inf, inf, 0, 0};
+    for (int j = t - 1 - warp; j >= 0; j -= WARPS) {
+      const int vb0 = j * kChunk;
+      bool skip = false;
+      if (prune_ok) {
+        const int vbm = vb0 + kChunk - 1;  // chunks below the diagonal are full
+        const uint4 *b4 = reinterpret_cast<const uint4 *>(recb + (size_t)vbm * kRecBWords);
+        uint32_t Bl[20];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          const uint4 q4 = __ldg(b4 + k);
+          Bl[4 * k] = q4.x; Bl[4 * k + 1] = q4.y; Bl[4 * k + 2] = q4.z; Bl[4 * k + 3] = q4.w;
+        }
+        int l_ni = (int)(A[2] - Bl[2]);
+#pragma unroll
+        for (int k = 3; k < 10; k++) l_ni = min(l_ni, (int)(A[k] - Bl[k]));
+        int l_in = (int)(A[11] - Bl[11]);
+#pragma unroll
+        for (int k = 12; k < 19; k++) l_in = min(l_in, (int)(A[k] - Bl[k]));
+        const int l_g = min((int)(A[0] - Bl[0]), (int)(A[1] - Bl[1]));
+        const int l_s = (int)(A[kSkyClass] - Bl[kSkyClass]);
+        const float seg_o_lb = fminf((float)l_ni, fadd(ic_lb, (float)l_in));
+        const float lbo = fsub(ffma(seg_o_lb, c.sw, fadd(dneg_o, cmin_o[j])), slack);
+        const float seg_gs_lb = (float)(vTc < vhor ? l_g : l_s);
+        const float pr_gs = vTc < vhor ? cmin_g[j] : cmin_s[j];
+        const float lbgs = fsub(ffma(seg_gs_lb, c.sw, fadd(dneg_gs, pr_gs)), slack);
+        const bool lane_done = !row_ok || ((lbo > carried.o || lbo == inf) && (lbgs > carried.gs || lbgs == inf));
+        skip = __all_sync(full_mask, lane_done);
+      }
+      if (skip) continue;
+      __syncwarp();
+      stage(j);
+      // Q[vB] of the chunk: global -> this warp's shared copy (row k by lane k)
+      {
+        const float4 *src = reinterpret_cast<const float4 *>(qg + (size_t)(vb0 + lane) * kDynWords);
+        float4 *dst = reinterpret_cast<float4 *>(q_w + lane * kDynWords);
+        const float4 x0 = __ldcg(src), x1 = __ldcg(src + 1), x2 = __ldcg(src + 2);
+        dst[0] = x0; dst[1] = x1; dst[2] = x2;
+      }
+      __syncwarp();
+      wait();
+      const uint32_t *bchunk = stage_w;
+      const int nsteps = kChunk;
+      const int kg = max(0, min(nsteps, vhor + 1 - vb0));
+      const unsigned cb0 = lutb + 4u * (unsigned)(vb0 - 1);
+      const int n0 = vTc + 1 - vb0;
+      Best local{inf, inf, 0, 0};
+      int k0 = 0;
+      if (j == 0) {
+        // first segment, vB = 0 (:481-594)
+        const CellBase b = cell_base<true, 1, HAS_INVALID>(A, bchunk, ca, lutb, (float)n0, c);
+        RowInfo q{};
+        const float first_k_o = fmul(fadd(fadd((vT <= vhor) ? kLn2 : 0.0f, p.rows_log), p.max_dis_log), c.pw);
+        float cost_gs, cost_o;
+        cell_finish<true, true, 1>(b, 0.0f, q, first_k_gs, first_k_o, c, cost_gs, cost_o);
+        if (cost_gs < local.gs) { local.gs = cost_gs; local.vb_gs = 0; }
+        if (cost_o < local.o) { local.o = cost_o; local.vb_o = 0; }
+        k0 = 1;
+      }
+      if (t * kChunk >= vhor)
+        dp_steps<true, 3, false, HAS_INVALID>(A, bchunk, cb0, ca, nullptr, q_w, vb0, k0, max(k0, kg), n0, lane, c, local);
+      else
+        dp_steps<true, 1, false, HAS_INVALID>(A, bchunk, cb0, ca, nullptr, q_w, vb0, k0, max(k0, kg), n0, lane, c, local);
+      dp_steps<true, 0, false, HAS_INVALID>(A, bchunk, cb0, ca, nullptr, q_w, vb0, max(k0, kg), nsteps, n0, lane, c, local);
+      merge_best(carried, local);
+      my_units++;
+    }
+    // ---- the warps' minima -> warp 0 ----
+    merge[warp * 32 + lane] = make_float4(carried.gs, carried.o, __int_as_float(carried.vb_gs), __int_as_float(carried.vb_o));
+    __syncthreads();
+
+    // ================= (2) the diagonal unit: the wavefront =================
+    if (warp == 0) {
+      Best best = carried;
+#pragma unroll
+      for (int w = 1; w < WARPS; w++) {
+        const float4 m4 = merge[w * 32 + lane];
+        merge_best(best, Best{m4.x, m4.y, __float_as_int(m4.z), __float_as_int(m4.w)});
+      }
+      const int j = t, vb0 = t * kChunk;
+      const int nsteps = min(kChunk, H - vb0);
+      const int kg = max(0, min(nsteps, vhor + 1 - vb0));
+      stage(j);
+      for (int i = lane; i < (kChunk + 1) * kStatWords; i += 32)
+        sst[i] = (vb0 + i / kStatWords) < H ? __ldg(S + (size_t)vb0 * kStatWords + i) : 0.0f;
+      __syncwarp();
+      wait();
+      const uint32_t *bchunk = stage_w;
+      float *qs_slot = q_w;  // Q[vb0 .. vb0+31] as they become known
+      // prefix values at the start row of the best object segment so far (previous_mean needs them)
+      float lo_d = f_(__ldg(rec + (size_t)kRecDisp * Hp + best.vb_o));
+      float lo_v = f_(__ldg(rec + (size_t)kRecValid * Hp + best.vb_o));
+      if (j > 0) {
+        if (lane < kDynWords) qs_slot[lane] = qnext[lane];
+        __syncwarp();
+      }
+      // smallest priors of the rows of this chunk (for the bounds of later tiles)
+      float mn_o = inf, mn_g = inf, mn_s = inf;
+      auto note_row = [&](const RowInfo &q, int vB) {
+        const bool ground_side = vB - 1 < vhor;
+        mn_o = fminf(mn_o, object_prior_floor(q, ground_side, c.pw));
+        if (ground_side) mn_g = fminf(mn_g, q.gs_k);
+        else mn_s = fminf(mn_s, q.gs_k);
+      };
+      auto finish_row = [&](int vB, int src_lane, float hi_d, float hi_v) {
+        const float c_gs = __shfl_sync(full_mask, best.gs, src_lane), c_o = __shfl_sync(full_mask, best.o, src_lane);
+        const int o_vb = __shfl_sync(full_mask, best.vb_o, src_lane);
+        const float l_d = __shfl_sync(full_mask, lo_d, src_lane), l_v = __shfl_sync(full_mask, lo_v, src_lane);
+        const bool ground_side = vB - 1 < vhor;
+        const float pm = segment_mean(hi_d, l_d, hi_v, l_v, vB - o_vb, HAS_INVALID);
+        RowPriors rp;
+        return make_row_info(sst + (vB - vb0) * kStatWords, ground_side, ground_side ? c_gs : inf, c_o,
+                             ground_side ? inf : c_gs, pm, odr, p, &rp);
+      };
+      auto base_of = [&](int k) {
+        const int vB = vb0 + k;
+        return cell_base<false, 2, HAS_INVALID>(A, bchunk + k * kRecBWords, ca, lutb + 4u * (unsigned)(vB - 1),
+                                                (float)max(vTc + 1 - vB, 1), c, k < kg);
+      };
+      CellBase b_cur = (j == 0) ? cell_base<true, 1, HAS_INVALID>(A, bchunk, ca, lutb, (float)(vTc + 1), c)
+                                : base_of(0);
+      for (int k = 0; k < nsteps; k++) {
+        const int vB = vb0 + k;
+        const float ps_d = f_(bchunk[k * kRecBWords + kRecDisp]), ps_v = f_(bchunk[k * kRecBWords + kRecValid]);
+        CellBase b_next = b_cur;
+        if (k + 1 < nsteps) b_next = base_of(k + 1);
+        RowInfo q{};
+        if (k > 0) {
+          q = finish_row(vB, k - 1, ps_d, ps_v);
+          if (lane == 0) {
+            store_row_info(qs_slot + k * kDynWords, q);
+            pm_col[vB] = q.pm;
+          }
+          note_row(q, vB);
+        } else if (vB > 0) {
+          q = load_row_info(qs_slot);
+          note_row(q, vB);
+        }
+        float cost_gs, cost_o;
+        if (vB == 0) {
+          const float first_k_o = fmul(fadd(fadd((vT <= vhor) ? kLn2 : 0.0f, p.rows_log), p.max_dis_log), c.pw);
+          cell_finish<true, true, 1>(b_cur, 0.0f, q, first_k_gs, first_k_o, c, cost_gs, cost_o);
+        } else {
+          cell_finish<true, false, 2>(b_cur, 0.0f, q, 0.0f, 0.0f, c, cost_gs, cost_o, k < kg);
+        }
+        const bool live = row_ok && lane >= k;
+        if (live && cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = vB; }
+        if (live && cost_o < best.o) { best.o = cost_o; best.vb_o = vB; lo_d = ps_d; lo_v = ps_v; }
+        b_cur = b_next;
+      }
+      if (t == 0) {
+        // the first-segment priors of vB = 0 (the smaller of the two object variants)
+        mn_g = fminf(mn_g, first_k_gs);
+        mn_o = fminf(mn_o, fmul(fadd(fadd(0.0f, p.rows_log), p.max_dis_log), c.pw));
+      }
+      // Q[vb0 + 32] for the next diagonal (row vb0 + 31 is final now)
+      if (vb0 + kChunk < H) {
+        const int vB = vb0 + kChunk;
+        const RowInfo q = finish_row(vB, 31, f_(__ldg(rec + (size_t)kRecDisp * Hp + vB)),
+                                     f_(__ldg(rec + (size_t)kRecValid * Hp + vB)));
+        if (lane == 0) {
+          store_row_info(qnext, q);
+          pm_col[vB] = q.pm;
+        }
+      }
+      if (row_ok) store_best(out + vT, best);
+      __syncwarp();
+      // publish Q of the chunk for the later tiles: shared copy -> global (row k by lane k), and its smallest priors
+      {
+        const float4 *srcq = reinterpret_cast<const float4 *>(qs_slot + lane * kDynWords);
+        float4 *dstq = reinterpret_cast<float4 *>(qg + (size_t)(vb0 + lane) * kDynWords);
+        if (lane < nsteps) { __stcg(dstq, srcq[0]); __stcg(dstq + 1, srcq[1]); __stcg(dstq + 2, srcq[2]); }
+      }
+      if (lane == 0) { cmin_o[t] = mn_o; cmin_g[t] = mn_g; cmin_s[t] = mn_s; }
+      my_units++;
+    }
+    __syncthreads();
+  }
+  if (lane == 0 && my_units) atomicAdd(units_evaluated, my_units);
+}
+
 }  // namespace
 
 size_t dp_smem_bytes(const KParams &p, bool pairwise) {
@@ -995,6 +1341,48 @@ static void launch_unary_pruned(const KParams &p, const BatchBuffers &b, int nco
   else launch_unary_pruned_warps<HAS_INVALID, kDpWarps>(p, b, ncolumns, s);
 }
 
+template <bool HAS_INVALID, int WARPS>
+static void launch_pairwise_walk_warps(const KParams &p, const BatchBuffers &b, int ncolumns, cudaStream_t s) {
+  const size_t smem = WalkLayout(p.rows, p.max_dis, WARPS).total;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(dp_pairwise_walk_kernel<HAS_INVALID, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    configured = smem;
+  }
+  dp_pairwise_walk_kernel<HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
+      b.records, b.records_b, b.object_lut, b.stat, b.ground, b.pm, b.qrows, b.vhor, b.object_disparity_range, b.dp,
+      b.dp_units, p);
+}
+
+template <bool HAS_INVALID>
+static void launch_pairwise_walk(const KParams &p, const BatchBuffers &b, int ncolumns, cudaStream_t s) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  bool latency = ncolumns < 2 * sms;
+  if (const char *e = std::getenv("ISX_DP_WARPS")) {
+    if (std::atoi(e) == kDpWarps) latency = false;
+    if (std::atoi(e) == kDpWarpsLatency) latency = true;
+  }
+  // throughput: ONE warp per column (16 columns per SM, no barrier between the tiles of a column, the warp's
+  // carried minima see every chunk it evaluated); ISX_WALK_WARPS=4 keeps the 4-warp CTA per column for A/B runs
+  int tw = 1;
+  if (const char *e = std::getenv("ISX_WALK_WARPS")) tw = std::atoi(e);
+  if (latency) launch_pairwise_walk_warps<HAS_INVALID, kDpWarpsLatency>(p, b, ncolumns, s);
+  else if (tw == kDpWarps) launch_pairwise_walk_warps<HAS_INVALID, kDpWarps>(p, b, ncolumns, s);
+  else launch_pairwise_walk_warps<HAS_INVALID, 1>(p, b, ncolumns, s);
+}
+
+// Which pairwise kernel runs: the tile-major walk (ISX_PAIRWISE_WALK=1) or the chunk-major exhaustive one.
+bool pairwise_walk_enabled() {
+  const char *e = std::getenv("ISX_PAIRWISE_WALK");
+  return e ? std::atoi(e) != 0 : (ISX_PAIRWISE_WALK_DEFAULT != 0);
+}
+
 void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s) {
   const int ncolumns = nframes * p.realcols;
   const size_t smem = dp_smem_bytes(p, pairwise);
@@ -1002,7 +1390,10 @@ void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwi
   // ISX_UNARY_EXHAUSTIVE=1: the unary DP without the walk from the diagonal (every unit of every tile)
   const char *ex = std::getenv("ISX_UNARY_EXHAUSTIVE");
   const bool exhaustive = ex && std::atoi(ex) != 0;
-  if (pairwise) {
+  if (pairwise && pairwise_walk_enabled() && b.qrows != nullptr) {
+    if (has_invalid) launch_pairwise_walk<true>(p, b, ncolumns, s);
+    else launch_pairwise_walk<false>(p, b, ncolumns, s);
+  } else if (pairwise) {
     if (has_invalid) launch_dp_variant<true, true>(p, b, ncolumns, smem, s);
     else launch_dp_variant<true, false>(p, b, ncolumns, smem, s);
   } else if (!exhaustive) {

@@ -23,6 +23,7 @@ struct BatchBuffers {
   uint32_t *records_b = nullptr;       // [B][C][rec_stride][kRecBWords], row-major copy (common.cuh)
   float *object_lut = nullptr;         // [B][C][D][lut_stride]
   float *pm = nullptr;                 // [B][C][H] previous_mean of row vB-1 (pairwise; backtracking re-derives priors)
+  float *qrows = nullptr;              // [B][C][rec_stride][kDynWords] transition records Q[vB] (pairwise tile-major walk)
   float4 *dp = nullptr;                // [B][C][H]: {cost_gs, cost_obj, as_float(vB_gs), as_float(vB_obj)}
   // model tables (device copies of HostModel vectors)
   const float *obj_cost_lut = nullptr;       // [D][D]
@@ -48,6 +49,7 @@ void launch_join_columns(const KParams &p, const BatchBuffers &b, int nframes, c
 void launch_frame_tables(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
 void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
 void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s);
+bool pairwise_walk_enabled();
 void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s);
 // segmentation ingest (FlipAndPad, ingest.cu): cnn float [n][channels][hs][ws] -> seg int32 [n][C][channels][hs2]
 void launch_flip_and_pad(const KParams &p, const float *cnn, int32_t *seg, int nframes, int hs, int ws,

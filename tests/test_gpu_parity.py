@@ -51,9 +51,16 @@ def dp_warps(request, monkeypatch):
     return request.param
 
 
+@pytest.fixture(params=["0", "1"], ids=["chunkmajor", "tilewalk"])
+def pairwise_walk(request, monkeypatch):
+    """Both pairwise DP kernels: chunk-major exhaustive, and the tile-major walk with exact pruning."""
+    monkeypatch.setenv("ISX_PAIRWISE_WALK", request.param)
+    return request.param
+
+
 @pytest.mark.skipif(not refbind.available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_bit_exact_against_reference_cuda_build(case, dp_warps):
+def test_bit_exact_against_reference_cuda_build(case, dp_warps, pairwise_walk):
     name, mode, rows, cols, step, frame, invalid, median = case
     pairwise = mode == "pairwise"
     pre = _preset(mode, rows, cols, step, invalid, median)
@@ -139,6 +146,55 @@ def test_unary_branch_and_bound_is_exact(shape, dp_warps, monkeypatch):
             assert r["exact"] == 1.0 and r["close"] == 1.0 and r["bitwise"] >= 0.995, r
             assert parity.compare_instances(inst, rinst)["same_partition"]
         ref.close()
+
+
+PAIRWISE_WALKS = {
+    "tilewalk": {"ISX_PAIRWISE_WALK": "1"},                                   # tile-major, pruned
+    "tilewalk_all": {"ISX_PAIRWISE_WALK": "1", "ISX_PAIRWISE_PRUNE": "0"},    # the same walk without the bound test
+    "tilewalk_cta": {"ISX_PAIRWISE_WALK": "1", "ISX_WALK_WARPS": "4"},        # a 4-warp CTA per column instead of a warp
+    "chunkmajor": {"ISX_PAIRWISE_WALK": "0"},                                 # exhaustive
+}
+
+
+@pytest.mark.parametrize("shape", [(256, 512, 8, -1.0), (200, 328, 8, 0.0), (784, 1792, 8, 0.0), (1024, 2048, 8, 0.0),
+                                   (1024, 1024, 4, 0.0)],
+                         ids=lambda s: f"{s[0]}x{s[1]}w{s[2]}inv{s[3]:g}")
+def test_pairwise_tile_walk_is_exact(shape, dp_warps, monkeypatch):
+    """The tile-major pairwise DP (with and without pruning) returns byte-identical Sections, instance records and
+    full (cost, argmin) tables to the chunk-major exhaustive kernel."""
+    rows, cols, step, invalid = shape
+    pre = _preset("pairwise", rows, cols, step, invalid, False)
+    frames = [synth.make_frame(f, rows=rows, cols=cols, column_step=step) for f in (1, 6)]
+    results, work = {}, {}
+    for walk, env in PAIRWISE_WALKS.items():
+        for k in ("ISX_PAIRWISE_WALK", "ISX_PAIRWISE_PRUNE", "ISX_WALK_WARPS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        st = api.make_stixels(pre, max_batch=2)
+        out = []
+        for fr in frames:
+            st.SetDisparityImage(fr.disparity)
+            st.SetSegmentation(fr.segmentation)
+            st.SetRoadParameters(**fr.road)
+            data = st.Compute(True)
+            out.append((data.sections.copy(), st.instance_records().copy(),
+                        st.read_tensor(L.T_COST_TABLE).copy(), st.read_tensor(L.T_INDEX_TABLE).copy()))
+        sec_b, _, _ = st.ComputeBatch(True, np.stack([f.disparity for f in frames]),
+                                      np.stack([f.segmentation for f in frames]), [f.road for f in frames])
+        for i in range(len(frames)):
+            assert parity.same_used_sections(sec_b[i], out[i][0])
+        results[walk], work[walk] = out, st.dp_units()
+        st.Finish()
+    for walk in ("tilewalk", "tilewalk_all", "tilewalk_cta"):
+        for (s0, i0, c0, x0), (s1, i1, c1, x1) in zip(results["chunkmajor"], results[walk]):
+            assert np.array_equal(c0.view(np.int32), c1.view(np.int32)), walk
+            assert np.array_equal(x0, x1), walk
+            assert np.array_equal(s0.view(np.uint8), s1.view(np.uint8)), walk
+            assert np.array_equal(i0.view(np.uint8), i1.view(np.uint8)), walk
+    ev, tot = work["tilewalk"]
+    assert work["tilewalk_all"][0] == tot and work["chunkmajor"][0] == tot and 0 < ev <= tot
+    print(f"pairwise tile walk {rows}x{cols} w{step}: {ev} of {tot} units evaluated")
 
 
 def test_against_golden_vectors(golden_files):
