@@ -41,13 +41,13 @@ WORKLOADS = {
 ROWS, COLS = 1024, 2048
 OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of a 32-frame chunk, from the `ncu --set full` captures
-# summarised in profiles/r1i_unary_b32.txt and profiles/r1h_pairwise_b32.txt (width 8; no capture for width 4).
+# summarised in profiles/r1j_{unary,pairwise}_b32.txt (width 8; no capture for width 4).
 # "tables" = join_columns + column_tables + object_lut kernels.
 NCU_CHUNK = 32
 NCU_TRAFFIC = {
-    ("unary", 8): dict(dp=(3.4238 + 0.1345) * 1e9,   # dp_unary_pruned_kernel (r1i)
+    ("unary", 8): dict(dp=(3.4238 + 0.1345) * 1e9,   # dp_unary_pruned_kernel
                        tables=(0.2685 + 0.0267 + 0.1555 + 2.1040 + 0.0338 + 4.2369) * 1e9),
-    ("pairwise", 8): dict(dp=None,   # dp_pairwise_walk_kernel: filled from the next capture
+    ("pairwise", 8): dict(dp=(12.9455 + 0.5673) * 1e9,   # dp_pairwise_walk_kernel (r1j): 2368 columns in flight, L2 hit 31 %
                           tables=(0.2685 + 0.0273 + 0.1559 + 2.1009 + 0.0338 + 4.2363) * 1e9),
 }
 
@@ -368,7 +368,7 @@ def main():
             clocks=clk.summary(),
             roofline=dict(bound="alu", kernel="dp_kernel", achieved=achieved, peak=peak, unit="Tlane-op/s",
                           frac=achieved / peak, traffic=ncu["dp"] if ncu else None,
-                          traffic_note=f"DRAM bytes per launch (ncu, profiles/r1i_unary_b32.txt / r1h_pairwise_b32.txt); the tables one launch reads "
+                          traffic_note=f"DRAM bytes per launch (ncu, profiles/r1j_*_b32.txt); the tables one launch reads "
                                        f"once are {dp_alg_bytes} bytes",
                           units_evaluated_frac=eval_frac,
                           note=f"{OPS_PER_CELL[wl['mode']]} lane-ops per DP cell x {cells_eval_per_launch:.0f} cells "
@@ -401,9 +401,10 @@ def main():
                 st.GetInstanceStixels()
                 return 1e3 * (time.perf_counter() - t0)
 
+            torch.cuda.synchronize()
             lat = sorted([one_frame(pin[0].numpy(), pin[1].numpy(), pin[2].numpy().view(api.L.SECTION_DTYPE))
-                          for _ in range(43)][3:])
-            lat_pageable = sorted([one_frame(fr.disparity, fr.segmentation, None) for _ in range(23)][3:])
+                          for _ in range(120)][40:])   # 40 warm-up frames: clocks and caches settle after the batches
+            lat_pageable = sorted([one_frame(fr.disparity, fr.segmentation, None) for _ in range(50)][10:])
             line["latency_ms_batch1"] = dict(p50=lat[len(lat) // 2], p99=lat[-1], buffers="pinned",
                                              p50_pageable=lat_pageable[len(lat_pageable) // 2])
         if not args.no_cpu_baseline and world == 1:

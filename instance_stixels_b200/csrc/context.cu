@@ -304,7 +304,7 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
     c->dp_units_total += (unsigned long long)n * C * (nt * (nt + 1) / 2);
     const char *ex = std::getenv("ISX_UNARY_EXHAUSTIVE");
     // the pruning kernels count on the device
-    const bool walks_all = (pairwise && !(pairwise_walk_enabled() && b.qrows)) || (!pairwise && ex && std::atoi(ex) != 0);
+    const bool walks_all = (pairwise && !pairwise_walk_used(n * C, b.qrows != nullptr)) || (!pairwise && ex && std::atoi(ex) != 0);
     c->dp_units_pairwise += walks_all ? (unsigned long long)n * C * (nt * (nt + 1) / 2) : 0;
   }
   mark(s);

@@ -1383,6 +1383,20 @@ bool pairwise_walk_enabled() {
   return e ? std::atoi(e) != 0 : (ISX_PAIRWISE_WALK_DEFAULT != 0);
 }
 
+// The tile-major walk runs one warp per column: it needs a launch that fills the 16 warp slots of every SM (ten
+// 1024 x 2048 frames at width 8); smaller launches keep the chunk-major kernel, whose 4 or 8 warps per column are
+// what a few hundred columns need.  ISX_DP_WARPS / ISX_WALK_WARPS (tests) force the walk's variants.
+bool pairwise_walk_used(int ncolumns, bool have_qrows) {
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const bool forced = std::getenv("ISX_DP_WARPS") != nullptr || std::getenv("ISX_WALK_WARPS") != nullptr;
+  return pairwise_walk_enabled() && have_qrows && (ncolumns >= 16 * sm_count || forced);
+}
+
 void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s) {
   const int ncolumns = nframes * p.realcols;
   const size_t smem = dp_smem_bytes(p, pairwise);
@@ -1390,7 +1404,7 @@ void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwi
   // ISX_UNARY_EXHAUSTIVE=1: the unary DP without the walk from the diagonal (every unit of every tile)
   const char *ex = std::getenv("ISX_UNARY_EXHAUSTIVE");
   const bool exhaustive = ex && std::atoi(ex) != 0;
-  if (pairwise && pairwise_walk_enabled() && b.qrows != nullptr) {
+  if (pairwise && pairwise_walk_used(ncolumns, b.qrows != nullptr)) {
     if (has_invalid) launch_pairwise_walk<true>(p, b, ncolumns, s);
     else launch_pairwise_walk<false>(p, b, ncolumns, s);
   } else if (pairwise) {

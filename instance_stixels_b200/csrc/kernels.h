@@ -50,6 +50,8 @@ void launch_frame_tables(const KParams &p, const BatchBuffers &b, int nframes, c
 void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s);
 void launch_dp(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s);
 bool pairwise_walk_enabled();
+// whether launch_dp takes the tile-major walk for a pairwise launch of `ncolumns` columns
+bool pairwise_walk_used(int ncolumns, bool have_qrows);
 void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pairwise, cudaStream_t s);
 // segmentation ingest (FlipAndPad, ingest.cu): cnn float [n][channels][hs][ws] -> seg int32 [n][C][channels][hs2]
 void launch_flip_and_pad(const KParams &p, const float *cnn, int32_t *seg, int nframes, int hs, int ws,
