@@ -552,6 +552,8 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &b.cand_scratch, ch * kInstanceClasses * cap));
   ISX_TRY(h, dev_alloc(h, &b.error_flag, 1));
   ISX_TRY(h, dev_alloc(h, &b.dp_units, 1));
+  ISX_TRY(h, dev_alloc(h, &b.col_flags, ch * C));
+  ISX_TRY(h, cudaMemset(b.col_flags, 0, ch * C * sizeof(int)));
   if (pairwise_walk_enabled()) {
     ISX_TRY(h, dev_alloc(h, &b.qrows, ch * C * (size_t)kp.rec_stride * kDynWords));
     ISX_TRY(h, cudaMemset(b.qrows, 0, ch * C * (size_t)kp.rec_stride * kDynWords * sizeof(float)));

@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kDpWarps ? ISX_PRUNED_CTA
 dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
                        const float *__restrict__ object_lut, const float *__restrict__ ground,
                        const int *__restrict__ vhor_arr, const float *__restrict__ inverse_height, float4 *dp_out,
-                       unsigned long long *__restrict__ units_evaluated, KParams p) {
+                       unsigned long long *__restrict__ units_evaluated, const int *__restrict__ col_flags, KParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kThreads = WARPS * 32;
   const unsigned full_mask = 0xffffffffu;
@@ -793,9 +793,10 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
   const float lb_s = fminf(p.pnexists_given_sky_log,
                            fadd(fminf(p.puniform_sky, p.normalization_sky), p.nopnexists_given_sky_log));
   const float lb_o = p.obj_cost_min;
-  // the bounds assume non-negative weights (NaN fails the test too): otherwise every chunk is evaluated
+  // the bounds assume non-negative weights (NaN fails the test too) and non-negative class values without int32
+  // wrap-around (col_flags, column_tables_kernel): otherwise every chunk is evaluated
   const bool prune_ok = ISX_UNARY_PRUNE && c.sw >= 0.0f && c.dw >= 0.0f && c.pw >= 0.0f && c.iw >= 0.0f &&
-                        p.prune_unary != 0;
+                        p.prune_unary != 0 && col_flags[gcol] == 0;
 
   unsigned ph0 = 0, ph1 = 0;  // phase parity of this warp's two buffers
   auto stage = [&](int ch, int b) {
@@ -998,7 +999,8 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__
                         const float *__restrict__ object_lut, const float *__restrict__ stat,
                         const float *__restrict__ ground, float *__restrict__ pm_out, float *__restrict__ qrows,
                         const int *__restrict__ vhor_arr, const float *__restrict__ object_disparity_range,
-                        float4 *dp_out, unsigned long long *__restrict__ units_evaluated, KParams p) {
+                        float4 *dp_out, unsigned long long *__restrict__ units_evaluated,
+                        const int *__restrict__ col_flags, KParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kThreads = WARPS * 32;
   const unsigned full_mask = 0xffffffffu;
@@ -1056,7 +1058,8 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__
   const float lb_s = fminf(p.pnexists_given_sky_log,
                            fadd(fminf(p.puniform_sky, p.normalization_sky), p.nopnexists_given_sky_log));
   const float lb_o = p.obj_cost_min;
-  const bool prune_ok = c.sw >= 0.0f && c.dw >= 0.0f && c.pw >= 0.0f && c.iw >= 0.0f && p.prune_pairwise != 0;
+  const bool prune_ok = c.sw >= 0.0f && c.dw >= 0.0f && c.pw >= 0.0f && c.iw >= 0.0f && p.prune_pairwise != 0 &&
+                        col_flags[gcol] == 0;
   const float slack = fadd(1.0f, c.dw);
   // first-segment priors (:189-199)
   const float first_k_gs = fmul(ffma(1.0f, kLn2, p.rows_log), c.pw);
@@ -1321,7 +1324,7 @@ static void launch_unary_pruned_warps(const KParams &p, const BatchBuffers &b, i
     configured = smem;
   }
   dp_unary_pruned_kernel<HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
-      b.records, b.records_b, b.object_lut, b.ground, b.vhor, b.inverse_height, b.dp, b.dp_units, p);
+      b.records, b.records_b, b.object_lut, b.ground, b.vhor, b.inverse_height, b.dp, b.dp_units, b.col_flags, p);
 }
 
 template <bool HAS_INVALID>
@@ -1352,7 +1355,7 @@ static void launch_pairwise_walk_warps(const KParams &p, const BatchBuffers &b, 
   }
   dp_pairwise_walk_kernel<HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
       b.records, b.records_b, b.object_lut, b.stat, b.ground, b.pm, b.qrows, b.vhor, b.object_disparity_range, b.dp,
-      b.dp_units, p);
+      b.dp_units, b.col_flags, p);
 }
 
 template <bool HAS_INVALID>

@@ -42,6 +42,7 @@ struct BatchBuffers {
   int *cand_label = nullptr;           // [B][8][C*200]
   int *cand_scratch = nullptr;         // [B][8][C*200] component representatives
   int *error_flag = nullptr;           // [1] sticky: column overflowed 200 stixels etc.
+  int *col_flags = nullptr;            // [B][C] 1: the column has negative class values -> no pruning in the DP
   unsigned long long *dp_units = nullptr;  // [1] 32 x 32-cell units the unary DP evaluated (it prunes the rest)
 };
 

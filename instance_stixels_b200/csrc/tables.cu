@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kTabThreads, 3)
 column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict__ segmentation,
                      const float *__restrict__ ground, const int *__restrict__ vhor_arr,
                      uint32_t *__restrict__ records, uint32_t *__restrict__ records_b,
-                     int *__restrict__ error_flag, KParams p) {
+                     int *__restrict__ error_flag, int *__restrict__ col_flags, KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = p.rows, C = p.realcols;
   const int col = blockIdx.x, f = blockIdx.y;
@@ -190,11 +190,17 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   const int K = p.n_classes;  // 19; channel K = y offsets, K+1 = x offsets
 
   // ---- 1/8-resolution channels (squared offsets like :411-416) ----
+  bool negative_class_value = false;
   for (int i = tid; i < 21 * nq; i += kTabThreads) {
     const int c = i / nq, q = i - c * nq;
     int v = 0;
     if (c < p.n_channels && q < p.hs2) v = seg_col[(size_t)c * p.hs2 + q];
-    if (c >= K) v = v * v;
+    if (c >= K) {
+      v = v * v;
+      negative_class_value |= v < 0 || v > (1 << 19);   // two channels x 1032 rows stay below 2^31
+    } else {
+      negative_class_value |= v < 0 || v > (1 << 20);   // likewise: the int32 prefix sums cannot wrap
+    }
     seg_s[c * segld + q] = v;
   }
   // ---- per-row terms (:371-446) ----
@@ -240,7 +246,11 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
     e_i64[2 * L.Hp + v] = mx * mx;
     e_i64[3 * L.Hp + v] = my * my;
   }
-  __syncthreads();
+  // The pruning DP kernels bound a segment's class sums from below by those of a shorter one, which needs
+  // non-negative values whose int32 prefix sums do not wrap (they are trunc(8 * -log softmax) and squared pixel
+  // offsets, wrappers.py:50-61); a column that breaks this is flagged and walked exhaustively.
+  const int any_negative = __syncthreads_or(negative_class_value ? 1 : 0);
+  if (tid == 0) col_flags[(size_t)f * C + col] = any_negative;
 
   // ---- prefix sums: warps 0-3 float (Blelloch order), 4-7 int64, all: 1/8-res ints ----
   if (warp < 4) {
@@ -392,7 +402,7 @@ void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, 
     configured = smem;
   }
   column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.records,
-                                                        b.records_b, b.error_flag, p);
+                                                        b.records_b, b.error_flag, b.col_flags, p);
   dim3 lgrid(p.realcols, (p.max_dis + 32 * kLutWarps - 1) / (32 * kLutWarps), nframes);
   object_lut_kernel<<<lgrid, kLutThreads, 0, s>>>(b.joined, b.obj_cost_lut_t, b.object_lut, p);
   g_launch_count += 2;

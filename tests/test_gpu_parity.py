@@ -197,6 +197,46 @@ def test_pairwise_tile_walk_is_exact(shape, dp_warps, monkeypatch):
     print(f"pairwise tile walk {rows}x{cols} w{step}: {ev} of {tot} units evaluated")
 
 
+@pytest.mark.parametrize("mode", ["unary", "pairwise"])
+def test_negative_class_values_disable_the_pruning_of_their_columns(mode, dp_warps, monkeypatch):
+    """The bounds of the pruning kernels need non-negative class values; a column with a negative one (the
+    reference just sums whatever it is given) is walked exhaustively -- results stay identical to the exhaustive
+    kernels, and the evaluated units show that exactly those columns lost their pruning."""
+    rows, cols = 512, 512
+    pairwise = mode == "pairwise"
+    pre = _preset(mode, rows, cols, 8, 0.0, False)
+    fr = synth.make_frame(2, rows=rows, cols=cols)
+    seg = fr.segmentation.copy()
+    bad_cols = [3, 17, 40]
+    for c in bad_cols:
+        seg[c, 5, 7] = -3          # one negative value of class 5 in each of three columns
+    outs, units = {}, {}
+    for name, env in {"pruning": {}, "exhaustive": {"ISX_UNARY_EXHAUSTIVE": "1", "ISX_PAIRWISE_WALK": "0"}}.items():
+        for k in ("ISX_UNARY_EXHAUSTIVE", "ISX_PAIRWISE_WALK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        res = []
+        for s_ in (fr.segmentation, seg):
+            st = api.make_stixels(pre, max_batch=1)
+            st.SetDisparityImage(fr.disparity)
+            st.SetSegmentation(s_)
+            st.SetRoadParameters(**fr.road)
+            data = st.Compute(pairwise)
+            res.append((data.sections.copy(), st.read_tensor(L.T_COST_TABLE).copy(),
+                        st.read_tensor(L.T_INDEX_TABLE).copy(), st.dp_units()))
+            st.Finish()
+        outs[name] = res
+    for (s0, c0, x0, _), (s1, c1, x1, _) in zip(outs["pruning"], outs["exhaustive"]):
+        assert np.array_equal(c0.view(np.int32), c1.view(np.int32)) and np.array_equal(x0, x1)
+        assert np.array_equal(s0.view(np.uint8), s1.view(np.uint8))
+    (ev_clean, tot), (ev_bad, _) = outs["pruning"][0][3], outs["pruning"][1][3]
+    per_col = tot // (cols // 8)
+    assert ev_clean < tot and ev_bad > ev_clean
+    # the three flagged columns are evaluated completely, the others as before (+- what the changed values prune)
+    assert ev_bad >= 3 * per_col
+
+
 def test_against_golden_vectors(golden_files):
     for path in golden_files:
         z = np.load(path)
