@@ -2,38 +2,29 @@
 // Replaces the first-segment block and the vB loop of StixelsKernel<PAIRWISE>
 // (InstanceStixels/src/StixelsKernels.cu:477-839).
 //
-// Mapping (B200): ONE CTA (8 warps) owns one (frame, column).  The column's rows
-// are cut into tiles of 32 top rows (lane l of a warp owns vT = a + l) and into
-// chunks of 32 candidate bottom rows vB.  A (tile, chunk) pair with tile >=
-// chunk is one unit of work: 32 x 32 DP cells.
+// The column's rows are cut into tiles of 32 top rows (lane l of a warp owns vT = a + l) and into chunks of 32
+// candidate bottom rows vB.  A (tile, chunk) pair with tile >= chunk is one unit of work: 32 x 32 DP cells,
+// evaluated by one warp with the records R[vT+1] of its rows in 30 registers ("A side", word-major copy of the
+// column tables) and the records R[vB] of the chunk in shared memory ("B side", row-major copy, one 4 KB bulk
+// async copy per chunk: cp.async.bulk + mbarrier).  Because one of GROUND/SKY is +inf for every row (ground only
+// exists below the horizon, sky only at/above it) the cost table keeps two slots per row: "gs" (ground if
+// vT < vhor else sky) and "object".  No tensor cores: the recurrence is min-plus, not a dense contraction.
 //
-//  * B side: the 32 prefix records of a chunk (4 KB, chunk-major copy of the
-//    column tables) travel global -> shared memory as ONE bulk async copy
-//    (cp.async.bulk, mbarrier complete_tx) into a ring of kStages slots; one
-//    elected lane is the producer, slots are recycled through empty barriers.
-//    Inside a unit the record of vB is read as 8 warp-uniform LDS.128.
-//  * A side: for a unit the warp loads its records R[vT+1] from the word-major
-//    copy (one coalesced line per word) into 30 registers; the running
-//    (cost, vB) minima of a tile live in shared memory between its units and
-//    are handed from the warp that did (tile, chunk-1) to the one doing
-//    (tile, chunk) through a per-tile mbarrier.  Strict '<' in ascending vB
-//    order reproduces the reference's tie rule (lowest vB wins).
-//  * Scheduling: units are handed out chunk-major from shared-memory counters
-//    (one atomicAdd per unit), lowest tile first, so the warps stay within a
-//    chunk or two of each other, nobody waits at a CTA-wide barrier, and in
-//    pairwise mode the units that the next diagonal needs are taken first.
+// Three kernels share the cell arithmetic below (cell_base / cell_finish / dp_steps):
 //
-// Pairwise mode adds the wavefront along the diagonal units (tile == chunk):
-// the warp that draws the diagonal unit j first evaluates the chain-independent part of its 32 x 32
-// cells in parallel (pass 1, parked in shared memory), then finalises row after
-// row (pass 2: row vB-1 -> transition scalars Q[vB] -> row vB) exchanging the
-// finished row through warp shuffles, and publishes Q[vB] of the chunk for the
-// off-diagonal units of the other warps through an mbarrier.
-// No tensor cores: the recurrence is min-plus, not a dense contraction.
-//
-// Because one of GROUND/SKY is +inf for every row (ground only exists below
-// the horizon, sky only at/above it) the cost table keeps two slots per row:
-// "gs" (ground if vT < vhor else sky) and "object".
+//  dp_kernel<PAIRWISE>        chunk-major, every unit.  One CTA (4 or 8 warps) per column; the chunk's B records sit
+//                             in a ring of shared-memory slots, units are drawn from shared-memory counters chunk by
+//                             chunk (lowest tile first), a tile's running (cost, vB) minima are handed from unit
+//                             (t, j-1) to (t, j) through the output array; in pairwise mode the diagonal units
+//                             (tile == chunk) form the serial chain of the column (row vB-1 final -> transition
+//                             scalars Q[vB] -> row vB) and are taken the moment their tile is complete.  Strict '<'
+//                             in ascending vB order is the reference's tie rule (lowest vB wins).
+//                             Used for small pairwise launches, and as the exhaustive reference of the other two.
+//  dp_unary_pruned_kernel     unary mode: a warp owns a tile and walks its chunks downwards from the diagonal until
+//                             a lower bound proves that nothing below can win (exact branch and bound).
+//  dp_pairwise_walk_kernel    pairwise mode: one warp per column, tile by tile behind the diagonal chain, each
+//                             off-diagonal unit only if its lower bound does not exceed the carried minima.
+// Both pruning kernels return the same bytes as dp_kernel (tests/test_gpu_parity.py); their headers derive the bounds.
 #include <cstdlib>
 
 #include "dp_common.cuh"
