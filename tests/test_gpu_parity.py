@@ -237,6 +237,69 @@ def test_negative_class_values_disable_the_pruning_of_their_columns(mode, dp_war
     assert ev_bad >= 3 * per_col
 
 
+def _stress_inputs(kind, rows, cols, step, seed):
+    """Inputs far from the synthetic street scenes, to stress the bounds of the pruning kernels."""
+    rng = np.random.default_rng(seed)
+    fr = synth.make_frame(seed % 7, rows=rows, cols=cols, column_step=step)
+    disp, seg = fr.disparity.copy(), fr.segmentation.copy()
+    used = (rows + 7) // 8
+    if kind == "zero_costs":            # a CNN that is certain everywhere: every class sum is 0, only priors decide
+        seg[:, :19, :] = 0
+    elif kind == "noise_costs":         # no structure at all
+        seg[:, :19, :used] = rng.integers(0, 60, size=seg[:, :19, :used].shape)
+    elif kind == "sparse_costs":        # mostly zeros, a few expensive rows
+        seg[:, :19, :used] = np.where(rng.random(seg[:, :19, :used].shape) < 0.03, 200, 0)
+    elif kind == "all_invalid":         # no disparity measurement at all
+        disp[:] = 0.0
+    elif kind == "random_disparity":
+        disp[:] = rng.uniform(0.0, 127.0, size=disp.shape).astype(np.float32)
+    elif kind == "huge_offsets":        # instance offsets at the edge of the exact-float range
+        seg[:, 19:21, :used] = rng.integers(-400, 400, size=seg[:, 19:21, :used].shape)
+    return disp, seg, fr.road
+
+
+@pytest.mark.parametrize("kind", ["zero_costs", "noise_costs", "sparse_costs", "all_invalid", "random_disparity",
+                                  "huge_offsets"])
+@pytest.mark.parametrize("mode,weights", [
+    ("unary", {}), ("pairwise", {}),
+    ("unary", dict(prior_weight=1.0, disparity_weight=1.0)),                 # the prior no longer dominates
+    ("pairwise", dict(segmentation_weight=0.05, instance_weight=0.05, disparity_weight=0.5)),
+])
+def test_pruning_kernels_are_exact_on_unusual_inputs(kind, mode, weights, monkeypatch):
+    rows, cols, step = 512, 256, 8
+    pairwise = mode == "pairwise"
+    pre = _preset(mode, rows, cols, step, 0.0, False)
+    pre.update(weights)
+    disp, seg, road = _stress_inputs(kind, rows, cols, step, seed=len(kind) + len(weights))
+    monkeypatch.setenv("ISX_DP_WARPS", "4")     # forces the walk variants even for one frame
+    outs = {}
+    for name, env in {"pruning": {}, "exhaustive": {"ISX_UNARY_EXHAUSTIVE": "1", "ISX_PAIRWISE_WALK": "0"}}.items():
+        for k in ("ISX_UNARY_EXHAUSTIVE", "ISX_PAIRWISE_WALK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        st = api.make_stixels(pre, max_batch=1)
+        st.SetDisparityImage(disp)
+        st.SetSegmentation(seg)
+        st.SetRoadParameters(**road)
+        try:
+            data = st.Compute(pairwise)
+        except api.StixelsError as e:       # e.g. > 199 stixels in a column: both kernels must agree on that too
+            outs[name] = ("error", str(e))
+            st.Finish()
+            continue
+        outs[name] = (data.sections.copy(), st.read_tensor(L.T_COST_TABLE).copy(),
+                      st.read_tensor(L.T_INDEX_TABLE).copy())
+        st.Finish()
+    a, b = outs["pruning"], outs["exhaustive"]
+    a_err, b_err = isinstance(a[0], str), isinstance(b[0], str)
+    assert a_err == b_err, (a[1] if a_err else "ok", b[1] if b_err else "ok")
+    if not a_err:
+        assert np.array_equal(a[1].view(np.int32), b[1].view(np.int32))
+        assert np.array_equal(a[2], b[2])
+        assert np.array_equal(a[0].view(np.uint8), b[0].view(np.uint8))
+
+
 def test_against_golden_vectors(golden_files):
     for path in golden_files:
         z = np.load(path)
