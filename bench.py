@@ -226,6 +226,21 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the stixel path has no CPU fallback")
     torch.cuda.set_device(local)
+    # Bind this process to the CPUs next to its GPU before any host buffer is allocated or pinned: the host <-> device
+    # copies of the e2e arm then stay on the local NUMA node (what a multi-GPU launcher does per rank).
+    host_cpus = None
+    if not os.environ.get("ISX_BENCH_NO_AFFINITY"):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                nvh = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(local).uuid))
+            except Exception:
+                nvh = pynvml.nvmlDeviceGetHandleByIndex(local)
+            pynvml.nvmlDeviceSetCpuAffinity(nvh)
+            host_cpus = len(os.sched_getaffinity(0))
+        except Exception:
+            host_cpus = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -365,6 +380,7 @@ def main():
             e2e_single=dict(value=world * B * args.steps / e2e_single_s, unit="frames/s",
                             pipeline="1 host thread, 1 context, synchronous batches"),
             gpu_launches=int(launches),
+            host=dict(cpus_bound_to_gpu=host_cpus),
             clocks=clk.summary(),
             roofline=dict(bound="alu", kernel="dp_kernel", achieved=achieved, peak=peak, unit="Tlane-op/s",
                           frac=achieved / peak, traffic=ncu["dp"] if ncu else None,
@@ -408,6 +424,10 @@ def main():
             line["latency_ms_batch1"] = dict(p50=lat[len(lat) // 2], p99=lat[-1], buffers="pinned",
                                              p50_pageable=lat_pageable[len(lat_pageable) // 2])
         if not args.no_cpu_baseline and world == 1:
+            try:   # the CPU baseline gets every core of the box again
+                os.sched_setaffinity(0, range(os.cpu_count()))
+            except Exception:
+                pass
             line["cpu_baseline"] = cpu_baseline(wl, 24)
         print(json.dumps(line), flush=True)
     st.Finish()
