@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ISX_ABI_VERSION 1
+#define ISX_ABI_VERSION 2
 
 typedef enum isx_status {
   ISX_OK = 0,
@@ -111,6 +111,18 @@ typedef struct isx_instance {
   int32_t label;
   int32_t semantic_class;
 } isx_instance;
+
+/* Where one frame of a batch lies in the packed result arrays (isx_wait_batch_packed): the used Sections of its
+ * columns back to back (column 0 first, inside a column top to bottom like the reference's array, no
+ * terminators), and its instance records.  `error` holds the per-frame error bits (1: a column reached
+ * MAX_STIXELS_PER_COLUMN, 2: instance offsets out of range); `overflow` != 0 means the frame did not fit the
+ * packed arrays (bit 0: sections, bit 1: instance records) and must be read with isx_fetch_batch_results. */
+typedef struct isx_packed_frame {
+  int32_t section_offset, section_count;
+  int32_t instance_offset, instance_count;
+  int32_t error, overflow;
+  int32_t reserved[2];
+} isx_packed_frame;
 
 typedef struct isx_context *isx_handle;
 
@@ -230,6 +242,27 @@ int isx_synchronize(isx_handle h);
 int isx_submit_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
                           const isx_road *roads, isx_section *sections);
 int isx_wait_batch_host(isx_handle h, isx_instance *instances, int instances_capacity, int32_t *instance_offsets);
+/* Zero-copy form of isx_wait_batch_host: waits for the oldest batch in flight and hands out the packed results
+ * where the device wrote them (pinned host memory owned by the handle): `*sections` / `*instances` are the packed
+ * arrays, `*counts` = [n][realcols] stixels per column, `*frames` = [n] descriptors (offsets into the packed
+ * arrays), `*n` = frames of the batch.  The `sections` buffer given to isx_submit_batch_host (may be NULL for
+ * callers that only use this form) is not written.  The pointers stay valid until the second isx_submit_batch_host
+ * after this call (two result sets alternate).  Any pointer argument may be NULL. */
+int isx_wait_batch_packed(isx_handle h, const isx_section **sections, const int32_t **counts,
+                          const isx_instance **instances, const isx_packed_frame **frames, int *n);
+/* Narrow host inputs, extensions beside the float API for callers whose data is narrower at its source (over the
+ * host link the input bytes are what limits a batch): `disparity` = uint16 [n][rows][cols], pixel value =
+ * u16 * disparity_scale (a 16-bit disparity PNG with scale 1/256 is what apps/run_cityscapes.cu:141-147 turns
+ * into floats on the host); `segmentation` = int16 [n][realcols][channels][ceil(rows/8)], the same values as
+ * the int32 tensor without the zero padding to rows_power2_segmentation (isx_narrow_segmentation_elems() per
+ * frame).  Widened on the device; results are bit-identical to the float entry points called with the widened
+ * arrays.  rows*cols must be a multiple of 8.  Otherwise like isx_compute_batch_host / isx_submit_batch_host. */
+size_t isx_narrow_segmentation_elems(isx_handle h);
+int isx_compute_batch_host_u16(isx_handle h, int pairwise, int n, const uint16_t *disparity, float disparity_scale,
+                               const int16_t *segmentation, const isx_road *roads, isx_section *sections,
+                               isx_instance *instances, int instances_capacity, int32_t *instance_offsets);
+int isx_submit_batch_host_u16(isx_handle h, int pairwise, int n, const uint16_t *disparity, float disparity_scale,
+                              const int16_t *segmentation, const isx_road *roads, isx_section *sections);
 /* Copy results of the last device batch to host buffers (same layouts as
  * isx_compute_batch_host). */
 int isx_fetch_batch_results(isx_handle h, int n, isx_section *sections, isx_instance *instances,
@@ -242,6 +275,24 @@ uint64_t isx_stream(isx_handle h);
  * and isx_rasterize_batch_device do this themselves; a caller that records its own events or launches its own
  * consumers on isx_stream() after isx_compute_batch_device calls it first.  Asynchronous. */
 int isx_flush(isx_handle h);
+
+/* ------------------------------------------------------------------ */
+/* Frame pool: one context and one host worker thread per GPU inside ONE process; a call shards
+ * its frames into contiguous blocks, frame f -> worker f * G / n, and every worker streams its block through
+ * isx_submit_batch_host / isx_wait_batch_host in sub-batches of `max_batch` frames (two in flight).  No
+ * collective: frames are independent, results land in the caller's arrays in frame order.  `devices` may name a
+ * GPU more than once (several workers on one GPU).  The reference has no counterpart (one frame per Compute). */
+typedef struct isx_pool *isx_pool_handle;
+int isx_pool_create(isx_pool_handle *out, const int *devices, int n_devices, const isx_config *cfg, int max_batch);
+int isx_pool_destroy(isx_pool_handle p);
+int isx_pool_size(isx_pool_handle p);          /* number of workers */
+int isx_pool_real_cols(isx_pool_handle p);
+size_t isx_pool_segmentation_elems(isx_pool_handle p);
+/* Same arguments and layouts as isx_compute_batch_host, any n >= 1.  Blocks until all frames are done. */
+int isx_pool_compute_host(isx_pool_handle p, int pairwise, int n, const float *disparity,
+                          const int32_t *segmentation, const isx_road *roads, isx_section *sections,
+                          isx_instance *instances, int instances_capacity, int32_t *instance_offsets);
+const char *isx_pool_last_error(isx_pool_handle p);
 
 /* ------------------------------------------------------------------ */
 /* Introspection for parity tests / profiling (device -> host copies of

@@ -28,6 +28,10 @@ EXPORTS = [
     "isx_compute_batch_host", "isx_submit_batch_host", "isx_wait_batch_host", "isx_compute_batch_device", "isx_synchronize", "isx_fetch_batch_results",
     "isx_stream", "isx_tensor_elems", "isx_read_tensor", "isx_set_profiling", "isx_get_stage_times",
     "isx_chunk_frames",
+    # compact results / narrow inputs / frame pool
+    "isx_wait_batch_packed", "isx_narrow_segmentation_elems", "isx_compute_batch_host_u16", "isx_submit_batch_host_u16",
+    "isx_pool_create", "isx_pool_destroy", "isx_pool_size", "isx_pool_real_cols", "isx_pool_segmentation_elems",
+    "isx_pool_compute_host", "isx_pool_last_error",
     # segmentation ingest
     "isx_set_segmentation_from_cnn_device", "isx_flip_and_pad_batch_device",
     # result images
@@ -82,7 +86,10 @@ SECTION_DTYPE = np.dtype([("type", "<i4"), ("vB", "<i4"), ("vT", "<i4"), ("dispa
                           ("semantic_class", "<i4"), ("cost", "<f4"), ("instance_meanx", "<f4"),
                           ("instance_meany", "<f4")])
 INSTANCE_DTYPE = np.dtype([("column", "<i4"), ("index", "<i4"), ("label", "<i4"), ("semantic_class", "<i4")])
-assert SECTION_DTYPE.itemsize == 32 and INSTANCE_DTYPE.itemsize == 16
+PACKED_FRAME_DTYPE = np.dtype([("section_offset", "<i4"), ("section_count", "<i4"), ("instance_offset", "<i4"),
+                               ("instance_count", "<i4"), ("error", "<i4"), ("overflow", "<i4"),
+                               ("reserved", "<i4", (2,))])
+assert SECTION_DTYPE.itemsize == 32 and INSTANCE_DTYPE.itemsize == 16 and PACKED_FRAME_DTYPE.itemsize == 32
 
 ISX_OK = 0
 T_JOINED_DISPARITY, T_OBJECT_LUT, T_DISPARITY_PS, T_VALID_PS, T_GROUND_PS, T_SKY_PS, T_COST_TABLE, \
@@ -130,6 +137,22 @@ def _declare(lib):
                                            C.c_void_p, i, C.c_void_p]
     lib.isx_submit_batch_host.argtypes = [H, i, i, C.c_void_p, C.c_void_p, C.POINTER(Road), C.c_void_p]
     lib.isx_wait_batch_host.argtypes = [H, C.c_void_p, i, C.c_void_p]
+    lib.isx_wait_batch_packed.argtypes = [H] + [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(i)]
+    lib.isx_narrow_segmentation_elems.argtypes = [H]
+    lib.isx_narrow_segmentation_elems.restype = C.c_size_t
+    lib.isx_compute_batch_host_u16.argtypes = [H, i, i, C.c_void_p, f, C.c_void_p, C.POINTER(Road), C.c_void_p,
+                                               C.c_void_p, i, C.c_void_p]
+    lib.isx_submit_batch_host_u16.argtypes = [H, i, i, C.c_void_p, f, C.c_void_p, C.POINTER(Road), C.c_void_p]
+    lib.isx_pool_create.argtypes = [C.POINTER(H), C.POINTER(i), i, C.POINTER(Config), i]
+    lib.isx_pool_destroy.argtypes = [H]
+    lib.isx_pool_size.argtypes = [H]
+    lib.isx_pool_real_cols.argtypes = [H]
+    lib.isx_pool_segmentation_elems.argtypes = [H]
+    lib.isx_pool_segmentation_elems.restype = C.c_size_t
+    lib.isx_pool_compute_host.argtypes = [H, i, i, C.c_void_p, C.c_void_p, C.POINTER(Road), C.c_void_p, C.c_void_p, i,
+                                          C.c_void_p]
+    lib.isx_pool_last_error.argtypes = [H]
+    lib.isx_pool_last_error.restype = C.c_char_p
     lib.isx_compute_batch_device.argtypes = [H, i, i, C.c_void_p, C.c_void_p, C.POINTER(Road)]
     lib.isx_synchronize.argtypes = [H]
     lib.isx_flush.argtypes = [H]

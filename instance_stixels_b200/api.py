@@ -82,6 +82,7 @@ class Stixels:
     def SetConfig(self, config: L.Config):
         self._check(self._lib.isx_set_config(self._h, C.byref(config)))
         self._pairwise = bool(config.pairwise)
+        self._cols = int(config.cols)
 
     def Initialize(self, max_batch: int = 1):
         self._check(self._lib.isx_initialize(self._h, max_batch))
@@ -226,6 +227,71 @@ class Stixels:
         self._in_flight = getattr(self, "_in_flight", [])
         self._in_flight.append((n, disparity, segmentation, sections_out))
 
+    def narrow_segmentation_elems(self) -> int:
+        return self._lib.isx_narrow_segmentation_elems(self._h)
+
+    def ComputeBatchU16(self, pairwise: bool, disparity_u16: np.ndarray, disparity_scale: float,
+                        segmentation_i16: np.ndarray, roads: Sequence[dict],
+                        sections_out: Optional[np.ndarray] = None):
+        """ComputeBatch with narrow host inputs: uint16 disparity (value = u16 * disparity_scale, e.g. a 16-bit
+        disparity PNG with 1/256) and int16 segmentation [n][C][21][ceil(rows/8)] without the zero padding."""
+        n = len(roads)
+        d = np.ascontiguousarray(disparity_u16, dtype=np.uint16)
+        g = np.ascontiguousarray(segmentation_i16, dtype=np.int16)
+        if g.size != n * self.narrow_segmentation_elems() or d.size != n * self._frame_pixels():
+            raise InvalidArgument("ComputeBatchU16: wrong input size")
+        C_, S = self.GetRealCols(), self.GetMaxSections()
+        if sections_out is None:
+            sections_out = np.zeros((n, C_, S), dtype=L.SECTION_DTYPE)
+        inst, offs, cap = self._instance_buffers(n)
+        self._check(self._lib.isx_compute_batch_host_u16(
+            self._h, int(pairwise), n, d.ctypes.data, disparity_scale, g.ctypes.data, _roads(roads),
+            sections_out.ctypes.data, inst.ctypes.data, cap, offs.ctypes.data))
+        return sections_out, inst[:offs[n]].copy(), offs.copy()
+
+    def SubmitBatchU16(self, pairwise: bool, disparity_u16: np.ndarray, disparity_scale: float,
+                       segmentation_i16: np.ndarray, roads: Sequence[dict], sections_out: Optional[np.ndarray]):
+        """Asynchronous ComputeBatchU16 (see SubmitBatch)."""
+        n = len(roads)
+        if disparity_u16.dtype != np.uint16 or segmentation_i16.dtype != np.int16 or \
+                not disparity_u16.flags.c_contiguous or not segmentation_i16.flags.c_contiguous:
+            raise InvalidArgument("SubmitBatchU16 needs C-contiguous uint16 / int16 arrays (no hidden copies)")
+        self._check(self._lib.isx_submit_batch_host_u16(
+            self._h, int(pairwise), n, disparity_u16.ctypes.data, disparity_scale, segmentation_i16.ctypes.data,
+            _roads(roads), sections_out.ctypes.data if sections_out is not None else None))
+        self._in_flight = getattr(self, "_in_flight", [])
+        self._in_flight.append((n, disparity_u16, segmentation_i16, sections_out))
+
+    def _frame_pixels(self) -> int:
+        rows = self._lib.isx_tensor_elems(self._h, L.T_JOINED_DISPARITY) // self.GetRealCols()
+        return rows * self._cols
+
+    def WaitBatchPacked(self):
+        """Wait for the oldest submitted batch and return its packed results WITHOUT expanding them: views of the
+        pinned arrays the device wrote (valid until the second SubmitBatch after this call):
+        (sections [total], counts [n][C], instances [total], frames [n] of PACKED_FRAME_DTYPE)."""
+        if not getattr(self, "_in_flight", None):
+            raise InvalidArgument("no submitted batch is in flight")
+        self._in_flight.pop(0)
+        ps, pc, pi, pf = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_int(0)
+        self._check(self._lib.isx_wait_batch_packed(self._h, C.byref(ps), C.byref(pc), C.byref(pi), C.byref(pf),
+                                                    C.byref(n)))
+        n = n.value
+        C_ = self.GetRealCols()
+
+        def view(ptr, count, dtype):
+            if count == 0:
+                return np.zeros(0, dtype=dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr.value)
+            return np.frombuffer(buf, dtype=dtype, count=count)
+
+        frames = view(pf, n, L.PACKED_FRAME_DTYPE)
+        nsec = int((frames["section_offset"] + frames["section_count"]).max()) if n else 0
+        ninst = int((frames["instance_offset"] + frames["instance_count"]).max()) if n else 0
+        return (view(ps, nsec, L.SECTION_DTYPE), view(pc, n * C_, np.int32).reshape(n, C_),
+                view(pi, ninst, L.INSTANCE_DTYPE), frames)
+
     def WaitBatch(self, want_instances: bool = True):
         """Wait for the oldest submitted batch; returns (sections, instances, offsets) like ComputeBatch."""
         if not getattr(self, "_in_flight", None):
@@ -239,8 +305,9 @@ class Stixels:
         return sections_out, inst[:offs[n]].copy(), offs.copy()
 
     def _instance_buffers(self, n: int):
-        """Reusable result buffers for the packed instance records of a batch of n frames."""
-        cap = 16384 * n
+        """Reusable result buffers for the packed instance records of a batch of n frames (every stixel of a frame
+        can be an instance stixel: isx_instance_capacity() records per frame)."""
+        cap = self.instance_capacity() * n
         cached = getattr(self, "_inst_cache", None)
         if cached is None or cached[2] != cap:
             cached = (np.empty(cap, dtype=L.INSTANCE_DTYPE), np.zeros(n + 1, dtype=np.int32), cap)
@@ -399,6 +466,53 @@ def dbscan_fit(xy: np.ndarray, eps: float, min_pts: int, core_candidates: np.nda
     if rc != L.ISX_OK:
         raise StixelsError(f"isx_dbscan_fit_host: {lib.isx_last_error(None).decode()} ({rc})")
     return labels
+
+
+class StixelsPool:
+    """One context + host worker thread per GPU in this process (isx_pool_*): frames of a call are sharded into
+    contiguous blocks, frame f -> worker f*G/n, and streamed through the submit/wait pipeline of every context."""
+
+    def __init__(self, config: L.Config, devices: Sequence[int], max_batch: int = 64):
+        self._lib = L.load()
+        self._p = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        rc = self._lib.isx_pool_create(C.byref(self._p), devs, len(devices), C.byref(config), max_batch)
+        if rc != L.ISX_OK:
+            raise StixelsError(f"isx_pool_create: {self._lib.isx_pool_last_error(None).decode()} ({rc})")
+        self._inst_cap = int(config.cols) // int(config.column_step) * 200
+
+    def size(self) -> int:
+        return self._lib.isx_pool_size(self._p)
+
+    def GetRealCols(self) -> int:
+        return self._lib.isx_pool_real_cols(self._p)
+
+    def ComputeBatch(self, pairwise: bool, disparity: np.ndarray, segmentation: np.ndarray, roads: Sequence[dict],
+                     sections_out: Optional[np.ndarray] = None):
+        n = len(roads)
+        disparity = np.ascontiguousarray(disparity, dtype=np.float32)
+        segmentation = np.ascontiguousarray(segmentation, dtype=np.int32)
+        if sections_out is None:
+            sections_out = np.zeros((n, self.GetRealCols(), 200), dtype=L.SECTION_DTYPE)
+        inst = np.empty(self._inst_cap * n, dtype=L.INSTANCE_DTYPE)
+        offs = np.zeros(n + 1, dtype=np.int32)
+        rc = self._lib.isx_pool_compute_host(self._p, int(pairwise), n, disparity.ctypes.data,
+                                             segmentation.ctypes.data, _roads(roads), sections_out.ctypes.data,
+                                             inst.ctypes.data, inst.size, offs.ctypes.data)
+        if rc != L.ISX_OK:
+            raise StixelsError(f"isx_pool_compute_host: {self._lib.isx_pool_last_error(self._p).decode()} ({rc})")
+        return sections_out, inst[:offs[n]].copy(), offs
+
+    def close(self):
+        if self._p:
+            self._lib.isx_pool_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def make_stixels(preset: dict, max_batch: int = 1, device: int = 0) -> Stixels:

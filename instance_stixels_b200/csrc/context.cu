@@ -52,6 +52,9 @@ struct isx_context {
   cudaEvent_t ev_dp_done[2] = {nullptr, nullptr}, ev_emit_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
   cudaEvent_t ev_chunk_done = nullptr;
+  // narrow host inputs (isx_*_u16): staging for the raw uint16 / int16 data, allocated on first use
+  uint16_t *d_in_disp16[2] = {nullptr, nullptr};  // [chunk][H][W]
+  int16_t *d_in_seg16[2] = {nullptr, nullptr};    // [chunk][C][21][ceil(H/8)]
 
   // device memory
   std::vector<void *> allocations;
@@ -69,38 +72,41 @@ struct isx_context {
     uint32_t *records = nullptr, *records_b = nullptr;
     float4 *dp = nullptr;
     float *pm = nullptr;
+    int *err = nullptr;   // [chunk] kErr* bits per frame, zeroed when the chunk is enqueued
   } sets[2];
   int last_set = 0;
   bool emit_join_pending = false;  // results of the last device batch are not yet ordered on s_compute
-  isx_section *d_sections_all = nullptr;          // [max_batch][C][200]
-  int *d_nsections_all = nullptr;                 // [max_batch][C]
-  isx_instance *d_inst_all = nullptr;             // [max_batch][inst_cap]
-  int *d_inst_count_all = nullptr;                // [max_batch]
+  // Results of one batch.  The padded device arrays feed the rasteriser and the fallback copy; what a host caller
+  // gets is packed by pack_results_kernel (emit.cu) straight into pinned host memory that is mapped into the
+  // device address space (h_* = host address, m_* = the device's address of the same memory).
+  struct ResultSet {
+    bool allocated = false;
+    isx_section *d_sections = nullptr;            // [max_batch][C][200]
+    int *d_nsections = nullptr;                   // [max_batch][C]
+    isx_instance *d_inst = nullptr;               // [max_batch][inst_cap]
+    int *d_inst_count = nullptr;                  // [max_batch]
+    int *d_cursors = nullptr;                     // [2] next free packed section / instance record
+    isx_section *h_sections = nullptr, *m_sections = nullptr;   // packed Sections of the batch
+    isx_instance *h_inst = nullptr, *m_inst = nullptr;          // packed instance records of the batch
+    int *h_counts = nullptr, *m_counts = nullptr;               // [max_batch][C] stixels per column
+    isx_packed_frame *h_frames = nullptr, *m_frames = nullptr;  // [max_batch]
+    int sections_cap = 0, inst_cap = 0;           // entries of the packed arrays
+  } rs[2];
+  int cur = 0;                                    // result set of the batch being enqueued / of the last batch
   int *d_raster_table = nullptr;                  // [max_batch][C][200] instance id per stixel (rasteriser)
-  int inst_cap = 0;
+  int inst_cap = 0;                               // instance records per frame of the device arrays: C * 200
   float *d_export_cost = nullptr;
   int *d_export_index = nullptr;
 
   // pinned host staging
   float *h_ground = nullptr;                      // [2][chunk][3][H]
   int *h_vhor = nullptr;                          // [2][chunk]
-  isx_instance *h_inst = nullptr;                 // [max_batch][inst_cap]
-  int *h_inst_count = nullptr;                    // [max_batch]
-  int *h_error = nullptr;
-  // isx_submit_batch_host keeps up to two batches in flight: the result arrays above (device and pinned host) are
-  // the CURRENT set; the other one lives here and the two are swapped at every submit.
-  struct ResultSet {
-    isx_section *d_sections = nullptr;
-    int *d_nsections = nullptr;
-    isx_instance *d_inst = nullptr;
-    int *d_inst_count = nullptr;
-    isx_instance *h_inst = nullptr;
-    int *h_inst_count = nullptr;
-    int *h_error = nullptr;
-  } other_results;
-  bool other_results_allocated = false;
+  // isx_submit_batch_host keeps up to two batches in flight: rs[cur] belongs to the batch submitted last, the other
+  // set to the one before (the second set is allocated on the first submit).
   cudaEvent_t ev_batch_done[2] = {nullptr, nullptr};  // by ticket parity
   int batch_n[2] = {0, 0};                            // frames of the batch in flight with that parity, 0 = none
+  int batch_set[2] = {0, 0};                          // its result set
+  isx_section *batch_sections[2] = {nullptr, nullptr};  // the caller's padded array the wait expands into
   unsigned long long submitted = 0, waited = 0;       // tickets: batches [waited, submitted) are in flight
   unsigned long long dp_units_pairwise = 0;           // ... of which in pairwise mode (never pruned)
   unsigned long long dp_units_total = 0;              // 32 x 32-cell units of all DP launches so far
@@ -210,34 +216,6 @@ static void fill_kparams(isx_context *c) {
   k.prune_pairwise = (e2 && std::atoi(e2) == 0) ? 0 : 1;
 }
 
-// Compacts the grouping result of every frame into isx_instance records
-// ordered by (class, column, index).
-__global__ void pack_instances_kernel(const int *__restrict__ cand_count, const int2 *__restrict__ cand_idx,
-                                      const int *__restrict__ cand_label, isx_instance *__restrict__ out,
-                                      int *__restrict__ out_count, int inst_cap, KParams p) {
-  const int f = blockIdx.x;
-  const size_t cap = (size_t)p.realcols * kMaxSections;
-  int base = 0;
-  for (int k = 0; k < kInstanceClasses; k++) {
-    const int n = cand_count[f * kInstanceClasses + k];
-    const size_t src = ((size_t)f * kInstanceClasses + k) * cap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int dst = base + i;
-      if (dst < inst_cap) {
-        isx_instance r;
-        const int2 ci = cand_idx[src + i];
-        r.column = ci.x;
-        r.index = ci.y;
-        r.label = cand_label[src + i];
-        r.semantic_class = kFirstInstanceClass + k;
-        out[(size_t)f * inst_cap + dst] = r;
-      }
-    }
-    base += n;
-  }
-  if (threadIdx.x == 0) out_count[f] = base;
-}
-
 static const float *road_tables(isx_context *c, const isx_road &r) {
   RoadKey key{r.vhor, r.camera_tilt, r.camera_height, r.alpha_ground};
   auto it = c->road_cache.find(key);
@@ -273,13 +251,16 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
   ISX_TRY(c, cudaStreamWaitEvent(s, c->ev_emit_done[slot], 0));
   ISX_TRY(c, cudaMemcpyAsync(cs.ground, hg, sizeof(float) * 3 * H * n, cudaMemcpyHostToDevice, s));
   ISX_TRY(c, cudaMemcpyAsync(cs.vhor, hv, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  ISX_TRY(c, cudaMemsetAsync(cs.err, 0, sizeof(int) * n, s));  // the error words of THIS chunk's frames
+  isx_context::ResultSet &R = c->rs[c->cur];
   BatchBuffers b = c->buf;
   b.ground = cs.ground; b.vhor = cs.vhor; b.stat = cs.stat;
   b.records = cs.records; b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
+  b.error_flag = cs.err;
   b.disparity = d_disp;
   b.segmentation = d_seg;
-  b.sections = c->d_sections_all + (size_t)first * C * kMaxSections;
-  b.n_sections = c->d_nsections_all + (size_t)first * C;
+  b.sections = R.d_sections + (size_t)first * C * kMaxSections;
+  b.n_sections = R.d_nsections + (size_t)first * C;
   // profiling events per chunk: 0 join | 1 frame tables | 2 column tables + LUT | 3 dp | 4 dp end (s_compute);
   //                             5 backtrack + collect | 6 grouping + pack | 7 end (s_emit)
   auto mark = [&](cudaStream_t st) {
@@ -314,10 +295,18 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
   launch_emit(kp, b, n, pairwise, se);
   mark(se);
   launch_grouping(kp, b, n, se);
-  pack_instances_kernel<<<n, 256, 0, se>>>(b.cand_count, b.cand_idx, b.cand_label,
-                                           c->d_inst_all + (size_t)first * c->inst_cap,
-                                           c->d_inst_count_all + first, c->inst_cap, kp);
-  g_launch_count++;
+  {
+    PackArgs a;
+    a.sections = b.sections; a.n_sections = b.n_sections;
+    a.cand_count = b.cand_count; a.cand_idx = b.cand_idx; a.cand_label = b.cand_label;
+    a.err = cs.err; a.col_offset = b.pack_offset;
+    a.inst_out = R.d_inst + (size_t)first * c->inst_cap; a.inst_count_out = R.d_inst_count + first;
+    a.inst_cap = c->inst_cap; a.cursors = R.d_cursors;
+    a.h_sections = R.m_sections; a.h_sections_cap = R.sections_cap;
+    a.h_inst = R.m_inst; a.h_inst_cap = R.inst_cap;
+    a.h_counts = R.m_counts + (size_t)first * C; a.h_frames = R.m_frames + first;
+    launch_pack(kp, a, n, se);
+  }
   mark(se);
   ISX_TRY(c, cudaEventRecord(c->ev_emit_done[slot], se));
   ISX_TRY(c, cudaGetLastError());
@@ -325,6 +314,46 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
   c->last_chunk_n = n;
   c->last_pairwise = pairwise;
   c->last_set = slot;
+  return ISX_OK;
+}
+
+// Every batch starts its packed result arrays from the front (ordered on the emission stream behind the packing of
+// whatever batch used this result set before).
+static int begin_batch(isx_context *c) {
+  ISX_TRY(c, cudaMemsetAsync(c->rs[c->cur].d_cursors, 0, 2 * sizeof(int), c->s_emit));
+  return ISX_OK;
+}
+
+// The result arrays of one batch: padded device arrays + packed arrays in mapped pinned host memory.
+static int alloc_result_set(isx_context *c, int i) {
+  isx_context::ResultSet &R = c->rs[i];
+  if (R.allocated) return ISX_OK;
+  const size_t C = c->kp.realcols, MB = c->max_batch;
+  ISX_TRY(c, dev_alloc(c, &R.d_sections, MB * C * kMaxSections));
+  // entries after a column's terminator are never written: start them from zero
+  ISX_TRY(c, cudaMemset(R.d_sections, 0, MB * C * kMaxSections * sizeof(isx_section)));
+  ISX_TRY(c, dev_alloc(c, &R.d_nsections, MB * C));
+  ISX_TRY(c, dev_alloc(c, &R.d_inst, MB * (size_t)c->inst_cap));
+  ISX_TRY(c, dev_alloc(c, &R.d_inst_count, MB));
+  ISX_TRY(c, dev_alloc(c, &R.d_cursors, 2));
+  ISX_TRY(c, cudaMemset(R.d_cursors, 0, 2 * sizeof(int)));
+  // Packed arrays: sized for `budget` stixels per column on average (street scenes have about ten; the capacity of
+  // the reference's array is 200).  A batch that needs more falls back to the padded arrays frame by frame.
+  size_t budget = 32;
+  if (const char *e = std::getenv("ISX_PACK_BUDGET")) budget = std::atoi(e) > 0 ? (size_t)std::atoi(e) : budget;
+  budget = budget < (size_t)kMaxSections ? budget : (size_t)kMaxSections;
+  R.sections_cap = R.inst_cap = (int)(MB * C * budget);
+  const unsigned flags = cudaHostAllocMapped | cudaHostAllocPortable;
+  ISX_TRY(c, cudaHostAlloc(&R.h_sections, sizeof(isx_section) * (size_t)R.sections_cap, flags));
+  ISX_TRY(c, cudaHostAlloc(&R.h_inst, sizeof(isx_instance) * (size_t)R.inst_cap, flags));
+  ISX_TRY(c, cudaHostAlloc(&R.h_counts, sizeof(int) * MB * C, flags));
+  ISX_TRY(c, cudaHostAlloc(&R.h_frames, sizeof(isx_packed_frame) * MB, flags));
+  ISX_TRY(c, cudaHostGetDevicePointer(&R.m_sections, R.h_sections, 0));
+  ISX_TRY(c, cudaHostGetDevicePointer(&R.m_inst, R.h_inst, 0));
+  ISX_TRY(c, cudaHostGetDevicePointer(&R.m_counts, R.h_counts, 0));
+  ISX_TRY(c, cudaHostGetDevicePointer(&R.m_frames, R.h_frames, 0));
+  std::memset(R.h_frames, 0, sizeof(isx_packed_frame) * MB);
+  R.allocated = true;
   return ISX_OK;
 }
 
@@ -501,7 +530,7 @@ int isx_initialize(isx_handle h, int max_batch) {
   h->kp.lut_cols = h->chunk * (int)C;
   const size_t ch = h->chunk, MB = max_batch;
   const size_t cap = C * kMaxSections;
-  h->inst_cap = (int)(cap * kInstanceClasses < 16384 ? cap * kInstanceClasses : 16384);
+  h->inst_cap = (int)cap;  // every stixel of a frame can be an instance stixel (the reference sizes 8 x this)
 
   ISX_TRY(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
   {
@@ -541,6 +570,7 @@ int isx_initialize(isx_handle h, int max_batch) {
     ISX_TRY(h, dev_alloc(h, &cs.pm, ch * C * H));
     ISX_TRY(h, cudaMemset(cs.pm, 0, ch * C * H * sizeof(float)));
     ISX_TRY(h, dev_alloc(h, &cs.dp, ch * C * H));
+    ISX_TRY(h, dev_alloc(h, &cs.err, ch));
   }
   ISX_TRY(h, dev_alloc(h, &b.object_lut, lut_buffer_bytes(ch * C, D * (size_t)kp.lut_stride * 4) / 4));
   ISX_TRY(h, dev_alloc(h, &b.cand_count, ch * kInstanceClasses));
@@ -550,7 +580,7 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &b.cand_core, ch * kInstanceClasses * cap));
   ISX_TRY(h, dev_alloc(h, &b.cand_label, ch * kInstanceClasses * cap));
   ISX_TRY(h, dev_alloc(h, &b.cand_scratch, ch * kInstanceClasses * cap));
-  ISX_TRY(h, dev_alloc(h, &b.error_flag, 1));
+  ISX_TRY(h, dev_alloc(h, &b.pack_offset, ch * (C + 1)));
   ISX_TRY(h, dev_alloc(h, &b.dp_units, 1));
   ISX_TRY(h, dev_alloc(h, &b.col_flags, ch * C));
   ISX_TRY(h, cudaMemset(b.col_flags, 0, ch * C * sizeof(int)));
@@ -559,13 +589,8 @@ int isx_initialize(isx_handle h, int max_batch) {
     ISX_TRY(h, cudaMemset(b.qrows, 0, ch * C * (size_t)kp.rec_stride * kDynWords * sizeof(float)));
   }
   ISX_TRY(h, cudaMemset(b.dp_units, 0, sizeof(unsigned long long)));
-  ISX_TRY(h, cudaMemset(b.error_flag, 0, sizeof(int)));
-  ISX_TRY(h, dev_alloc(h, &h->d_sections_all, MB * C * kMaxSections));
-  // entries after a column's terminator are never written: start them from zero
-  ISX_TRY(h, cudaMemset(h->d_sections_all, 0, MB * C * kMaxSections * sizeof(isx_section)));
-  ISX_TRY(h, dev_alloc(h, &h->d_nsections_all, MB * C));
-  ISX_TRY(h, dev_alloc(h, &h->d_inst_all, MB * (size_t)h->inst_cap));
-  ISX_TRY(h, dev_alloc(h, &h->d_inst_count_all, MB));
+  h->cur = 0;
+  if (int rc = alloc_result_set(h, 0)) return rc;
   ISX_TRY(h, dev_alloc(h, &h->d_raster_table, MB * C * kMaxSections));
   ISX_TRY(h, dev_alloc(h, &h->d_export_cost, C * H * 3));
   ISX_TRY(h, dev_alloc(h, &h->d_export_index, C * H * 3));
@@ -593,9 +618,6 @@ int isx_initialize(isx_handle h, int max_batch) {
 
   ISX_TRY(h, cudaMallocHost(&h->h_ground, sizeof(float) * 2 * ch * 3 * H));
   ISX_TRY(h, cudaMallocHost(&h->h_vhor, sizeof(int) * 2 * ch));
-  ISX_TRY(h, cudaMallocHost(&h->h_inst, sizeof(isx_instance) * MB * h->inst_cap));
-  ISX_TRY(h, cudaMallocHost(&h->h_inst_count, sizeof(int) * MB));
-  ISX_TRY(h, cudaMallocHost(&h->h_error, sizeof(int)));
   h->road_cache.clear();
   h->initialized = true;
   h->last_batch = 0;
@@ -611,17 +633,22 @@ int isx_finish(isx_handle h) {
   h->allocations.clear();
   cudaFreeHost(h->h_ground);
   cudaFreeHost(h->h_vhor);
-  cudaFreeHost(h->h_inst);
-  cudaFreeHost(h->h_inst_count);
-  cudaFreeHost(h->h_error);
-  if (h->other_results_allocated) {
-    cudaFreeHost(h->other_results.h_inst);
-    cudaFreeHost(h->other_results.h_inst_count);
-    cudaFreeHost(h->other_results.h_error);
-    for (int i = 0; i < 2; i++) cudaEventDestroy(h->ev_batch_done[i]);
-    h->other_results = isx_context::ResultSet();
-    h->other_results_allocated = false;
+  for (int i = 0; i < 2; i++) {
+    isx_context::ResultSet &R = h->rs[i];
+    if (R.allocated) {
+      cudaFreeHost(R.h_sections);
+      cudaFreeHost(R.h_inst);
+      cudaFreeHost(R.h_counts);
+      cudaFreeHost(R.h_frames);
+    }
+    R = isx_context::ResultSet();
+    if (h->ev_batch_done[i]) cudaEventDestroy(h->ev_batch_done[i]);
+    h->ev_batch_done[i] = nullptr;
+    h->d_in_disp16[i] = nullptr;
+    h->d_in_seg16[i] = nullptr;
+    h->batch_sections[i] = nullptr;
   }
+  h->cur = 0;
   h->submitted = h->waited = 0;
   h->host_slot = 0;
   h->dp_units_total = h->dp_units_pairwise = 0;
@@ -703,32 +730,75 @@ int isx_set_road_parameters(isx_handle h, int vhor, float camera_tilt, float cam
   return ISX_OK;
 }
 
-static int deliver_instances(isx_handle h, int n, isx_instance *instances, int instances_capacity,
-                             int32_t *instance_offsets);
 static int no_batches_in_flight(isx_handle h);
-static int fetch_results(isx_handle h, int n, isx_section *sections, isx_instance *instances, int instances_capacity,
-                         int32_t *instance_offsets, cudaStream_t s) {
+
+// Hands the results of n frames of result set R to the caller: the packed Sections are expanded into the caller's
+// padded [n][C][200] array (used entries + the type == -1 terminator of every column; entries behind a terminator
+// are not touched, like the reference's d_stixels, StixelsKernels.cu:951-955), the instance records are copied
+// frame after frame.  Everything comes from pinned host memory the device has already written (the caller has
+// waited for the emission stream); only a frame that did not fit the packed arrays costs a device -> host copy.
+// Returns the first per-frame error AFTER delivering what there is.
+static int deliver(isx_handle h, isx_context::ResultSet &R, int n, isx_section *sections, isx_instance *instances,
+                   int instances_capacity, int32_t *instance_offsets) {
   const size_t C = h->kp.realcols;
-  if (int rc = ensure_joined(h)) return rc;
-  if (sections)
-    ISX_TRY(h, cudaMemcpyAsync(sections, h->d_sections_all, sizeof(isx_section) * n * C * kMaxSections,
-                               cudaMemcpyDeviceToHost, s));
-  ISX_TRY(h, cudaMemcpyAsync(h->h_inst_count, h->d_inst_count_all, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
-  ISX_TRY(h, cudaMemcpyAsync(h->h_error, h->buf.error_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-  ISX_TRY(h, cudaStreamSynchronize(s));
-  if (instances || instance_offsets) {
-    // only the used part of every frame's [inst_cap] record array travels
-    int most = 0;
-    for (int f = 0; f < n; f++) most = h->h_inst_count[f] > most ? h->h_inst_count[f] : most;
-    most = most < h->inst_cap ? most : h->inst_cap;
-    if (most > 0) {
-      const size_t pitch = sizeof(isx_instance) * (size_t)h->inst_cap;
-      ISX_TRY(h, cudaMemcpy2DAsync(h->h_inst, pitch, h->d_inst_all, pitch, sizeof(isx_instance) * (size_t)most, n,
-                                   cudaMemcpyDeviceToHost, s));
-      ISX_TRY(h, cudaStreamSynchronize(s));
+  int rc = ISX_OK;
+  int total = 0;
+  for (int f = 0; f < n; f++) {
+    const isx_packed_frame &d = R.h_frames[f];
+    if (d.error && rc == ISX_OK) {
+      char msg[160];
+      if (d.error & kErrOffsetRange) {
+        std::snprintf(msg, sizeof msg, "frame %d: instance offsets out of range: |sum of instance means| of a column "
+                      "must stay below 2^24", f);
+        rc = fail(h, ISX_ERR_UNSUPPORTED, msg);
+      } else {
+        std::snprintf(msg, sizeof msg, "frame %d: a column produced >= 200 stixels (MAX_STIXELS_PER_COLUMN)", f);
+        rc = fail(h, ISX_ERR_CAPACITY, msg);
+      }
     }
+    if (sections) {
+      isx_section *dst = sections + (size_t)f * C * kMaxSections;
+      if (d.overflow & 1) {
+        ISX_TRY(h, cudaMemcpy(dst, R.d_sections + (size_t)f * C * kMaxSections, sizeof(isx_section) * C * kMaxSections,
+                              cudaMemcpyDeviceToHost));
+      } else {
+        const isx_section *src = R.h_sections + d.section_offset;
+        const int *cnt = R.h_counts + (size_t)f * C;
+        isx_section term;
+        term.type = -1;
+        term.vB = term.vT = 0;
+        term.disparity = term.cost = term.instance_meanx = term.instance_meany = 0.0f;
+        term.semantic_class = 0;
+        for (size_t c = 0; c < C; c++) {
+          const int k = cnt[c];
+          std::memcpy(dst + c * kMaxSections, src, sizeof(isx_section) * (size_t)k);
+          dst[c * kMaxSections + k] = term;
+          src += k;
+        }
+      }
+    }
+    if (instance_offsets) instance_offsets[f] = total;
+    if (instances) {
+      const int room = instances_capacity - total;
+      const int take = d.instance_count < room ? d.instance_count : (room > 0 ? room : 0);
+      if (take > 0) {
+        if (d.overflow & 2)
+          ISX_TRY(h, cudaMemcpy(instances + total, R.d_inst + (size_t)f * h->inst_cap, sizeof(isx_instance) * take,
+                                cudaMemcpyDeviceToHost));
+        else
+          std::memcpy(instances + total, R.h_inst + d.instance_offset, sizeof(isx_instance) * (size_t)take);
+      }
+    }
+    total += d.instance_count;
   }
-  return deliver_instances(h, n, instances, instances_capacity, instance_offsets);
+  if (instance_offsets) instance_offsets[n] = total;
+  return rc;
+}
+
+// Waits until the results of the last enqueued batch are in host memory.
+static int wait_last_emission(isx_handle h) {
+  ISX_TRY(h, cudaEventSynchronize(h->ev_emit_done[h->last_set]));
+  return ISX_OK;
 }
 
 int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_meta *meta,
@@ -737,11 +807,16 @@ int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_met
   if (!h->single_has_road) return fail(h, ISX_ERR_INVALID_ARGUMENT, "SetRoadParameters has not been called");
   if (int rc = no_batches_in_flight(h)) return rc;
   const int32_t *seg = d_segmentation_local ? d_segmentation_local : h->d_single_seg;
+  // slot 0's pinned road-table staging may still be the source of a copy a device batch has queued
+  ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[0]));
+  if (int rc = begin_batch(h)) return rc;
   if (int rc = enqueue_chunk(h, pairwise != 0, 0, 1, h->d_single_disp, seg, &h->single_road, 0)) return rc;
+  ISX_TRY(h, cudaEventRecord(h->ev_in_free[0], h->s_compute));
   if (int rc = join_emit_stream(h)) return rc;
   h->last_batch = 1;
   h->last_roads.assign(1, h->single_road);
-  if (int rc = fetch_results(h, 1, sections, nullptr, 0, nullptr, h->s_compute)) return rc;
+  if (int rc = wait_last_emission(h)) return rc;
+  if (int rc = deliver(h, h->rs[h->cur], 1, sections, nullptr, 0, nullptr)) return rc;
   if (meta) {
     meta->rows = h->kp.rows; meta->cols = h->kp.cols; meta->realcols = h->kp.realcols;
     meta->max_sections = kMaxSections; meta->max_dis = h->kp.max_dis; meta->column_step = h->kp.column_step;
@@ -768,8 +843,10 @@ int isx_dbscan_fit_host(int device, const float *xy, int n, float eps, int min_p
 int isx_get_instance_stixels(isx_handle h, isx_instance *out, int capacity, int *n) {
   if (int rc = check_ready(h)) return rc;
   if (h->last_batch < 1) return fail(h, ISX_ERR_INVALID_ARGUMENT, "Compute has not been called");
+  if (int rc = no_batches_in_flight(h)) return rc;
+  if (int rc = wait_last_emission(h)) return rc;
   int32_t offs[2] = {0, 0};
-  if (int rc = fetch_results(h, 1, nullptr, out, out ? capacity : 0, offs, h->s_compute)) return rc;
+  if (int rc = deliver(h, h->rs[h->cur], 1, nullptr, out, out ? capacity : 0, offs)) return rc;
   if (n) *n = offs[1];
   return ISX_OK;
 }
@@ -782,6 +859,7 @@ int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_d
   if (!d_disparity || !d_segmentation || !roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
   const size_t hw = (size_t)h->kp.rows * h->kp.cols, se = seg_elems(h);
   int slot = h->host_slot;  // keeps alternating across batches (see enqueue_host_batch)
+  if (int rc = begin_batch(h)) return rc;
   for (int first = 0; first < n; first += h->chunk) {
     const int cn = (n - first) < h->chunk ? (n - first) : h->chunk;
     // the pinned ground staging half must not be rewritten while its copy is in flight
@@ -815,15 +893,48 @@ int isx_fetch_batch_results(isx_handle h, int n, isx_section *sections, isx_inst
                             int instances_capacity, int32_t *instance_offsets) {
   if (int rc = check_ready(h)) return rc;
   if (n < 1 || n > h->last_batch) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no results for that many frames");
-  return fetch_results(h, n, sections, instances, instances_capacity, instance_offsets, h->s_compute);
+  if (int rc = no_batches_in_flight(h)) return rc;
+  if (int rc = ensure_joined(h)) return rc;
+  if (int rc = wait_last_emission(h)) return rc;
+  return deliver(h, h->rs[h->cur], n, sections, instances, instances_capacity, instance_offsets);
 }
 
-// The copy/kernel pipeline of one host batch: H2D on s_h2d, kernels on s_compute / s_emit, D2H of the sections
-// chunk by chunk on s_d2h.  Blocks the caller only for the reuse of an input slot (two chunks behind).
-static int enqueue_host_batch(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
-                              const isx_road *roads, isx_section *sections) {
-  const size_t hw = (size_t)h->kp.rows * h->kp.cols, se = seg_elems(h);
-  const size_t C = h->kp.realcols;
+// Host inputs of one batch: the reference's types (float disparity, int32 segmentation with its padding), or the
+// narrow forms of the isx_*_u16 entry points.
+struct HostInputs {
+  const float *disparity = nullptr;
+  const int32_t *segmentation = nullptr;
+  const uint16_t *disparity16 = nullptr;
+  float scale = 0.0f;
+  const int16_t *segmentation16 = nullptr;
+  bool narrow() const { return disparity16 != nullptr; }
+};
+
+static size_t narrow_seg_elems(const isx_context *c) {
+  const size_t used = (size_t)(c->kp.rows + kDownsample - 1) / kDownsample;
+  return (size_t)c->kp.realcols * c->kp.n_channels * (used < (size_t)c->kp.hs2 ? used : (size_t)c->kp.hs2);
+}
+
+static int ensure_narrow_staging(isx_handle h) {
+  if (h->d_in_disp16[0]) return ISX_OK;
+  const size_t hw = (size_t)h->kp.rows * h->kp.cols, ch = h->chunk;
+  for (int i = 0; i < 2; i++) {
+    ISX_TRY(h, dev_alloc(h, &h->d_in_disp16[i], ch * hw));
+    ISX_TRY(h, dev_alloc(h, &h->d_in_seg16[i], ch * narrow_seg_elems(h)));
+  }
+  return ISX_OK;
+}
+
+// The copy/kernel pipeline of one host batch: H2D on s_h2d, kernels on s_compute / s_emit; the results reach host
+// memory through pack_results_kernel (no D2H copies).  Blocks the caller only for the reuse of an input slot (two
+// chunks behind).
+static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInputs &in, const isx_road *roads) {
+  const size_t hw = (size_t)h->kp.rows * h->kp.cols, se = seg_elems(h), se16 = narrow_seg_elems(h);
+  if (in.narrow()) {
+    if (hw % 8 != 0) return fail(h, ISX_ERR_UNSUPPORTED, "the uint16 disparity path needs rows*cols to be a multiple of 8");
+    if (int rc = ensure_narrow_staging(h)) return rc;
+  }
+  if (int rc = begin_batch(h)) return rc;
   // The slots keep alternating across batches, so that the first copy of a pipelined batch only waits for the
   // second-to-last chunk of the batch before it.
   int slot = h->host_slot;
@@ -835,64 +946,39 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const float *di
     if (first == 0 && pipeline_idle && n > h->chunk && h->chunk >= 8) cn = h->chunk / 4;
     // H2D of this chunk on the copy stream, once the kernels that last read this slot are done
     ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_in_free[slot], 0));
-    ISX_TRY(h, cudaMemcpyAsync(h->d_in_disp[slot], disparity + first * hw, sizeof(float) * hw * cn,
-                               cudaMemcpyHostToDevice, h->s_h2d));
-    {
+    if (in.narrow()) {
+      ISX_TRY(h, cudaMemcpyAsync(h->d_in_disp16[slot], in.disparity16 + first * hw, sizeof(uint16_t) * hw * cn,
+                                 cudaMemcpyHostToDevice, h->s_h2d));
+      ISX_TRY(h, cudaMemcpyAsync(h->d_in_seg16[slot], in.segmentation16 + first * se16, sizeof(int16_t) * se16 * cn,
+                                 cudaMemcpyHostToDevice, h->s_h2d));
+    } else {
+      ISX_TRY(h, cudaMemcpyAsync(h->d_in_disp[slot], in.disparity + first * hw, sizeof(float) * hw * cn,
+                                 cudaMemcpyHostToDevice, h->s_h2d));
       // Only the first rows/8 entries of every [rows_power2_segmentation] channel row are ever read
       // (StixelsKernels.cu:393-405, 462-468 index v/8 with v < rows); the zero padding of FlipAndPad does not
       // travel: a 2-D copy of the used part, the rest of the staging buffer stays zero from isx_initialize.
       const size_t hs2 = (size_t)h->kp.hs2;
       size_t used = (size_t)(h->kp.rows + kDownsample - 1) / kDownsample;
       used = used < hs2 ? used : hs2;
-      ISX_TRY(h, cudaMemcpy2DAsync(h->d_in_seg[slot], hs2 * sizeof(int32_t), segmentation + first * se,
+      ISX_TRY(h, cudaMemcpy2DAsync(h->d_in_seg[slot], hs2 * sizeof(int32_t), in.segmentation + first * se,
                                    hs2 * sizeof(int32_t), used * sizeof(int32_t), (se / hs2) * cn,
                                    cudaMemcpyHostToDevice, h->s_h2d));
     }
     ISX_TRY(h, cudaEventRecord(h->ev_in_ready[slot], h->s_h2d));
     ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[slot]));  // pinned ground staging of this slot is reusable
     ISX_TRY(h, cudaStreamWaitEvent(h->s_compute, h->ev_in_ready[slot], 0));
+    if (in.narrow())
+      launch_widen_inputs(h->kp, h->d_in_disp16[slot], in.scale, h->d_in_seg16[slot], h->d_in_disp[slot],
+                          h->d_in_seg[slot], cn, h->s_compute);
     if (int rc = enqueue_chunk(h, pairwise != 0, first, cn, h->d_in_disp[slot], h->d_in_seg[slot], roads + first,
                                slot))
       return rc;
     ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_compute));
-    // D2H of this chunk's sections overlaps the next chunk's kernels
-    if (sections) {
-      ISX_TRY(h, cudaStreamWaitEvent(h->s_d2h, h->ev_emit_done[slot], 0));
-      ISX_TRY(h, cudaMemcpyAsync(sections + (size_t)first * C * kMaxSections,
-                                 h->d_sections_all + (size_t)first * C * kMaxSections,
-                                 sizeof(isx_section) * cn * C * kMaxSections, cudaMemcpyDeviceToHost, h->s_d2h));
-    }
     slot ^= 1;
   }
   h->host_slot = slot;
   h->last_batch = n;
   h->last_roads.assign(roads, roads + n);
-  return ISX_OK;
-}
-
-// Error flag + packed instance records of n frames from the pinned copies (h_error, h_inst_count, h_inst).
-static int deliver_instances(isx_handle h, int n, isx_instance *instances, int instances_capacity,
-                             int32_t *instance_offsets) {
-  if (*h->h_error & kErrOffsetRange)
-    return fail(h, ISX_ERR_UNSUPPORTED,
-                "instance offsets out of range: |sum of instance means| of a column must stay below 2^24");
-  if (*h->h_error) return fail(h, ISX_ERR_CAPACITY, "a column produced >= 200 stixels (MAX_STIXELS_PER_COLUMN)");
-  if (instances || instance_offsets) {
-    int total = 0;
-    for (int f = 0; f < n; f++) {
-      if (instance_offsets) instance_offsets[f] = total;
-      const int cnt = h->h_inst_count[f] < h->inst_cap ? h->h_inst_count[f] : h->inst_cap;
-      if (h->h_inst_count[f] > h->inst_cap)
-        return fail(h, ISX_ERR_CAPACITY, "more instance stixels in one frame than the packed result can hold");
-      if (instances) {
-        const int room = instances_capacity - total;
-        const int take = cnt < room ? cnt : (room > 0 ? room : 0);
-        std::memcpy(instances + total, h->h_inst + (size_t)f * h->inst_cap, sizeof(isx_instance) * take);
-      }
-      total += cnt;
-    }
-    if (instance_offsets) instance_offsets[n] = total;
-  }
   return ISX_OK;
 }
 
@@ -902,84 +988,119 @@ static int no_batches_in_flight(isx_handle h) {
   return ISX_OK;
 }
 
-int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
-                           const isx_road *roads, isx_section *sections, isx_instance *instances,
-                           int instances_capacity, int32_t *instance_offsets) {
+static int compute_batch_host(isx_handle h, int pairwise, int n, const HostInputs &in, const isx_road *roads,
+                              isx_section *sections, isx_instance *instances, int instances_capacity,
+                              int32_t *instance_offsets) {
   if (int rc = check_ready(h)) return rc;
   if (int rc = no_batches_in_flight(h)) return rc;
   if (n < 1 || n > h->max_batch) return fail(h, ISX_ERR_CAPACITY, "batch size exceeds isx_initialize(max_batch)");
-  if (!disparity || !segmentation || !roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
-  if (int rc = enqueue_host_batch(h, pairwise, n, disparity, segmentation, roads, sections)) return rc;
+  if (!roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  if (int rc = enqueue_host_batch(h, pairwise, n, in, roads)) return rc;
   if (int rc = join_emit_stream(h)) return rc;
-  if (int rc = fetch_results(h, n, nullptr, instances, instances_capacity, instance_offsets, h->s_compute)) return rc;
-  ISX_TRY(h, cudaStreamSynchronize(h->s_d2h));
-  return ISX_OK;
+  if (int rc = wait_last_emission(h)) return rc;
+  return deliver(h, h->rs[h->cur], n, sections, instances, instances_capacity, instance_offsets);
 }
 
-// Swap the current result arrays with the other set (allocated on first use).
-static int swap_result_sets(isx_handle h) {
-  isx_context::ResultSet &o = h->other_results;
-  if (!h->other_results_allocated) {
-    const size_t C = h->kp.realcols, MB = h->max_batch;
-    ISX_TRY(h, dev_alloc(h, &o.d_sections, MB * C * kMaxSections));
-    ISX_TRY(h, cudaMemset(o.d_sections, 0, MB * C * kMaxSections * sizeof(isx_section)));
-    ISX_TRY(h, dev_alloc(h, &o.d_nsections, MB * C));
-    ISX_TRY(h, dev_alloc(h, &o.d_inst, MB * (size_t)h->inst_cap));
-    ISX_TRY(h, dev_alloc(h, &o.d_inst_count, MB));
-    ISX_TRY(h, cudaMallocHost(&o.h_inst, sizeof(isx_instance) * MB * h->inst_cap));
-    ISX_TRY(h, cudaMallocHost(&o.h_inst_count, sizeof(int) * MB));
-    ISX_TRY(h, cudaMallocHost(&o.h_error, sizeof(int)));
-    for (int i = 0; i < 2; i++) ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_batch_done[i], cudaEventDisableTiming));
-    h->other_results_allocated = true;
-  }
-  std::swap(o.d_sections, h->d_sections_all);
-  std::swap(o.d_nsections, h->d_nsections_all);
-  std::swap(o.d_inst, h->d_inst_all);
-  std::swap(o.d_inst_count, h->d_inst_count_all);
-  std::swap(o.h_inst, h->h_inst);
-  std::swap(o.h_inst_count, h->h_inst_count);
-  std::swap(o.h_error, h->h_error);
-  return ISX_OK;
+int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
+                           const isx_road *roads, isx_section *sections, isx_instance *instances,
+                           int instances_capacity, int32_t *instance_offsets) {
+  if (!disparity || !segmentation) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  HostInputs in;
+  in.disparity = disparity;
+  in.segmentation = segmentation;
+  return compute_batch_host(h, pairwise, n, in, roads, sections, instances, instances_capacity, instance_offsets);
 }
 
-int isx_submit_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
-                          const isx_road *roads, isx_section *sections) {
+int isx_compute_batch_host_u16(isx_handle h, int pairwise, int n, const uint16_t *disparity, float disparity_scale,
+                               const int16_t *segmentation, const isx_road *roads, isx_section *sections,
+                               isx_instance *instances, int instances_capacity, int32_t *instance_offsets) {
+  if (!disparity || !segmentation) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  HostInputs in;
+  in.disparity16 = disparity;
+  in.scale = disparity_scale;
+  in.segmentation16 = segmentation;
+  return compute_batch_host(h, pairwise, n, in, roads, sections, instances, instances_capacity, instance_offsets);
+}
+
+size_t isx_narrow_segmentation_elems(isx_handle h) { return (h && h->initialized) ? narrow_seg_elems(h) : 0; }
+
+static int submit_batch_host(isx_handle h, int pairwise, int n, const HostInputs &in, const isx_road *roads,
+                             isx_section *sections) {
   if (int rc = check_ready(h)) return rc;
   if (n < 1 || n > h->max_batch) return fail(h, ISX_ERR_CAPACITY, "batch size exceeds isx_initialize(max_batch)");
-  if (!disparity || !segmentation || !roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  if (!roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
   if (h->submitted - h->waited >= 2)
     return fail(h, ISX_ERR_CAPACITY, "two batches are already in flight: call isx_wait_batch_host first");
-  // the set that becomes current was delivered by the wait before last (or never used)
-  if (int rc = swap_result_sets(h)) return rc;
-  if (int rc = enqueue_host_batch(h, pairwise, n, disparity, segmentation, roads, sections)) return rc;
-  // everything the wait delivers, on the copy-out stream behind the last emission: counts, error flag and the
-  // whole record array of every frame (the used part is only known on the device)
+  // the other result set was delivered by the wait before last (or never used)
+  if (int rc = alloc_result_set(h, h->cur ^ 1)) return rc;
+  for (int i = 0; i < 2; i++)
+    if (!h->ev_batch_done[i]) ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_batch_done[i], cudaEventDisableTiming));
+  h->cur ^= 1;
+  if (int rc = enqueue_host_batch(h, pairwise, n, in, roads)) return rc;
   const int par = (int)(h->submitted & 1);
-  ISX_TRY(h, cudaStreamWaitEvent(h->s_d2h, h->ev_emit_done[h->last_set], 0));
-  ISX_TRY(h, cudaMemcpyAsync(h->h_inst_count, h->d_inst_count_all, sizeof(int) * n, cudaMemcpyDeviceToHost, h->s_d2h));
-  ISX_TRY(h, cudaMemcpyAsync(h->h_error, h->buf.error_flag, sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
-  ISX_TRY(h, cudaMemcpyAsync(h->h_inst, h->d_inst_all, sizeof(isx_instance) * (size_t)n * h->inst_cap,
-                             cudaMemcpyDeviceToHost, h->s_d2h));
-  ISX_TRY(h, cudaEventRecord(h->ev_batch_done[par], h->s_d2h));
+  ISX_TRY(h, cudaEventRecord(h->ev_batch_done[par], h->s_emit));  // behind the packing of the last chunk
   h->batch_n[par] = n;
+  h->batch_set[par] = h->cur;
+  h->batch_sections[par] = sections;
   h->submitted++;
   h->emit_join_pending = true;  // s_compute itself has not been ordered behind the emission stream
   return ISX_OK;
 }
 
-int isx_wait_batch_host(isx_handle h, isx_instance *instances, int instances_capacity, int32_t *instance_offsets) {
+int isx_submit_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
+                          const isx_road *roads, isx_section *sections) {
+  if (!disparity || !segmentation) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  HostInputs in;
+  in.disparity = disparity;
+  in.segmentation = segmentation;
+  return submit_batch_host(h, pairwise, n, in, roads, sections);
+}
+
+int isx_submit_batch_host_u16(isx_handle h, int pairwise, int n, const uint16_t *disparity, float disparity_scale,
+                              const int16_t *segmentation, const isx_road *roads, isx_section *sections) {
+  if (!disparity || !segmentation) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
+  HostInputs in;
+  in.disparity16 = disparity;
+  in.scale = disparity_scale;
+  in.segmentation16 = segmentation;
+  return submit_batch_host(h, pairwise, n, in, roads, sections);
+}
+
+// Waits for the oldest batch in flight; returns its ticket parity (>= 0) or an error (< 0).
+static int wait_oldest(isx_handle h) {
   if (int rc = check_ready(h)) return rc;
   if (h->submitted == h->waited) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no submitted batch is in flight");
   const int par = (int)(h->waited & 1);
   ISX_TRY(h, cudaEventSynchronize(h->ev_batch_done[par]));
+  h->waited++;
+  return par;
+}
+
+int isx_wait_batch_host(isx_handle h, isx_instance *instances, int instances_capacity, int32_t *instance_offsets) {
+  const int par = wait_oldest(h);
+  if (par < 0) return par;
   const int n = h->batch_n[par];
   h->batch_n[par] = 0;
-  h->waited++;
-  // the oldest batch's pinned copies are the current set's when it is the only one in flight, else the other set's
-  const bool in_other = h->submitted != h->waited;
-  if (in_other) swap_result_sets(h);
-  const int rc = deliver_instances(h, n, instances, instances_capacity, instance_offsets);
-  if (in_other) swap_result_sets(h);
+  return deliver(h, h->rs[h->batch_set[par]], n, h->batch_sections[par], instances, instances_capacity,
+                 instance_offsets);
+}
+
+int isx_wait_batch_packed(isx_handle h, const isx_section **sections, const int32_t **counts,
+                          const isx_instance **instances, const isx_packed_frame **frames, int *n) {
+  const int par = wait_oldest(h);
+  if (par < 0) return par;
+  const isx_context::ResultSet &R = h->rs[h->batch_set[par]];
+  if (sections) *sections = R.h_sections;
+  if (counts) *counts = R.h_counts;
+  if (instances) *instances = R.h_inst;
+  if (frames) *frames = R.h_frames;
+  if (n) *n = h->batch_n[par];
+  int rc = ISX_OK;
+  for (int f = 0; f < h->batch_n[par] && rc == ISX_OK; f++) {
+    if (R.h_frames[f].error & kErrOffsetRange) rc = fail(h, ISX_ERR_UNSUPPORTED, "instance offsets out of range in a frame of the batch");
+    else if (R.h_frames[f].error) rc = fail(h, ISX_ERR_CAPACITY, "a column produced >= 200 stixels (MAX_STIXELS_PER_COLUMN)");
+  }
+  h->batch_n[par] = 0;
   return rc;
 }
 
@@ -991,8 +1112,9 @@ int isx_rasterize_batch_device(isx_handle h, int first, int n, uint8_t *d_label_
   if (!d_label_ids && !d_instance_ids && !d_disparity) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no output image");
   if (int rc = ensure_joined(h)) return rc;
   const size_t C = h->kp.realcols;
-  launch_rasterize(h->kp, h->d_sections_all + (size_t)first * C * kMaxSections, h->d_nsections_all + (size_t)first * C,
-                   h->d_inst_all + (size_t)first * h->inst_cap, h->d_inst_count_all + first, h->inst_cap,
+  const isx_context::ResultSet &R = h->rs[h->cur];
+  launch_rasterize(h->kp, R.d_sections + (size_t)first * C * kMaxSections, R.d_nsections + (size_t)first * C,
+                   R.d_inst + (size_t)first * h->inst_cap, R.d_inst_count + first, h->inst_cap,
                    h->d_raster_table, n, d_label_ids, d_instance_ids, d_disparity, h->s_compute);
   ISX_TRY(h, cudaGetLastError());
   return ISX_OK;

@@ -32,7 +32,7 @@
 
 namespace isx {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 namespace {
 
@@ -768,10 +768,12 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
   }
   for (int i = tid; i <= H; i += kThreads) ihs[i] = __ldg(inverse_height + i);
   if (warp == 0) {
-    // smallest normalization_ground of the frame: per-row ground cost >= min(puniform, it) + ... (:217-234)
+    // smallest normalization_ground over the rows that HAVE a ground cost (v < vhor; at/above the horizon ground_lut
+    // is +inf, :437-446, while normalization_ground itself runs to -inf there: log of a vanishing range,
+    // Stixels.cu:86, 812-814): per-row ground cost >= min(puniform, it) + ... (:217-234)
     const float *norm_g = ground + (size_t)f * 3 * H + H;
     float m = inf;
-    for (int v = lane; v < H; v += 32) m = fminf(m, __ldg(norm_g + v));
+    for (int v = lane; v < min(H, vhor); v += 32) m = fminf(m, __ldg(norm_g + v));
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(full_mask, m, d));
     if (lane == 0) *norm_g_min_s = m;
@@ -1039,8 +1041,8 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__
   for (int i = tid; i < p.max_dis; i += kThreads) odr[i] = __ldg(object_disparity_range + i);
   float norm_g_min = inf;
   {
-    const float *norm_g = ground + (size_t)f * 3 * H + H;
-    for (int v = lane; v < H; v += 32) norm_g_min = fminf(norm_g_min, __ldg(norm_g + v));
+    const float *norm_g = ground + (size_t)f * 3 * H + H;   // rows below the horizon only (see dp_unary_pruned_kernel)
+    for (int v = lane; v < min(H, vhor); v += 32) norm_g_min = fminf(norm_g_min, __ldg(norm_g + v));
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) norm_g_min = fminf(norm_g_min, __shfl_xor_sync(full_mask, norm_g_min, d));
   }
@@ -1278,24 +1280,15 @@ size_t dp_smem_bytes(const KParams &p, bool pairwise) {
 
 template <bool PAIRWISE, bool HAS_INVALID, int WARPS>
 static void launch_dp_warps(const KParams &p, const BatchBuffers &b, int ncolumns, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(dp_kernel<PAIRWISE, HAS_INVALID, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  opt_in_smem(dp_kernel<PAIRWISE, HAS_INVALID, WARPS>, optin);
   dp_kernel<PAIRWISE, HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
       b.records, b.records_b, b.object_lut, b.stat, b.pm, b.vhor, b.object_disparity_range, b.inverse_height, b.dp, p);
 }
 
 template <bool PAIRWISE, bool HAS_INVALID>
 static void launch_dp_variant(const KParams &p, const BatchBuffers &b, int ncolumns, size_t smem, cudaStream_t s) {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = device_sm_count();
   bool latency = ncolumns < 2 * sms;
   if (const char *e = std::getenv("ISX_DP_WARPS")) {  // tests pin the variant
     if (std::atoi(e) == kDpWarps) latency = false;
@@ -1308,24 +1301,15 @@ static void launch_dp_variant(const KParams &p, const BatchBuffers &b, int ncolu
 template <bool HAS_INVALID, int WARPS>
 static void launch_unary_pruned_warps(const KParams &p, const BatchBuffers &b, int ncolumns, cudaStream_t s) {
   const size_t smem = PruneLayout(p.rows, WARPS).total;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(dp_unary_pruned_kernel<HAS_INVALID, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  opt_in_smem(dp_unary_pruned_kernel<HAS_INVALID, WARPS>, optin);
   dp_unary_pruned_kernel<HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
       b.records, b.records_b, b.object_lut, b.ground, b.vhor, b.inverse_height, b.dp, b.dp_units, b.col_flags, p);
 }
 
 template <bool HAS_INVALID>
 static void launch_unary_pruned(const KParams &p, const BatchBuffers &b, int ncolumns, cudaStream_t s) {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = device_sm_count();
   bool latency = ncolumns < 2 * sms;
   if (const char *e = std::getenv("ISX_DP_WARPS")) {  // tests pin the variant
     if (std::atoi(e) == kDpWarps) latency = false;
@@ -1338,12 +1322,8 @@ static void launch_unary_pruned(const KParams &p, const BatchBuffers &b, int nco
 template <bool HAS_INVALID, int WARPS>
 static void launch_pairwise_walk_warps(const KParams &p, const BatchBuffers &b, int ncolumns, cudaStream_t s) {
   const size_t smem = WalkLayout(p.rows, p.max_dis, WARPS).total;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(dp_pairwise_walk_kernel<HAS_INVALID, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  opt_in_smem(dp_pairwise_walk_kernel<HAS_INVALID, WARPS>, optin);
   dp_pairwise_walk_kernel<HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
       b.records, b.records_b, b.object_lut, b.stat, b.ground, b.pm, b.qrows, b.vhor, b.object_disparity_range, b.dp,
       b.dp_units, b.col_flags, p);
@@ -1351,12 +1331,7 @@ static void launch_pairwise_walk_warps(const KParams &p, const BatchBuffers &b, 
 
 template <bool HAS_INVALID>
 static void launch_pairwise_walk(const KParams &p, const BatchBuffers &b, int ncolumns, cudaStream_t s) {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = device_sm_count();
   bool latency = ncolumns < 2 * sms;
   if (const char *e = std::getenv("ISX_DP_WARPS")) {
     if (std::atoi(e) == kDpWarps) latency = false;
@@ -1381,12 +1356,7 @@ bool pairwise_walk_enabled() {
 // 1024 x 2048 frames at width 8); smaller launches keep the chunk-major kernel, whose 4 or 8 warps per column are
 // what a few hundred columns need.  ISX_DP_WARPS / ISX_WALK_WARPS (tests) force the walk's variants.
 bool pairwise_walk_used(int ncolumns, bool have_qrows) {
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sm_count = device_sm_count();
   const bool forced = std::getenv("ISX_DP_WARPS") != nullptr || std::getenv("ISX_WALK_WARPS") != nullptr;
   return pairwise_walk_enabled() && have_qrows && (ncolumns >= 16 * sm_count || forced);
 }

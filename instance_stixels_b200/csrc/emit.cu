@@ -174,7 +174,7 @@ backtrack_kernel(const uint32_t *__restrict__ records, const float4 *__restrict_
     i++;
     if (vB == 0) break;
     if (i >= kMaxSections - 1) {  // reference: assert(i < max_sections) (:950)
-      atomicOr(error_flag, kErrSectionOverflow);
+      atomicOr(error_flag + f, kErrSectionOverflow);
       break;
     }
     type = predecessor_type<PAIRWISE>(type, vB, clamp_neg(mean), dp_col, S, pm_col, vhor, object_disparity_range, p);
@@ -265,6 +265,109 @@ collect_candidates_kernel(const isx_section *__restrict__ sections, const int *_
   }
 }
 
+// ---------------------------------------------------------------------------
+// Result packing.  A frame yields a few thousand stixels, but the reference's result array is the full-capacity
+// [C][200] x 32 B (Stixels.cu:629-633 copies all of it, 1.6 MB per frame, for ~80 KB of payload).  This kernel
+// writes what a host caller needs -- the used Sections of every column back to back, the per-column counts, the
+// instance records (class, column, index order; GetInstanceStixels, Stixels.cu:744-776) and one descriptor per
+// frame -- straight into PINNED HOST memory mapped into the device address space, in 1 KB bursts per warp.  There is
+// no device -> host memcpy and no size the host would have to learn first: when the emission stream's event fires
+// the packed results are in host memory, and the host expands them into the caller's [C][200] array.
+// One CTA per frame.  The frames of a batch take their place in the packed arrays with one atomicAdd per frame on
+// the result set's cursors (placement varies from run to run, content does not; the descriptor says where).
+// A frame that does not fit (more stixels than the packed arrays were sized for) is flagged and left to the
+// padded device arrays, which stay complete in any case.
+// ---------------------------------------------------------------------------
+constexpr int kPackThreads = 256;
+
+__global__ void __launch_bounds__(kPackThreads)
+pack_results_kernel(PackArgs a, KParams p) {
+  __shared__ int warp_tot[kPackThreads / 32];
+  __shared__ int s_base[2], s_running;
+  const int f = blockIdx.x, C = p.realcols;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const isx_section *fs = a.sections + (size_t)f * C * kMaxSections;
+  const int *ns = a.n_sections + (size_t)f * C;
+  int *off = a.col_offset + (size_t)f * (C + 1);
+  // ---- exclusive prefix of the stixel counts over the columns ----
+  if (tid == 0) s_running = 0;
+  __syncthreads();
+  for (int base = 0; base < C; base += kPackThreads) {
+    const int col = base + tid;
+    const int n = col < C ? ns[col] : 0;
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = s_running;
+    for (int w = 0; w < warp; w++) before += warp_tot[w];
+    if (col < C) {
+      off[col] = before + incl - n;
+      a.h_counts[(size_t)f * C + col] = n;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = s_running;
+      for (int w = 0; w < kPackThreads / 32; w++) t += warp_tot[w];
+      s_running = t;
+    }
+    __syncthreads();
+  }
+  const int n_sec = s_running;
+  int n_inst = 0;
+  for (int k = 0; k < kInstanceClasses; k++) n_inst += a.cand_count[f * kInstanceClasses + k];
+  if (tid == 0) {
+    s_base[0] = atomicAdd(a.cursors + 0, n_sec);
+    s_base[1] = atomicAdd(a.cursors + 1, n_inst);
+  }
+  __syncthreads();
+  const int sec_base = s_base[0], inst_base = s_base[1];
+  const bool sec_fits = sec_base + n_sec <= a.h_sections_cap;
+  const bool inst_fits = inst_base + n_inst <= a.h_inst_cap;
+  // ---- sections: one warp per column, 32 B per lane (two 16-byte stores; a warp writes up to 1 KB back to back) ----
+  if (sec_fits) {
+    for (int col = warp; col < C; col += kPackThreads / 32) {
+      const int n = ns[col];
+      const uint4 *src = reinterpret_cast<const uint4 *>(fs + (size_t)col * kMaxSections);
+      uint4 *dst = reinterpret_cast<uint4 *>(a.h_sections + sec_base + off[col]);
+      for (int j = lane; j < 2 * n; j += 32) dst[j] = src[j];
+    }
+  }
+  // ---- instance records in (class, column, index) order: device copy (rasteriser, fetch) and host copy ----
+  {
+    const size_t cap = (size_t)C * kMaxSections;
+    int base = 0;
+    for (int k = 0; k < kInstanceClasses; k++) {
+      const int n = a.cand_count[f * kInstanceClasses + k];
+      const size_t src = ((size_t)f * kInstanceClasses + k) * cap;
+      for (int i = tid; i < n; i += kPackThreads) {
+        const int2 ci = a.cand_idx[src + i];
+        const int4 r = make_int4(ci.x, ci.y, a.cand_label[src + i], kFirstInstanceClass + k);  // isx_instance
+        const int dst = base + i;
+        if (dst < a.inst_cap) *reinterpret_cast<int4 *>(a.inst_out + (size_t)f * a.inst_cap + dst) = r;
+        if (inst_fits) *reinterpret_cast<int4 *>(a.h_inst + inst_base + dst) = r;
+      }
+      base += n;
+    }
+  }
+  if (tid == 0) {
+    a.inst_count_out[f] = n_inst;
+    isx_packed_frame d;
+    d.section_offset = sec_base;
+    d.section_count = n_sec;
+    d.instance_offset = inst_base;
+    d.instance_count = n_inst;
+    d.error = a.err[f];
+    d.overflow = (sec_fits ? 0 : 1) | (inst_fits ? 0 : 2);
+    d.reserved[0] = d.reserved[1] = 0;
+    a.h_frames[f] = d;
+  }
+}
+
 // cost_table / index_table in the reference's layout (parity tests only).
 template <bool PAIRWISE>
 __global__ void export_tables_kernel(const uint32_t *__restrict__ records, const float4 *__restrict__ dp,
@@ -325,6 +428,11 @@ void launch_emit(const KParams &p, const BatchBuffers &b, int nframes, bool pair
   collect_candidates_kernel<<<nframes, 256, 0, s>>>(b.sections, b.n_sections, b.cand_count, b.cand_offset, b.cand_xy,
                                                      b.cand_idx, b.cand_core, p);
   g_launch_count += 2;
+}
+
+void launch_pack(const KParams &p, const PackArgs &a, int nframes, cudaStream_t s) {
+  pack_results_kernel<<<nframes, kPackThreads, 0, s>>>(a, p);
+  g_launch_count++;
 }
 
 void launch_export_tables(const KParams &p, const BatchBuffers &b, int frame, bool pairwise, float *cost_table,

@@ -186,11 +186,8 @@ grouping_kernel(const int *__restrict__ cand_count, const float2 *__restrict__ c
 }  // namespace
 
 void launch_grouping(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(grouping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGroupSmemBytes);
-    configured = true;
-  }
+  static SmemOptIn optin;
+  opt_in_smem(grouping_kernel, optin);
   dim3 grid(kInstanceClasses, nframes);
   const int threads = nframes <= 4 ? kGroupThreadsLatency : kGroupThreads;
   grouping_kernel<<<grid, threads, kGroupSmemBytes, s>>>(b.cand_count, b.cand_xy, b.cand_core, b.cand_label,
@@ -220,11 +217,8 @@ int dbscan_fit_host(const float *xy, int n, float eps, int min_pts, const uint8_
     p.eps_cluster = eps;
     p.min_pts = min_pts;
     if (e == cudaSuccess) {
-      static bool configured = false;
-      if (!configured) {
-        cudaFuncSetAttribute(grouping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGroupSmemBytes);
-        configured = true;
-      }
+      static SmemOptIn optin;
+      opt_in_smem(grouping_kernel, optin);
       grouping_kernel<<<dim3(1, 1), threads, kGroupSmemBytes>>>(d_count, d_xy, d_core, d_label, d_scratch, p);
       g_launch_count++;
       ok(cudaGetLastError());

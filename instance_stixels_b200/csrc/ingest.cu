@@ -47,7 +47,52 @@ flip_and_pad_kernel(const float *__restrict__ cnn, int32_t *__restrict__ seg, in
   }
 }
 
+// ---------------------------------------------------------------------------
+// Narrow host inputs (extension beside the float API): over a host link that carries 11 MB per frame, the bytes are
+// the limit, and both inputs are narrower at their source than the types the reference's API takes:
+//   disparity    uint16 [n][H][W], value = u16 * scale -- Cityscapes disparity PNGs are 16-bit, the reference's
+//                loader divides by 256 on the host (apps/run_cityscapes.cu:141-147: (float)u16 / 256.0f, exact)
+//   segmentation int16 [n][C][21][ceil(H/8)] -- trunc(8 * -log softmax) and pixel offsets * 8 fit 16 bits, and the
+//                zero padding of FlipAndPad (to rows_power2_segmentation) carries nothing
+// One pass widens them into the float / int32 staging buffers of the path; 5.6 instead of 11.1 MB per frame cross
+// the link.  Results are bit-identical to the float API called with the widened arrays (tests/test_gpu_api.py).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+widen_inputs_kernel(const uint16_t *__restrict__ disp16, float scale, const int16_t *__restrict__ seg16,
+                    float *__restrict__ disp, int32_t *__restrict__ seg, size_t n_disp8, size_t n_seg, int used,
+                    int hs2) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // disparity: 8 pixels per thread and iteration (one 16-byte load, two 16-byte stores)
+  const uint4 *src = reinterpret_cast<const uint4 *>(disp16);
+  float4 *dst = reinterpret_cast<float4 *>(disp);
+  for (size_t i = t0; i < n_disp8; i += stride) {
+    const uint4 v = __ldg(src + i);
+    dst[2 * i] = make_float4(__fmul_rn((float)(v.x & 0xffffu), scale), __fmul_rn((float)(v.x >> 16), scale),
+                             __fmul_rn((float)(v.y & 0xffffu), scale), __fmul_rn((float)(v.y >> 16), scale));
+    dst[2 * i + 1] = make_float4(__fmul_rn((float)(v.z & 0xffffu), scale), __fmul_rn((float)(v.z >> 16), scale),
+                                 __fmul_rn((float)(v.w & 0xffffu), scale), __fmul_rn((float)(v.w >> 16), scale));
+  }
+  // segmentation: compact [rows of `used` entries] -> padded rows of hs2 entries (the padding stays zero)
+  for (size_t i = t0; i < n_seg; i += stride) {
+    const size_t row = i / (size_t)used;
+    const int q = (int)(i - row * used);
+    seg[row * (size_t)hs2 + q] = (int32_t)seg16[i];
+  }
+}
+
 }  // namespace
+
+void launch_widen_inputs(const KParams &p, const uint16_t *disp16, float scale, const int16_t *seg16, float *disp,
+                         int32_t *seg, int nframes, cudaStream_t s) {
+  const size_t n_disp = (size_t)nframes * p.rows * p.cols;  // rows * cols is a multiple of 8 (checked by the caller)
+  const int used = (p.rows + kDownsample - 1) / kDownsample;
+  const size_t n_seg = (size_t)nframes * p.realcols * p.n_channels * used;
+  const int blocks = device_sm_count() * 8;
+  widen_inputs_kernel<<<blocks, 256, 0, s>>>(disp16, scale, seg16, disp, seg, n_disp / 8, n_seg,
+                                             used < p.hs2 ? used : p.hs2, p.hs2);
+  g_launch_count++;
+}
 
 void launch_flip_and_pad(const KParams &p, const float *cnn, int32_t *seg, int nframes, int hs, int ws,
                          cudaStream_t s) {

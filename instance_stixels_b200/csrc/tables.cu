@@ -309,7 +309,7 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
       recb_col[(size_t)v * (kRecBWords / 4) + g] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
     }
   }
-  if (out_of_range) atomicOr(error_flag, kErrOffsetRange);
+  if (out_of_range) atomicOr(error_flag + f, kErrOffsetRange);
   (void)lane;
 }
 
@@ -396,11 +396,8 @@ static size_t tab_smem_bytes(const KParams &p) { return TabSmem(p.rows, p.hs2).t
 void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s) {
   dim3 grid(p.realcols, nframes);
   const size_t smem = tab_smem_bytes(p);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(column_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  opt_in_smem(column_tables_kernel, optin);
   column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.records,
                                                         b.records_b, b.error_flag, b.col_flags, p);
   dim3 lgrid(p.realcols, (p.max_dis + 32 * kLutWarps - 1) / (32 * kLutWarps), nframes);

@@ -28,7 +28,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_sizes():
     lib = L.load()
-    assert lib.isx_abi_version() == 1
+    assert lib.isx_abi_version() == 2
+    assert L.PACKED_FRAME_DTYPE.itemsize == 32  # isx_packed_frame
     assert C.sizeof(L.Config) == 41 * 4
     assert L.SECTION_DTYPE.itemsize == 32  # Section, types.h:186-194
     assert C.sizeof(L.FrameMeta) == 36 and C.sizeof(L.Road) == 16
