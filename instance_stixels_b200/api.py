@@ -223,7 +223,7 @@ class Stixels:
             raise InvalidArgument("SubmitBatch needs C-contiguous float32 / int32 arrays (no hidden copies)")
         self._check(self._lib.isx_submit_batch_host(self._h, int(pairwise), n, disparity.ctypes.data,
                                                     segmentation.ctypes.data, _roads(roads),
-                                                    sections_out.ctypes.data))
+                                                    sections_out.ctypes.data if sections_out is not None else None))
         self._in_flight = getattr(self, "_in_flight", [])
         self._in_flight.append((n, disparity, segmentation, sections_out))
 

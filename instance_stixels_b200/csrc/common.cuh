@@ -96,6 +96,7 @@ struct KParams {
   int lut_cols;      // column slots of the object-LUT buffer (chunk * C), see lut_column_address
   // unary branch and bound (dp.cu)
   float obj_cost_min;  // smallest entry of obj_cost_lut
+  float obj_cost_absmax;  // largest |entry| of obj_cost_lut (scale of the rounding of the object LUT's prefix sums)
   int prune_unary;     // 0: walk every chunk (debug / A-B runs, ISX_UNARY_PRUNE=0)
   int prune_pairwise;  // same for the pairwise tile-major walk (ISX_PAIRWISE_PRUNE=0)
 };

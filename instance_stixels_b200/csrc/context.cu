@@ -208,8 +208,14 @@ static void fill_kparams(isx_context *c) {
   k.rec_stride = kRecStride;  // constant whatever the height (rows <= 1024 is checked in isx_initialize)
   k.lut_stride = (m.rows + 31) & ~31;
   float mn = m.obj_cost_lut.empty() ? 0.0f : m.obj_cost_lut[0];
-  for (float v : m.obj_cost_lut) mn = v < mn ? v : mn;
+  float amax = 0.0f;
+  for (float v : m.obj_cost_lut) {
+    mn = v < mn ? v : mn;
+    const float a = v < 0.0f ? -v : v;
+    amax = a > amax ? a : amax;   // NaN entries are skipped; an infinite one makes the slack infinite: no pruning
+  }
   k.obj_cost_min = mn;
+  k.obj_cost_absmax = amax;
   const char *e = std::getenv("ISX_UNARY_PRUNE");
   k.prune_unary = (e && std::atoi(e) == 0) ? 0 : 1;
   const char *e2 = std::getenv("ISX_PAIRWISE_PRUNE");

@@ -694,8 +694,8 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
 //         seg_c(vB, vT) >= P_c(vT + 1) - P_c(last row of chunk j-1)                          (prefixes are monotone)
 //         instance term >= -2^-19 * iw * (sum of squared means up to the tile)               (float error of the variance)
 //         data terms    >= rows * min(0, smallest per-row cost)                              (over the longest segment)
-//     combined with the same monotone float operations as the cell itself, minus (1 + dw) of slack for the
-//     rounding of the float prefix sums; the bound only grows further down, so the walk stops as soon as
+//     combined with the same monotone float operations as the cell itself, minus the slack prune_bound() derives
+//     from the magnitudes involved; the bound only grows further down, so the walk stops as soon as
 //     it exceeds the carried cost of both slots in every row of the tile.
 // The result is bit-identical to the exhaustive scan (same cells win, same ties); tests run both.
 // B records travel global -> shared memory per warp (two 4 KB buffers, cp.async.bulk + mbarrier), the next
@@ -704,6 +704,26 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
 #ifndef ISX_UNARY_PRUNE
 #define ISX_UNARY_PRUNE 1
 #endif
+
+// ---- how far a computed cell cost can lie below the bound's exact value (derivation: DESIGN.md section 4) ----
+// A bound X = sw * seg_lb + (dw * data_lb + prior_lb) is evaluated with the cell's own operations on lower bounds
+// of its inputs, and float rounding is monotone, so the only places where the cell can come out BELOW X are
+//  (a) the data term: it is the difference of two float prefix sums (object LUT rows, ground / sky prefixes), each
+//      the result of at most 37 additions (32 chunk carries + 5 Kogge-Stone / Blelloch levels) of partial sums whose
+//      magnitude is at most rows * cmax (cmax = largest |per-row cost| of the model): |error| <= 2 * 37 * 2^-24 *
+//      rows * cmax, plus one rounding each for the bound's own rows * lb product and its scaling by dw.
+//      kDataErr = 2^-17 = 128 * 2^-24 covers 2 * 37 + 6 roundings;
+//  (b) the order of the final operations (the cell: one FFMA on the data term and the prior, then one on the class
+//      sum; the bound: FMUL, FADD, FFMA): each rounding is relative 2^-24 of a value no larger than
+//      |X| + |dw * data_lb| + |prior_lb|; kRelErr = 2^-20 leaves a factor 16 over the <= 4 roundings involved.
+// Nothing else is hand-picked: the bound holds for any rows, max_dis and non-negative weights.
+constexpr float kDataErr = 7.62939453125e-06f;     // 2^-17
+constexpr float kRelErr = 9.5367431640625e-07f;    // 2^-20
+__device__ __forceinline__ float prune_bound(float x, float dneg, float prior, float data_slack) {
+  if (!(x < inf_f())) return x;   // +inf (no finite candidate in the chunk) stays +inf; NaN never prunes
+  const float mag = fadd(fadd(fabsf(x), fabsf(dneg)), fabsf(prior));
+  return fsub(x, ffma(mag, kRelErr, data_slack));
+}
 #ifndef ISX_PRUNED_CTAS
 #define ISX_PRUNED_CTAS 4  // 128 registers: carried + local minima and the bound ingredients beside the 30 A words
 #endif
@@ -786,6 +806,12 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
   const float lb_s = fminf(p.pnexists_given_sky_log,
                            fadd(fminf(p.puniform_sky, p.normalization_sky), p.nopnexists_given_sky_log));
   const float lb_o = p.obj_cost_min;
+  // largest magnitude of a per-row data cost of each model: what the rounding of their float prefix sums scales with
+  const float cmax_g = fmaxf(fabsf(p.pnexists_given_ground_log),
+                             fmaxf(fabsf(fadd(p.puniform, p.nopnexists_given_ground_log)), fabsf(lb_g)));
+  const float cmax_s = fmaxf(fabsf(p.pnexists_given_sky_log),
+                             fmaxf(fabsf(fadd(p.puniform_sky, p.nopnexists_given_sky_log)), fabsf(lb_s)));
+  const float cmax_o = p.obj_cost_absmax;
   // the bounds assume non-negative weights (NaN fails the test too) and non-negative class values without int32
   // wrap-around (col_flags, column_tables_kernel): otherwise every chunk is evaluated
   const bool prune_ok = ISX_UNARY_PRUNE && c.sw >= 0.0f && c.dw >= 0.0f && c.pw >= 0.0f && c.iw >= 0.0f &&
@@ -830,11 +856,11 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
     sq = __shfl_sync(full_mask, sq, 0);
     const float ic_lb = -fmul(fmul(sq, c.iw), 1.9073486328125e-06f);  // 2^-19: > 5 roundings + MUFU.RCP, relative
     const float nmaxf = (float)(vTmaxc + 1);
-    // rounding of the float prefix sums behind the data terms (two prefixes of <= 37 additions each, entries below
-    // 2^17: < 0.6 absolute, scaled by dw) and of the final FFMAs
-    const float slack = fadd(1.0f, c.dw);
     const float dneg_o = fmul(c.dw, fmul(nmaxf, fminf(lb_o, 0.0f)));
     const float dneg_gs = fmul(c.dw, fmul(nmaxf, fminf(vTc < vhor ? lb_g : lb_s, 0.0f)));
+    // slack of the data terms (prune_slack below): dw * kDataErr * rows * largest per-row cost
+    const float dslack_o = fmul(c.dw, fmul(fmul(nmaxf, cmax_o), kDataErr));
+    const float dslack_gs = fmul(c.dw, fmul(fmul(nmaxf, vTc < vhor ? cmax_g : cmax_s), kDataErr));
 
     Best carried{inf, inf, 0, 0};
     int buf = 0;
@@ -907,11 +933,11 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
         const int l_s = (int)(A[kSkyClass] - Bl[kSkyClass]);
         // object slot: seg_o >= min(0 + S_ni, ic + S_in), prior >= 0
         const float seg_o_lb = fminf((float)l_ni, fadd(ic_lb, (float)l_in));
-        const float lbo = fsub(ffma(seg_o_lb, c.sw, dneg_o), slack);
+        const float lbo = prune_bound(ffma(seg_o_lb, c.sw, dneg_o), dneg_o, 0.0f, dslack_o);
         // ground / sky slot of this lane's row; sky cells need vB > vhor, ground rows always have candidates
         const bool gs_possible = vTc < vhor || vbm > vhor;
         const float seg_gs_lb = (float)(vTc < vhor ? l_g : l_s);
-        const float lbgs = fsub(ffma(seg_gs_lb, c.sw, dneg_gs), slack);
+        const float lbgs = prune_bound(ffma(seg_gs_lb, c.sw, dneg_gs), dneg_gs, 0.0f, dslack_gs);
         const bool lane_done = !row_ok || (lbo > carried.o && (!gs_possible || lbgs > carried.gs));
         stop = __all_sync(full_mask, lane_done);
       }
@@ -942,7 +968,7 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
 //              smallest of the candidate priors for the object slot),
 //     seg   >= class sums over the shortest segment (last row of chunk j .. vT), instance term >= -2^-19*iw*sum(means^2),
 //     data  >= rows * min(0, smallest per-row cost),
-// combined with the cell's own monotone float operations, minus (1 + dw) of slack.  Minima are merged
+// combined with the cell's own monotone float operations, minus the slack of prune_bound().  Minima are merged
 // lexicographically by (cost, vB): the reference's "lowest vB wins ties" whatever the order of evaluation.
 // ---------------------------------------------------------------------------
 #ifndef ISX_WALK_CTAS
@@ -1051,9 +1077,13 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__
   const float lb_s = fminf(p.pnexists_given_sky_log,
                            fadd(fminf(p.puniform_sky, p.normalization_sky), p.nopnexists_given_sky_log));
   const float lb_o = p.obj_cost_min;
+  const float cmax_g = fmaxf(fabsf(p.pnexists_given_ground_log),
+                             fmaxf(fabsf(fadd(p.puniform, p.nopnexists_given_ground_log)), fabsf(lb_g)));
+  const float cmax_s = fmaxf(fabsf(p.pnexists_given_sky_log),
+                             fmaxf(fabsf(fadd(p.puniform_sky, p.nopnexists_given_sky_log)), fabsf(lb_s)));
+  const float cmax_o = p.obj_cost_absmax;
   const bool prune_ok = c.sw >= 0.0f && c.dw >= 0.0f && c.pw >= 0.0f && c.iw >= 0.0f && p.prune_pairwise != 0 &&
                         col_flags[gcol] == 0;
-  const float slack = fadd(1.0f, c.dw);
   // first-segment priors (:189-199)
   const float first_k_gs = fmul(ffma(1.0f, kLn2, p.rows_log), c.pw);
 
@@ -1089,6 +1119,8 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__
     const float nmaxf = (float)(vTmaxc + 1);
     const float dneg_o = fmul(c.dw, fmul(nmaxf, fminf(lb_o, 0.0f)));
     const float dneg_gs = fmul(c.dw, fmul(nmaxf, fminf(vTc < vhor ? lb_g : lb_s, 0.0f)));
+    const float dslack_o = fmul(c.dw, fmul(fmul(nmaxf, cmax_o), kDataErr));
+    const float dslack_gs = fmul(c.dw, fmul(fmul(nmaxf, vTc < vhor ? cmax_g : cmax_s), kDataErr));
 
     // ================= (1) the chunks below the diagonal, nearest first, interleaved over the warps =================
     Best carried{inf, inf, 0, 0};
@@ -1113,10 +1145,11 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__
         const int l_g = min((int)(A[0] - Bl[0]), (int)(A[1] - Bl[1]));
         const int l_s = (int)(A[kSkyClass] - Bl[kSkyClass]);
         const float seg_o_lb = fminf((float)l_ni, fadd(ic_lb, (float)l_in));
-        const float lbo = fsub(ffma(seg_o_lb, c.sw, fadd(dneg_o, cmin_o[j])), slack);
+        const float pr_o = cmin_o[j];
+        const float lbo = prune_bound(ffma(seg_o_lb, c.sw, fadd(dneg_o, pr_o)), dneg_o, pr_o, dslack_o);
         const float seg_gs_lb = (float)(vTc < vhor ? l_g : l_s);
         const float pr_gs = vTc < vhor ? cmin_g[j] : cmin_s[j];
-        const float lbgs = fsub(ffma(seg_gs_lb, c.sw, fadd(dneg_gs, pr_gs)), slack);
+        const float lbgs = prune_bound(ffma(seg_gs_lb, c.sw, fadd(dneg_gs, pr_gs)), dneg_gs, pr_gs, dslack_gs);
         const bool lane_done = !row_ok || ((lbo > carried.o || lbo == inf) && (lbgs > carried.gs || lbgs == inf));
         skip = __all_sync(full_mask, lane_done);
       }

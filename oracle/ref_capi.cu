@@ -14,6 +14,7 @@
 #include "Stixels.hpp"
 #undef private
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -227,6 +228,54 @@ double ref_time_frames(void *p, int pairwise, int n_frames, const float *dispari
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return (double)ms * 1e-3;
+}
+
+extern "C" double ref_dbscan_standin_seconds(int reset);  // dbscan_standin.cu
+
+// The same loop with the host clock around every call of the sequence (they all block: cudaMemcpy / device-wide
+// synchronisation inside): out[0] SetDisparityImage + SetSegmentation (H2D), out[1] Compute (road tables, kernels,
+// ClusterInstances, D2H of all Sections), out[2] GetInstanceStixels (two full-capacity D2H copies + std::map),
+// out[3] the part of out[1] spent in the DBSCAN stand-in (not reference code).  Seconds over all frames.
+double ref_time_frames_split(void *p, int pairwise, int n_frames, const float *disparity, size_t n_disp,
+                             const int32_t *seg, size_t n_seg, int vhor, float tilt, float height, float alpha,
+                             double *out) {
+  RefCtx *c = static_cast<RefCtx *>(p);
+  std::vector<std::vector<pixel_t>> disp(n_frames);
+  std::vector<std::vector<int32_t>> segv(n_frames);
+  for (int f = 0; f < n_frames; f++) {
+    disp[f].assign(disparity + (size_t)f * n_disp, disparity + (size_t)(f + 1) * n_disp);
+    segv[f].assign(seg + (size_t)f * n_seg, seg + (size_t)(f + 1) * n_seg);
+  }
+  using clk = std::chrono::steady_clock;
+  auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  cudaDeviceSynchronize();
+  ref_dbscan_standin_seconds(1);
+  double t_set = 0, t_compute = 0, t_get = 0;
+  const auto start = clk::now();
+  for (int f = 0; f < n_frames; f++) {
+    const auto a = clk::now();
+    c->stixels.SetDisparityImage(disp[f]);
+    c->stixels.SetSegmentation(segv[f]);
+    c->stixels.SetRoadParameters(vhor, tilt, height, alpha);
+    cudaDeviceSynchronize();   // the disparity copy is the one asynchronous call (pageable source: returns once staged)
+    const auto b = clk::now();
+    c->stixels.Compute(pairwise != 0, c->data);
+    const auto d = clk::now();
+    c->instances = c->stixels.GetInstanceStixels();
+    const auto e = clk::now();
+    t_set += secs(a, b);
+    t_compute += secs(b, d);
+    t_get += secs(d, e);
+  }
+  cudaDeviceSynchronize();
+  const double total = secs(start, clk::now());
+  if (out) {
+    out[0] = t_set;
+    out[1] = t_compute;
+    out[2] = t_get;
+    out[3] = ref_dbscan_standin_seconds(1);
+  }
+  return total;
 }
 
 int ref_num_instances(void *p) { return (int)static_cast<RefCtx *>(p)->instances.size(); }

@@ -42,6 +42,8 @@ def load():
         lib.ref_time_frames.argtypes = [V, C.c_int, C.c_int, V, C.c_size_t, V, C.c_size_t, C.c_int, C.c_float,
                                         C.c_float, C.c_float]
         lib.ref_time_frames.restype = C.c_double
+        lib.ref_time_frames_split.argtypes = lib.ref_time_frames.argtypes + [C.POINTER(C.c_double)]
+        lib.ref_time_frames_split.restype = C.c_double
         lib.ref_num_instances.argtypes = [V]
         lib.ref_get_instances.argtypes = [V, V, C.c_int]
         lib.ref_tensor_elems.argtypes = [V, C.c_int]
@@ -95,6 +97,17 @@ class RefStixels:
         return self.lib.ref_time_frames(self.h, int(pairwise), n, d.ctypes.data, d[0].size, s.ctypes.data,
                                         s[0].size, int(road["vhor"]), road["camera_tilt"],
                                         road["camera_height"], road["alpha_ground"])
+
+    def time_frames_split(self, pairwise: bool, disparity: np.ndarray, segmentation: np.ndarray, road: dict) -> dict:
+        """Host-clock split of the same loop (every call of the sequence blocks): seconds over all frames."""
+        d = np.ascontiguousarray(disparity, dtype=np.float32)
+        s = np.ascontiguousarray(segmentation, dtype=np.int32)
+        out = (C.c_double * 4)()
+        total = self.lib.ref_time_frames_split(self.h, int(pairwise), d.shape[0], d.ctypes.data, d[0].size,
+                                               s.ctypes.data, s[0].size, int(road["vhor"]), road["camera_tilt"],
+                                               road["camera_height"], road["alpha_ground"], out)
+        return dict(total=total, set_inputs=out[0], compute=out[1], get_instance_stixels=out[2],
+                    dbscan_standin=out[3], frames=int(d.shape[0]))
 
     def read_tensor(self, tensor: int) -> np.ndarray:
         n = self.lib.ref_tensor_elems(self.h, tensor)
