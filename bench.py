@@ -46,7 +46,7 @@ WORKLOADS = {
     "pairwise_stream_b256": dict(mode="pairwise", step=8, batch=256),
 }
 ROWS, COLS = 1024, 2048
-RECORD_WORDS_PER_ROW = 30 + 32   # prefix records per row and column: word-major copy + 128-byte row-major copy (common.cuh)
+RECORD_WORDS_PER_ROW = 32   # prefix records: one 128-byte row per image row and column (common.cuh kRecBWords)
 OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of a 32-frame chunk, from the `ncu --set full` captures
 # summarised in profiles/r1j_{unary,pairwise}_b32.txt (width 8; no capture for width 4).

@@ -27,12 +27,13 @@ constexpr float kNegLog07 = 0.35667496919631958008f;   // -logf(0.7f) folded by 
 constexpr float kLg2_03 = -1.7369655370712280273f;     // lg2(0.3f) folded by nvcc (StixelsKernels.cu:186)
 
 // ---- column tables: prefix sums over rows [0, v) of one stixel column ----
-// Stored word-major ("SoA"): records[column][word][v], v in [0, rec_stride), rec_stride = H + 1
-// rounded up to 32, so that both access patterns of the DP are coalesced 128-byte lines:
-//   * "A side": lane l reads word w of row vT + 1 = a + l + 1  (one line per word),
-//   * "B side": the 32 rows of a vB chunk are staged once per CTA into shared memory.
-// The row length is the constant kRecStride (H <= 1024) whatever the image height, so that the word
-// offsets of the A-side loads are immediates of the load instructions (one address per unit, not 30).
+// One record of 32 words (30 used) per row v in [0, H]: records_b[column][v][32], 128-byte rows, rec_stride rows
+// per column.  Both access patterns of the DP move whole lines:
+//   * "B side": the 32 rows of a vB chunk are one contiguous 4 KB block for cp.async.bulk into shared memory,
+//   * "A side": lane l reads the row of vT + 1 = a + l + 1 (its own 128-byte line), once per tile.
+// (Round 1 kept a second, word-major copy for the A side: 32 MB per frame of extra writes for a load that the
+// pruning kernels issue once per tile.)
+// The row count per column is the constant kRecStride (H <= 1024) whatever the image height.
 constexpr int kRecStride = 1056;  // 1024 + 1 rounded up to 32
 constexpr int kRecWords = 30;
 constexpr int kRecSeg = 0;     // 19 words: full-resolution prefix of class c, exact int32
@@ -56,9 +57,7 @@ constexpr int kRecValid = 27;  // float prefix of valid                       (:
 constexpr int kRecGround = 28; // float Blelloch-order prefix of ground_lut   (:437-446,460)
 constexpr int kRecSky = 29;    // float Blelloch-order prefix of sky_lut      (:424-433,461)
 constexpr int kSqSplitBits = 12;
-// Second copy for the B side: records_b[column][v][32 words] (30 used), 128-byte rows, so that the 32
-// rows of a vB chunk are one contiguous 4 KB block for cp.async.bulk.
-constexpr int kRecBWords = 32;
+constexpr int kRecBWords = 32;  // words per stored row (128 bytes)
 // bits of the sticky device error flag
 constexpr int kErrSectionOverflow = 1;  // a column produced >= 200 stixels (StixelsKernels.cu:950 asserts)
 constexpr int kErrOffsetRange = 2;      // instance-offset sums outside the exact-float range above
@@ -91,7 +90,7 @@ struct KParams {
   float pord, epsilon, pgrav, pblg;
   float prior_weight, disparity_weight, segmentation_weight, instance_weight;
   // derived strides
-  int rec_stride;    // entries per (column, word) row of the records: always kRecStride
+  int rec_stride;    // rows per column of the records: always kRecStride
   int lut_stride;    // floats per fn row of the object LUT (>= H, multiple of 32)
   int lut_cols;      // column slots of the object-LUT buffer (chunk * C), see lut_column_address
   // unary branch and bound (dp.cu)

@@ -69,7 +69,7 @@ struct isx_context {
     float *ground = nullptr;
     int *vhor = nullptr;
     float *stat = nullptr;
-    uint32_t *records = nullptr, *records_b = nullptr;
+    uint32_t *records_b = nullptr;
     float4 *dp = nullptr;
     float *pm = nullptr;
     int *err = nullptr;   // [chunk] kErr* bits per frame, zeroed when the chunk is enqueued
@@ -261,7 +261,7 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
   isx_context::ResultSet &R = c->rs[c->cur];
   BatchBuffers b = c->buf;
   b.ground = cs.ground; b.vhor = cs.vhor; b.stat = cs.stat;
-  b.records = cs.records; b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
+  b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
   b.error_flag = cs.err;
   b.disparity = d_disp;
   b.segmentation = d_seg;
@@ -343,9 +343,10 @@ static int alloc_result_set(isx_context *c, int i) {
   ISX_TRY(c, dev_alloc(c, &R.d_inst_count, MB));
   ISX_TRY(c, dev_alloc(c, &R.d_cursors, 2));
   ISX_TRY(c, cudaMemset(R.d_cursors, 0, 2 * sizeof(int)));
-  // Packed arrays: sized for `budget` stixels per column on average (street scenes have about ten; the capacity of
-  // the reference's array is 200).  A batch that needs more falls back to the padded arrays frame by frame.
-  size_t budget = 32;
+  // Packed arrays: sized for `budget` stixels per column on average over a batch (the pairwise model yields about
+  // ten per column on street scenes, the unary model with its 1/n prior sixty to seventy; the capacity of the
+  // reference's array is 200).  A batch that needs more falls back to the padded arrays frame by frame.
+  size_t budget = 100;
   if (const char *e = std::getenv("ISX_PACK_BUDGET")) budget = std::atoi(e) > 0 ? (size_t)std::atoi(e) : budget;
   budget = budget < (size_t)kMaxSections ? budget : (size_t)kMaxSections;
   R.sections_cap = R.inst_cap = (int)(MB * C * budget);
@@ -569,8 +570,6 @@ int isx_initialize(isx_handle h, int max_batch) {
     ISX_TRY(h, dev_alloc(h, &cs.ground, ch * 3 * H));
     ISX_TRY(h, dev_alloc(h, &cs.vhor, ch));
     ISX_TRY(h, dev_alloc(h, &cs.stat, ch * H * kStatWords));
-    ISX_TRY(h, dev_alloc(h, &cs.records, ch * C * kRecWords * (size_t)kp.rec_stride));
-    ISX_TRY(h, cudaMemset(cs.records, 0, ch * C * kRecWords * (size_t)kp.rec_stride * sizeof(uint32_t)));
     ISX_TRY(h, dev_alloc(h, &cs.records_b, ch * C * kRecBWords * (size_t)kp.rec_stride));
     ISX_TRY(h, cudaMemset(cs.records_b, 0, ch * C * kRecBWords * (size_t)kp.rec_stride * sizeof(uint32_t)));
     ISX_TRY(h, dev_alloc(h, &cs.pm, ch * C * H));
@@ -1162,7 +1161,7 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
   {
     const isx_context::ChunkSet &cs = h->sets[h->last_set];
     b.ground = cs.ground; b.vhor = cs.vhor; b.stat = cs.stat;
-    b.records = cs.records; b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
+    b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
   }
   if (tensor == ISX_T_GROUND_TABLES) {
     ISX_TRY(h, cudaMemcpy(host, b.ground + (size_t)local * 3 * H, need, cudaMemcpyDeviceToHost));
@@ -1187,10 +1186,11 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
                      : tensor == ISX_T_VALID_PS   ? kRecValid
                      : tensor == ISX_T_GROUND_PS  ? kRecGround
                                                   : kRecSky;
-    // word-major records: [column][word][rec_stride] -> [column][H+1]
-    ISX_TRY(h, cudaMemcpy2D(host, (H + 1) * 4,
-                            b.records + ((size_t)local * C * kRecWords + word) * kp.rec_stride,
-                            (size_t)kRecWords * kp.rec_stride * 4, (H + 1) * 4, C, cudaMemcpyDeviceToHost));
+    // records [column][row][32 words] -> word `word` of rows 0 .. H of every column: [column][H+1]
+    for (size_t col = 0; col < C; col++)
+      ISX_TRY(h, cudaMemcpy2D(static_cast<float *>(host) + col * (H + 1), 4,
+                              b.records_b + (((size_t)local * C + col) * kp.rec_stride) * kRecBWords + word,
+                              (size_t)kRecBWords * 4, 4, H + 1, cudaMemcpyDeviceToHost));
   } else {
     launch_export_tables(kp, b, local, h->last_pairwise, h->d_export_cost, h->d_export_index, h->s_compute);
     ISX_TRY(h, cudaStreamSynchronize(h->s_compute));

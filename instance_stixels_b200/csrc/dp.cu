@@ -4,8 +4,8 @@
 //
 // The column's rows are cut into tiles of 32 top rows (lane l of a warp owns vT = a + l) and into chunks of 32
 // candidate bottom rows vB.  A (tile, chunk) pair with tile >= chunk is one unit of work: 32 x 32 DP cells,
-// evaluated by one warp with the records R[vT+1] of its rows in 30 registers ("A side", word-major copy of the
-// column tables) and the records R[vB] of the chunk in shared memory ("B side", row-major copy, one 4 KB bulk
+// evaluated by one warp with the records R[vT+1] of its rows in 30 registers ("A side", each lane reads its own
+// 128-byte row) and the records R[vB] of the chunk in shared memory ("B side", the same rows as one 4 KB bulk
 // async copy per chunk: cp.async.bulk + mbarrier).  Because one of GROUND/SKY is +inf for every row (ground only
 // exists below the horizon, sky only at/above it) the cost table keeps two slots per row: "gs" (ground if
 // vT < vhor else sky) and "object".  No tensor cores: the recurrence is min-plus, not a dense contraction.
@@ -89,6 +89,24 @@ __device__ __forceinline__ float ldg_lut(unsigned lo, unsigned hi) {
 }
 
 __device__ __forceinline__ float f_(uint32_t u) { return __uint_as_float(u); }
+
+// A side of a unit: the record of this lane's row vT + 1, one 128-byte row of the row-major records (eight 16-byte
+// loads per lane; a warp touches 32 consecutive lines).  A pruning kernel loads it once per TILE, not per unit.
+__device__ __forceinline__ void load_a_side(uint32_t (&A)[kRecWords], const uint32_t *__restrict__ recb, int row) {
+  const uint4 *r4 = reinterpret_cast<const uint4 *>(recb + (size_t)row * kRecBWords);
+#pragma unroll
+  for (int g = 0; g < (kRecWords + 3) / 4; g++) {
+    const uint4 t = __ldg(r4 + g);
+    A[4 * g] = t.x;
+    A[4 * g + 1] = t.y;
+    if (4 * g + 2 < kRecWords) A[4 * g + 2] = t.z;
+    if (4 * g + 3 < kRecWords) A[4 * g + 3] = t.w;
+  }
+}
+// one word of one row of the row-major records
+__device__ __forceinline__ uint32_t rec_word(const uint32_t *__restrict__ recb, int row, int word) {
+  return __ldg(recb + (size_t)row * kRecBWords + word);
+}
 
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -372,7 +390,7 @@ __device__ __forceinline__ void store_best(float4 *p, const Best &b) {
 
 template <bool PAIRWISE, bool HAS_INVALID, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == kDpWarps ? (PAIRWISE ? ISX_PAIRWISE_CTAS : ISX_UNARY_CTAS) : 2)
-dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
+dp_kernel(const uint32_t *__restrict__ records_b,
           const float *__restrict__ object_lut, const float *__restrict__ stat, float *__restrict__ pm_out,
           const int *__restrict__ vhor_arr, const float *__restrict__ object_disparity_range,
           const float *__restrict__ inverse_height, float4 *dp_out, KParams p) {
@@ -408,7 +426,6 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
   c.lut_stride4 = (unsigned)p.lut_stride * 4u;
   c.epsilon = p.epsilon;
 
-  const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
   const uint32_t *recb = records_b + (size_t)gcol * Hp * kRecBWords;
   // low / high address words of LUT[0][0] of this column; the low word carries the -2^23-rows bias of
   // the float -> row trick in cell_base (all modulo 2^32)
@@ -522,8 +539,7 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
 
     // A side of the unit (independent of every wait below)
     uint32_t A[kRecWords];
-#pragma unroll
-    for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
+    load_a_side(A, recb, vTc + 1);
     const unsigned ca = lutb + 4u * (unsigned)vTc;
     const unsigned cb0 = lutb + 4u * (unsigned)(vb0 - 1);  // row vB - 1 of step k: cb0 + 4k
 
@@ -555,8 +571,8 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
         // chain's latency.
         const float *sst_j = sst + (j % kSstBufs) * kSstWords;
         // prefix values at the start row of the best object segment so far (previous_mean needs them)
-        float lo_d = f_(__ldg(rec + (size_t)kRecDisp * Hp + best.vb_o));
-        float lo_v = f_(__ldg(rec + (size_t)kRecValid * Hp + best.vb_o));
+        float lo_d = f_(rec_word(recb, best.vb_o, kRecDisp));
+        float lo_v = f_(rec_word(recb, best.vb_o, kRecValid));
         // Q[vb0] comes from the previous diagonal
         if (j > 0) {
           mbar_wait(&bar_q[(j - 1) % kStages], (unsigned)((j - 1) / kStages) & 1u);
@@ -612,8 +628,8 @@ dp_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ rec
         // Q[vb0 + 32] for the next diagonal (row vb0 + 31 is final now)
         if (vb0 + kChunk < H) {
           const int vB = vb0 + kChunk;
-          const RowInfo q = finish_row(vB, 31, f_(__ldg(rec + (size_t)kRecDisp * Hp + vB)),
-                                       f_(__ldg(rec + (size_t)kRecValid * Hp + vB)));
+          const RowInfo q = finish_row(vB, 31, f_(rec_word(recb, vB, kRecDisp)),
+                                       f_(rec_word(recb, vB, kRecValid)));
           if (lane == 0) {
             store_row_info(qnext + ((j + 1) & 1) * kDynWords, q);
             pm_col[vB] = q.pm;
@@ -743,7 +759,7 @@ struct PruneLayout {
 
 template <bool HAS_INVALID, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == kDpWarps ? ISX_PRUNED_CTAS : 2)
-dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
+dp_unary_pruned_kernel(const uint32_t *__restrict__ records_b,
                        const float *__restrict__ object_lut, const float *__restrict__ ground,
                        const int *__restrict__ vhor_arr, const float *__restrict__ inverse_height, float4 *dp_out,
                        unsigned long long *__restrict__ units_evaluated, const int *__restrict__ col_flags, KParams p) {
@@ -771,7 +787,6 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
   c.dm1f = (float)(p.max_dis - 1);
   c.lut_stride4 = (unsigned)p.lut_stride * 4u;
   c.epsilon = p.epsilon;
-  const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
   const uint32_t *recb = records_b + (size_t)gcol * Hp * kRecBWords;
   const unsigned long long lut_addr = lut_column_address((unsigned long long)object_lut, (size_t)gcol, p.lut_cols,
                                                          (size_t)p.max_dis * p.lut_stride * 4);
@@ -842,16 +857,14 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records, const uint32_t *__r
     stage(t, 0);
 
     uint32_t A[kRecWords];
-#pragma unroll
-    for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
+    load_a_side(A, recb, vTc + 1);
     const unsigned ca = lutb + 4u * (unsigned)vTc;
     // ---- what the bounds of this tile are made of ----
     const int vTmaxc = min(t * kChunk + kChunk - 1, H - 1);
     float sq = 0.0f;
     if (lane == 0) {
-      const uint32_t *r1 = rec + vTmaxc + 1;
-      sq = fadd(fadd(f_(__ldg(r1 + (size_t)kRecMx2Hi * Hp)), f_(__ldg(r1 + (size_t)kRecMx2Lo * Hp))),
-                fadd(f_(__ldg(r1 + (size_t)kRecMy2Hi * Hp)), f_(__ldg(r1 + (size_t)kRecMy2Lo * Hp))));
+      sq = fadd(fadd(f_(rec_word(recb, vTmaxc + 1, kRecMx2Hi)), f_(rec_word(recb, vTmaxc + 1, kRecMx2Lo))),
+                fadd(f_(rec_word(recb, vTmaxc + 1, kRecMy2Hi)), f_(rec_word(recb, vTmaxc + 1, kRecMy2Lo))));
     }
     sq = __shfl_sync(full_mask, sq, 0);
     const float ic_lb = -fmul(fmul(sq, c.iw), 1.9073486328125e-06f);  // 2^-19: > 5 roundings + MUFU.RCP, relative
@@ -1014,7 +1027,7 @@ __device__ __forceinline__ float object_prior_floor(const RowInfo &q, bool groun
 
 template <bool HAS_INVALID, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 16 : WARPS == kDpWarps ? ISX_WALK_CTAS : 2)
-dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__restrict__ records_b,
+dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
                         const float *__restrict__ object_lut, const float *__restrict__ stat,
                         const float *__restrict__ ground, float *__restrict__ pm_out, float *__restrict__ qrows,
                         const int *__restrict__ vhor_arr, const float *__restrict__ object_disparity_range,
@@ -1048,7 +1061,6 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__
   c.dm1f = (float)(p.max_dis - 1);
   c.lut_stride4 = (unsigned)p.lut_stride * 4u;
   c.epsilon = p.epsilon;
-  const uint32_t *rec = records + (size_t)gcol * kRecWords * Hp;
   const uint32_t *recb = records_b + (size_t)gcol * Hp * kRecBWords;
   const unsigned long long lut_addr = lut_column_address((unsigned long long)object_lut, (size_t)gcol, p.lut_cols,
                                                          (size_t)p.max_dis * p.lut_stride * 4);
@@ -1103,16 +1115,14 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__
     const bool row_ok = vT < H;
     const int vTc = row_ok ? vT : H - 1;
     uint32_t A[kRecWords];
-#pragma unroll
-    for (int w = 0; w < kRecWords; w++) A[w] = __ldg(rec + (size_t)w * Hp + vTc + 1);
+    load_a_side(A, recb, vTc + 1);
     const unsigned ca = lutb + 4u * (unsigned)vTc;
     // bound ingredients of this tile (see dp_unary_pruned_kernel)
     const int vTmaxc = min(t * kChunk + kChunk - 1, H - 1);
     float sq = 0.0f;
     if (lane == 0) {
-      const uint32_t *r1 = rec + vTmaxc + 1;
-      sq = fadd(fadd(f_(__ldg(r1 + (size_t)kRecMx2Hi * Hp)), f_(__ldg(r1 + (size_t)kRecMx2Lo * Hp))),
-                fadd(f_(__ldg(r1 + (size_t)kRecMy2Hi * Hp)), f_(__ldg(r1 + (size_t)kRecMy2Lo * Hp))));
+      sq = fadd(fadd(f_(rec_word(recb, vTmaxc + 1, kRecMx2Hi)), f_(rec_word(recb, vTmaxc + 1, kRecMx2Lo))),
+                fadd(f_(rec_word(recb, vTmaxc + 1, kRecMy2Hi)), f_(rec_word(recb, vTmaxc + 1, kRecMy2Lo))));
     }
     sq = __shfl_sync(full_mask, sq, 0);
     const float ic_lb = -fmul(fmul(sq, c.iw), 1.9073486328125e-06f);
@@ -1214,8 +1224,8 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__
       const uint32_t *bchunk = stage_w;
       float *qs_slot = q_w;  // Q[vb0 .. vb0+31] as they become known
       // prefix values at the start row of the best object segment so far (previous_mean needs them)
-      float lo_d = f_(__ldg(rec + (size_t)kRecDisp * Hp + best.vb_o));
-      float lo_v = f_(__ldg(rec + (size_t)kRecValid * Hp + best.vb_o));
+      float lo_d = f_(rec_word(recb, best.vb_o, kRecDisp));
+      float lo_v = f_(rec_word(recb, best.vb_o, kRecValid));
       if (j > 0) {
         if (lane < kDynWords) qs_slot[lane] = qnext[lane];
         __syncwarp();
@@ -1282,8 +1292,8 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records, const uint32_t *__
       // Q[vb0 + 32] for the next diagonal (row vb0 + 31 is final now)
       if (vb0 + kChunk < H) {
         const int vB = vb0 + kChunk;
-        const RowInfo q = finish_row(vB, 31, f_(__ldg(rec + (size_t)kRecDisp * Hp + vB)),
-                                     f_(__ldg(rec + (size_t)kRecValid * Hp + vB)));
+        const RowInfo q = finish_row(vB, 31, f_(rec_word(recb, vB, kRecDisp)),
+                                     f_(rec_word(recb, vB, kRecValid)));
         if (lane == 0) {
           store_row_info(qnext, q);
           pm_col[vB] = q.pm;
@@ -1316,7 +1326,7 @@ static void launch_dp_warps(const KParams &p, const BatchBuffers &b, int ncolumn
   static SmemOptIn optin;
   opt_in_smem(dp_kernel<PAIRWISE, HAS_INVALID, WARPS>, optin);
   dp_kernel<PAIRWISE, HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
-      b.records, b.records_b, b.object_lut, b.stat, b.pm, b.vhor, b.object_disparity_range, b.inverse_height, b.dp, p);
+      b.records_b, b.object_lut, b.stat, b.pm, b.vhor, b.object_disparity_range, b.inverse_height, b.dp, p);
 }
 
 template <bool PAIRWISE, bool HAS_INVALID>
@@ -1337,7 +1347,7 @@ static void launch_unary_pruned_warps(const KParams &p, const BatchBuffers &b, i
   static SmemOptIn optin;
   opt_in_smem(dp_unary_pruned_kernel<HAS_INVALID, WARPS>, optin);
   dp_unary_pruned_kernel<HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
-      b.records, b.records_b, b.object_lut, b.ground, b.vhor, b.inverse_height, b.dp, b.dp_units, b.col_flags, p);
+      b.records_b, b.object_lut, b.ground, b.vhor, b.inverse_height, b.dp, b.dp_units, b.col_flags, p);
 }
 
 template <bool HAS_INVALID>
@@ -1358,7 +1368,7 @@ static void launch_pairwise_walk_warps(const KParams &p, const BatchBuffers &b, 
   static SmemOptIn optin;
   opt_in_smem(dp_pairwise_walk_kernel<HAS_INVALID, WARPS>, optin);
   dp_pairwise_walk_kernel<HAS_INVALID, WARPS><<<ncolumns, WARPS * 32, smem, s>>>(
-      b.records, b.records_b, b.object_lut, b.stat, b.ground, b.pm, b.qrows, b.vhor, b.object_disparity_range, b.dp,
+      b.records_b, b.object_lut, b.stat, b.ground, b.pm, b.qrows, b.vhor, b.object_disparity_range, b.dp,
       b.dp_units, b.col_flags, p);
 }
 

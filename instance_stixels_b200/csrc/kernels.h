@@ -21,8 +21,7 @@ struct BatchBuffers {
   float *stat = nullptr;               // [B][H][kStatWords] static transition records (pairwise)
   // intermediates
   float *joined = nullptr;             // [B][C][H]
-  uint32_t *records = nullptr;         // [B][C][kRecWords][rec_stride], word-major (common.cuh)
-  uint32_t *records_b = nullptr;       // [B][C][rec_stride][kRecBWords], row-major copy (common.cuh)
+  uint32_t *records_b = nullptr;       // [B][C][rec_stride][kRecBWords]: one 128-byte record per row (common.cuh)
   float *object_lut = nullptr;         // [B][C][D][lut_stride]
   float *pm = nullptr;                 // [B][C][H] previous_mean of row vB-1 (pairwise; backtracking re-derives priors)
   float *qrows = nullptr;              // [B][C][rec_stride][kDynWords] transition records Q[vB] (pairwise tile-major walk)

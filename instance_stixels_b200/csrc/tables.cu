@@ -163,8 +163,8 @@ struct TabSmem {
 __global__ void __launch_bounds__(kTabThreads, 3)
 column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict__ segmentation,
                      const float *__restrict__ ground, const int *__restrict__ vhor_arr,
-                     uint32_t *__restrict__ records, uint32_t *__restrict__ records_b,
-                     int *__restrict__ error_flag, int *__restrict__ col_flags, KParams p) {
+                     uint32_t *__restrict__ records_b, int *__restrict__ error_flag, int *__restrict__ col_flags,
+                     KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = p.rows, C = p.realcols;
   const int col = blockIdx.x, f = blockIdx.y;
@@ -189,17 +189,23 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   const float invalid = p.invalid_disparity;
   const int K = p.n_classes;  // 19; channel K = y offsets, K+1 = x offsets
 
-  // ---- 1/8-resolution channels (squared offsets like :411-416) ----
+  // ---- 1/8-resolution channels: the 19 classes, and as a 20th the sum of the two squared offsets (:411-416; the
+  //      DP only ever uses the sum, ComputeNonInstanceOffsetCost :62-70) ----
   bool negative_class_value = false;
-  for (int i = tid; i < 21 * nq; i += kTabThreads) {
+  for (int i = tid; i < 20 * nq; i += kTabThreads) {
     const int c = i / nq, q = i - c * nq;
     int v = 0;
-    if (c < p.n_channels && q < p.hs2) v = seg_col[(size_t)c * p.hs2 + q];
-    if (c >= K) {
-      v = v * v;
-      negative_class_value |= v < 0 || v > (1 << 19);   // two channels x 1032 rows stay below 2^31
+    if (c < K) {
+      if (c < p.n_channels && q < p.hs2) v = seg_col[(size_t)c * p.hs2 + q];
+      negative_class_value |= v < 0 || v > (1 << 20);   // the int32 prefix sums over <= 1032 rows cannot wrap
     } else {
-      negative_class_value |= v < 0 || v > (1 << 20);   // likewise: the int32 prefix sums cannot wrap
+      int oy = 0, ox = 0;
+      if (q < p.hs2 && K < p.n_channels) oy = seg_col[(size_t)K * p.hs2 + q];
+      if (q < p.hs2 && K + 1 < p.n_channels) ox = seg_col[(size_t)(K + 1) * p.hs2 + q];
+      oy = oy * oy;
+      ox = ox * ox;
+      negative_class_value |= oy < 0 || oy > (1 << 19) || ox < 0 || ox > (1 << 19);   // their sum: likewise
+      v = oy + ox;
     }
     seg_s[c * segld + q] = v;
   }
@@ -259,55 +265,50 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   } else {
     exact_prefix_warp<long long>(e_i64 + (warp - 4) * L.Hp, H, ps_i64 + (warp - 4) * L.Hp);
   }
-  for (int c = warp; c < 21; c += kTabThreads / 32) exact_prefix_warp<int>(seg_s + c * segld, nq, seg_ps + c * segld);
+  for (int c = warp; c < 20; c += kTabThreads / 32) exact_prefix_warp<int>(seg_s + c * segld, nq, seg_ps + c * segld);
   __syncthreads();
 
-  // ---- records, v in [0, H], in both layouts (common.cuh): word-major for the A side of the DP
-  //      (coalesced over v) and row-major 128-byte rows for the bulk-copied B side ----
-  uint32_t *rec_col = records + ((size_t)f * C + col) * (size_t)kRecWords * p.rec_stride;
+  // ---- records, v in [0, H]: one 128-byte row per v (common.cuh).  Eight lanes share a row, lane g writes words
+  //      4g .. 4g+3 as one 16-byte store, so a warp instruction stores 512 contiguous bytes (four full lines).
+  //      Groups 0-4 are the 20 integer words (one formula), 5-7 the float words. ----
   uint4 *recb_col = reinterpret_cast<uint4 *>(records_b + ((size_t)f * C + col) * (size_t)p.rec_stride * kRecBWords);
   bool out_of_range = false;
-  for (int v = tid; v <= H; v += kTabThreads) {
-    const int q = v >> 3, r = v & 7;
-    // instance-mean sums as exactly representable floats (see common.cuh)
-    const long long smx = ps_i64[0 * L.Hp + v], smy = ps_i64[1 * L.Hp + v];
-    const long long smx2 = ps_i64[2 * L.Hp + v], smy2 = ps_i64[3 * L.Hp + v];
-    const long long lim1 = 1ll << 24, lim2 = 1ll << (24 + kSqSplitBits);
-    out_of_range |= smx <= -lim1 || smx >= lim1 || smy <= -lim1 || smy >= lim1 || smx2 >= lim2 || smy2 >= lim2;
-    const long long lomask = (1ll << kSqSplitBits) - 1;
-    // word k of the record of row v (k is a compile-time constant after unrolling)
-    auto word = [&](int k) -> uint32_t {
-      if (k < 19)  // P_c(v) = 8*ps[q] + seg[q]*r  (Cityscapes.h:28-42)
-        return (uint32_t)(seg_ps[k * segld + q] * kDownsample + seg_s[k * segld + q] * r);
-      switch (k) {
-        case kRecOff:
-          return (uint32_t)((seg_ps[19 * segld + q] + seg_ps[20 * segld + q]) * kDownsample +
-                            (seg_s[19 * segld + q] + seg_s[20 * segld + q]) * r);
-        case kRecMx: return __float_as_uint((float)smx);
-        case kRecMy: return __float_as_uint((float)smy);
-        case kRecMx2Hi: return __float_as_uint((float)(smx2 & ~lomask));
-        case kRecMx2Lo: return __float_as_uint((float)(smx2 & lomask));
-        case kRecMy2Hi: return __float_as_uint((float)(smy2 & ~lomask));
-        case kRecMy2Lo: return __float_as_uint((float)(smy2 & lomask));
-        case kRecDisp: return __float_as_uint(ps_f[0][v]);
-        case kRecValid: return __float_as_uint(ps_f[1][v]);
-        case kRecGround: return __float_as_uint(ps_f[2][v]);
-        case kRecSky: return __float_as_uint(ps_f[3][v]);
-        default: return 0u;
-      }
-    };
-    // four words at a time: four word-major stores (coalesced over v) and one 16-byte store of the row-major copy,
-    // so that only four words are live at once (the kernel runs three CTAs per SM)
-#pragma unroll
-    for (int g = 0; g < kRecBWords / 4; g++) {
-      uint32_t w4[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) w4[u] = word(4 * g + u);
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (4 * g + u < kRecWords) rec_col[(size_t)(4 * g + u) * p.rec_stride + v] = w4[u];
-      recb_col[(size_t)v * (kRecBWords / 4) + g] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+  const long long lim1 = 1ll << 24, lim2 = 1ll << (24 + kSqSplitBits);
+  const long long lomask = (1ll << kSqSplitBits) - 1;
+  for (int idx = tid; idx < (H + 1) * (kRecBWords / 4); idx += kTabThreads) {
+    const int v = idx >> 3, g = idx & 7;
+    uint4 w;
+    if (g < 5) {
+      // P_c(v) = 8*ps[q] + seg[q]*r  (Cityscapes.h:28-42); word 19 = the same for the summed squared offsets
+      const int q = v >> 3, r = v & 7;
+      const int *ps = seg_ps + (4 * g) * segld + q, *sg = seg_s + (4 * g) * segld + q;
+      w.x = (uint32_t)(ps[0] * kDownsample + sg[0] * r);
+      w.y = (uint32_t)(ps[segld] * kDownsample + sg[segld] * r);
+      w.z = (uint32_t)(ps[2 * segld] * kDownsample + sg[2 * segld] * r);
+      w.w = (uint32_t)(ps[3 * segld] * kDownsample + sg[3 * segld] * r);
+    } else if (g == 5) {
+      // instance-mean sums as exactly representable floats (see common.cuh): words 20 .. 23
+      const long long smx = ps_i64[0 * L.Hp + v], smy = ps_i64[1 * L.Hp + v], smx2 = ps_i64[2 * L.Hp + v];
+      out_of_range |= smx <= -lim1 || smx >= lim1 || smy <= -lim1 || smy >= lim1 || smx2 >= lim2;
+      w.x = __float_as_uint((float)smx);
+      w.y = __float_as_uint((float)smy);
+      w.z = __float_as_uint((float)(smx2 & ~lomask));
+      w.w = __float_as_uint((float)(smx2 & lomask));
+    } else if (g == 6) {
+      // words 24 .. 27
+      const long long smy2 = ps_i64[3 * L.Hp + v];
+      out_of_range |= smy2 >= lim2;
+      w.x = __float_as_uint((float)(smy2 & ~lomask));
+      w.y = __float_as_uint((float)(smy2 & lomask));
+      w.z = __float_as_uint(ps_f[0][v]);
+      w.w = __float_as_uint(ps_f[1][v]);
+    } else {
+      // words 28 .. 31
+      w.x = __float_as_uint(ps_f[2][v]);
+      w.y = __float_as_uint(ps_f[3][v]);
+      w.z = w.w = 0u;
     }
+    recb_col[idx] = w;
   }
   if (out_of_range) atomicOr(error_flag + f, kErrOffsetRange);
   (void)lane;
@@ -398,8 +399,8 @@ void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, 
   const size_t smem = tab_smem_bytes(p);
   static SmemOptIn optin;
   opt_in_smem(column_tables_kernel, optin);
-  column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.records,
-                                                        b.records_b, b.error_flag, b.col_flags, p);
+  column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.records_b,
+                                                        b.error_flag, b.col_flags, p);
   dim3 lgrid(p.realcols, (p.max_dis + 32 * kLutWarps - 1) / (32 * kLutWarps), nframes);
   object_lut_kernel<<<lgrid, kLutThreads, 0, s>>>(b.joined, b.obj_cost_lut_t, b.object_lut, p);
   g_launch_count += 2;

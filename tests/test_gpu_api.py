@@ -148,7 +148,8 @@ def test_packed_results_equal_the_padded_arrays(budget, monkeypatch):
         assert parity.same_used_sections(data.sections, sec[f]), f
         assert np.array_equal(st.instance_records().view(np.uint8), inst[offs[f]:offs[f + 1]].view(np.uint8))
     # device batch + fetch
-    st.ComputeBatchDevice(True, n, torch.from_numpy(disp).cuda().data_ptr(), torch.from_numpy(seg).cuda().data_ptr(), roads)
+    d_disp, d_seg = torch.from_numpy(disp).cuda(), torch.from_numpy(seg).cuda()    # kept alive until the fetch
+    st.ComputeBatchDevice(True, n, d_disp.data_ptr(), d_seg.data_ptr(), roads)
     st.Synchronize()
     sec_d, inst_d, offs_d = st.FetchBatchResults(n)
     assert all(parity.same_used_sections(sec[f], sec_d[f]) for f in range(n))

@@ -1,0 +1,39 @@
+"""Developer probe (GPU box): one pairwise batch through the float and the narrow host entry points, for an ncu
+launch list / a quick A-B of the two paths."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from instance_stixels_b200 import api, synth
+
+B = int(os.environ.get("PROBE_B", "64"))
+pre = synth.preset("pairwise", 1024, 2048, 8)
+st = api.make_stixels(pre, max_batch=B)
+disp, seg, roads = synth.make_batch(min(B, 16), rows=1024, cols=2048)
+reps = B // len(roads)
+disp, seg, roads = np.concatenate([disp] * reps), np.concatenate([seg] * reps), roads * reps
+h_disp, h_seg = torch.from_numpy(disp).pin_memory(), torch.from_numpy(seg).pin_memory()
+d16 = torch.from_numpy(np.rint(disp * 256.0).astype(np.uint16)).pin_memory()
+s16 = torch.from_numpy(np.ascontiguousarray(seg[..., :128]).astype(np.int16)).pin_memory()
+C_ = st.GetRealCols()
+out = [torch.empty((B, C_, 200, 32), dtype=torch.uint8).pin_memory().numpy().view(api.L.SECTION_DTYPE).reshape(B, C_, 200) for _ in range(2)]
+for kind in ("float", "u16", "float", "u16"):
+    def submit(i):
+        if kind == "u16":
+            st.SubmitBatchU16(True, d16.numpy(), 1.0 / 256.0, s16.numpy(), roads, out[i & 1])
+        else:
+            st.SubmitBatch(True, h_disp.numpy(), h_seg.numpy(), roads, out[i & 1])
+    submit(0); st.WaitBatch()
+    torch.cuda.synchronize()
+    n = int(os.environ.get("PROBE_STEPS", "6"))
+    t0 = time.perf_counter()
+    for i in range(n):
+        submit(i)
+        if i:
+            st.WaitBatch()
+    st.WaitBatch()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(kind, "%.0f frames/s" % (B * n / dt), flush=True)
+st.Finish()
