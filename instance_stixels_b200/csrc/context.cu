@@ -107,6 +107,8 @@ struct isx_context {
   int batch_n[2] = {0, 0};                            // frames of the batch in flight with that parity, 0 = none
   int batch_set[2] = {0, 0};                          // its result set
   isx_section *batch_sections[2] = {nullptr, nullptr};  // the caller's padded array the wait expands into
+  bool batch_direct[2] = {false, false};                // ... or that the device has already filled (mapped memory)
+  isx_section *direct_sections = nullptr;               // device address of the caller's array for the batch being enqueued
   unsigned long long submitted = 0, waited = 0;       // tickets: batches [waited, submitted) are in flight
   unsigned long long dp_units_pairwise = 0;           // ... of which in pairwise mode (never pruned)
   unsigned long long dp_units_total = 0;              // 32 x 32-cell units of all DP launches so far
@@ -308,6 +310,7 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
     a.err = cs.err; a.col_offset = b.pack_offset;
     a.inst_out = R.d_inst + (size_t)first * c->inst_cap; a.inst_count_out = R.d_inst_count + first;
     a.inst_cap = c->inst_cap; a.cursors = R.d_cursors;
+    a.h_padded = c->direct_sections ? c->direct_sections + (size_t)first * C * kMaxSections : nullptr;
     a.h_sections = R.m_sections; a.h_sections_cap = R.sections_cap;
     a.h_inst = R.m_inst; a.h_inst_cap = R.inst_cap;
     a.h_counts = R.m_counts + (size_t)first * C; a.h_frames = R.m_frames + first;
@@ -321,6 +324,22 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
   c->last_pairwise = pairwise;
   c->last_set = slot;
   return ISX_OK;
+}
+
+// If the caller's Section array is pinned and mapped (cudaHostAlloc / cudaHostRegister / torch pin_memory), the
+// device writes the padded layout straight into it: returns the device address of `sections`, or null for
+// pageable memory (then the packed arrays are expanded on the host).  ISX_NO_DIRECT=1 forces the packed path.
+static isx_section *device_view_of(isx_section *sections) {
+  if (!sections) return nullptr;
+  if (const char *e = std::getenv("ISX_NO_DIRECT"))
+    if (std::atoi(e) != 0) return nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, sections) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
+  return static_cast<isx_section *>(attr.devicePointer);
 }
 
 // Every batch starts its packed result arrays from the front (ordered on the emission stream behind the packing of
@@ -744,7 +763,8 @@ static int no_batches_in_flight(isx_handle h);
 // waited for the emission stream); only a frame that did not fit the packed arrays costs a device -> host copy.
 // Returns the first per-frame error AFTER delivering what there is.
 static int deliver(isx_handle h, isx_context::ResultSet &R, int n, isx_section *sections, isx_instance *instances,
-                   int instances_capacity, int32_t *instance_offsets) {
+                   int instances_capacity, int32_t *instance_offsets, bool direct = false) {
+  if (direct) sections = nullptr;   // the device has written the caller's array itself
   const size_t C = h->kp.realcols;
   int rc = ISX_OK;
   int total = 0;
@@ -815,13 +835,17 @@ int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_met
   // slot 0's pinned road-table staging may still be the source of a copy a device batch has queued
   ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[0]));
   if (int rc = begin_batch(h)) return rc;
-  if (int rc = enqueue_chunk(h, pairwise != 0, 0, 1, h->d_single_disp, seg, &h->single_road, 0)) return rc;
+  h->direct_sections = device_view_of(sections);
+  const bool direct = h->direct_sections != nullptr;
+  const int erc = enqueue_chunk(h, pairwise != 0, 0, 1, h->d_single_disp, seg, &h->single_road, 0);
+  h->direct_sections = nullptr;
+  if (erc) return erc;
   ISX_TRY(h, cudaEventRecord(h->ev_in_free[0], h->s_compute));
   if (int rc = join_emit_stream(h)) return rc;
   h->last_batch = 1;
   h->last_roads.assign(1, h->single_road);
   if (int rc = wait_last_emission(h)) return rc;
-  if (int rc = deliver(h, h->rs[h->cur], 1, sections, nullptr, 0, nullptr)) return rc;
+  if (int rc = deliver(h, h->rs[h->cur], 1, sections, nullptr, 0, nullptr, direct)) return rc;
   if (meta) {
     meta->rows = h->kp.rows; meta->cols = h->kp.cols; meta->realcols = h->kp.realcols;
     meta->max_sections = kMaxSections; meta->max_dis = h->kp.max_dis; meta->column_step = h->kp.column_step;
@@ -1000,10 +1024,14 @@ static int compute_batch_host(isx_handle h, int pairwise, int n, const HostInput
   if (int rc = no_batches_in_flight(h)) return rc;
   if (n < 1 || n > h->max_batch) return fail(h, ISX_ERR_CAPACITY, "batch size exceeds isx_initialize(max_batch)");
   if (!roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
-  if (int rc = enqueue_host_batch(h, pairwise, n, in, roads)) return rc;
+  h->direct_sections = device_view_of(sections);
+  const bool direct = h->direct_sections != nullptr;
+  const int erc = enqueue_host_batch(h, pairwise, n, in, roads);
+  h->direct_sections = nullptr;
+  if (erc) return erc;
   if (int rc = join_emit_stream(h)) return rc;
   if (int rc = wait_last_emission(h)) return rc;
-  return deliver(h, h->rs[h->cur], n, sections, instances, instances_capacity, instance_offsets);
+  return deliver(h, h->rs[h->cur], n, sections, instances, instances_capacity, instance_offsets, direct);
 }
 
 int isx_compute_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
@@ -1041,8 +1069,13 @@ static int submit_batch_host(isx_handle h, int pairwise, int n, const HostInputs
   for (int i = 0; i < 2; i++)
     if (!h->ev_batch_done[i]) ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_batch_done[i], cudaEventDisableTiming));
   h->cur ^= 1;
-  if (int rc = enqueue_host_batch(h, pairwise, n, in, roads)) return rc;
+  h->direct_sections = device_view_of(sections);
+  const bool direct = h->direct_sections != nullptr;
+  const int erc = enqueue_host_batch(h, pairwise, n, in, roads);
+  h->direct_sections = nullptr;
+  if (erc) return erc;
   const int par = (int)(h->submitted & 1);
+  h->batch_direct[par] = direct;
   ISX_TRY(h, cudaEventRecord(h->ev_batch_done[par], h->s_emit));  // behind the packing of the last chunk
   h->batch_n[par] = n;
   h->batch_set[par] = h->cur;
@@ -1087,7 +1120,7 @@ int isx_wait_batch_host(isx_handle h, isx_instance *instances, int instances_cap
   const int n = h->batch_n[par];
   h->batch_n[par] = 0;
   return deliver(h, h->rs[h->batch_set[par]], n, h->batch_sections[par], instances, instances_capacity,
-                 instance_offsets);
+                 instance_offsets, h->batch_direct[par]);
 }
 
 int isx_wait_batch_packed(isx_handle h, const isx_section **sections, const int32_t **counts,

@@ -329,7 +329,15 @@ pack_results_kernel(PackArgs a, KParams p) {
   const bool sec_fits = sec_base + n_sec <= a.h_sections_cap;
   const bool inst_fits = inst_base + n_inst <= a.h_inst_cap;
   // ---- sections: one warp per column, 32 B per lane (two 16-byte stores; a warp writes up to 1 KB back to back) ----
-  if (sec_fits) {
+  if (a.h_padded) {
+    // the caller's padded array is device-visible: no packed copy, no expansion on the host
+    for (int col = warp; col < C; col += kPackThreads / 32) {
+      const int n = ns[col];
+      const uint4 *src = reinterpret_cast<const uint4 *>(fs + (size_t)col * kMaxSections);
+      uint4 *dst = reinterpret_cast<uint4 *>(a.h_padded + ((size_t)f * C + col) * kMaxSections);
+      for (int j = lane; j < 2 * (n + 1); j += 32) dst[j] = src[j];   // n stixels + the type == -1 terminator
+    }
+  } else if (sec_fits) {
     for (int col = warp; col < C; col += kPackThreads / 32) {
       const int n = ns[col];
       const uint4 *src = reinterpret_cast<const uint4 *>(fs + (size_t)col * kMaxSections);
@@ -357,12 +365,12 @@ pack_results_kernel(PackArgs a, KParams p) {
   if (tid == 0) {
     a.inst_count_out[f] = n_inst;
     isx_packed_frame d;
-    d.section_offset = sec_base;
+    d.section_offset = a.h_padded ? -1 : sec_base;
     d.section_count = n_sec;
     d.instance_offset = inst_base;
     d.instance_count = n_inst;
     d.error = a.err[f];
-    d.overflow = (sec_fits ? 0 : 1) | (inst_fits ? 0 : 2);
+    d.overflow = ((sec_fits || a.h_padded) ? 0 : 1) | (inst_fits ? 0 : 2);
     d.reserved[0] = d.reserved[1] = 0;
     a.h_frames[f] = d;
   }

@@ -82,6 +82,9 @@ struct PackArgs {
   int h_sections_cap;
   isx_instance *h_inst;          // packed instance records of the whole batch
   int h_inst_cap;
+  isx_section *h_padded;         // the caller's own [n][C][200] array when it is pinned and mapped (else null): the
+                                 // used Sections and the terminator of every column are written straight into it
+                                 // and the packed copy is skipped
   int *h_counts;                 // [n][C] stixels per column
   isx_packed_frame *h_frames;    // [n]
 };

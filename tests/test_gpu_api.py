@@ -141,11 +141,24 @@ def test_packed_results_equal_the_padded_arrays(budget, monkeypatch):
     disp, seg, roads = synth.make_batch(n, start=60, rows=rows, cols=cols)
     st = api.make_stixels(pre, max_batch=8)
     sec, inst, offs = st.ComputeBatch(True, disp, seg, roads)
-    # frame by frame through the reference call sequence
+    # a pinned (mapped) Section array is filled by the device itself: no packed copy, no expansion on the host
+    pinned = torch.empty((n, st.GetRealCols(), 200, 32), dtype=torch.uint8).pin_memory()
+    pinned.fill_(0x5A)
+    sec_pin = pinned.numpy().view(api.L.SECTION_DTYPE).reshape(n, st.GetRealCols(), 200)
+    sec_p, inst_p, offs_p = st.ComputeBatch(True, disp, seg, roads, sections_out=sec_pin)
+    assert all(parity.same_used_sections(sec[f], sec_p[f]) for f in range(n))
+    assert np.array_equal(inst.view(np.uint8), inst_p.view(np.uint8)) and np.array_equal(offs, offs_p)
+    pinned.fill_(0x5A)
+    st.SubmitBatch(True, disp, seg, roads, sec_pin)
+    sec_p2, inst_p2, _ = st.WaitBatch()
+    assert all(parity.same_used_sections(sec[f], sec_p2[f]) for f in range(n))
+    # frame by frame through the reference call sequence (pageable and pinned result arrays)
     for f in range(n):
         st.SetDisparityImage(disp[f]); st.SetSegmentation(seg[f]); st.SetRoadParameters(**roads[f])
         data = st.Compute(True)
         assert parity.same_used_sections(data.sections, sec[f]), f
+        data_p = st.Compute(True, sections_out=sec_pin[0])
+        assert parity.same_used_sections(data_p.sections, sec[f]), f
         assert np.array_equal(st.instance_records().view(np.uint8), inst[offs[f]:offs[f + 1]].view(np.uint8))
     # device batch + fetch
     d_disp, d_seg = torch.from_numpy(disp).cuda(), torch.from_numpy(seg).cuda()    # kept alive until the fetch

@@ -54,7 +54,7 @@ def _fuzz_case(rng, mode):
     pre["disparity_weight"] = float(10.0 ** rng.uniform(-4.0, 0.5))
     pre["invalid_disparity"] = float(rng.choice([0.0, -1.0]))
     pre["max_dis"] = int(rng.choice([64, 128]))
-    vhor = int(rng.integers(0, rows - 3))             # anywhere, including the top border
+    vhor = int(rng.integers(0, rows - 12))            # anywhere, including the top border
     fr = synth.make_frame(int(rng.integers(0, 1000)), rows=rows, cols=cols, column_step=step, max_dis=pre["max_dis"],
                           vhor=vhor)
     seg = fr.segmentation.copy()

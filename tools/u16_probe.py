@@ -18,10 +18,14 @@ d16 = torch.from_numpy(np.rint(disp * 256.0).astype(np.uint16)).pin_memory()
 s16 = torch.from_numpy(np.ascontiguousarray(seg[..., :128]).astype(np.int16)).pin_memory()
 C_ = st.GetRealCols()
 out = [torch.empty((B, C_, 200, 32), dtype=torch.uint8).pin_memory().numpy().view(api.L.SECTION_DTYPE).reshape(B, C_, 200) for _ in range(2)]
-for kind in ("float", "u16", "float", "u16"):
+h_deq = torch.from_numpy((d16.numpy().astype(np.float32) / np.float32(256.0)).astype(np.float32)).pin_memory()
+st.set_profiling(True)
+for kind in ("float", "float_dequantized", "u16", "float", "u16"):
     def submit(i):
         if kind == "u16":
             st.SubmitBatchU16(True, d16.numpy(), 1.0 / 256.0, s16.numpy(), roads, out[i & 1])
+        elif kind == "float_dequantized":
+            st.SubmitBatch(True, h_deq.numpy(), h_seg.numpy(), roads, out[i & 1])
         else:
             st.SubmitBatch(True, h_disp.numpy(), h_seg.numpy(), roads, out[i & 1])
     submit(0); st.WaitBatch()
@@ -35,5 +39,6 @@ for kind in ("float", "u16", "float", "u16"):
     st.WaitBatch()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    print(kind, "%.0f frames/s" % (B * n / dt), flush=True)
+    stages = st.stage_times(reset=True)
+    print(kind, "%.0f frames/s" % (B * n / dt), {k: round(v[0] / max(v[1], 1), 2) for k, v in stages.items()}, st.dp_units(), flush=True)
 st.Finish()
