@@ -33,6 +33,7 @@
 #include "RoadEstimation.h"  // RoadEstimation (drop-in)
 #include "Stixels.hpp"       // Stixels (drop-in)
 #include "configuration.h"   // pixel_t
+#include "h5_reader.h"
 #include "loaders.h"
 
 namespace {
@@ -41,16 +42,30 @@ struct Options {
     std::string dataset;
     bool pairwise = false;
     StixelConfig config;  // everything that does not depend on the frame
+    // extensions (not in the reference's CLI): --batch B frames per batched call, --gpus G GPUs of this box
+    int batch = 1, gpus = 1;
 };
 
 bool parse_options(int argc, char** argv, Options* o) {
+    // optional flags behind the reference's positional arguments
+    std::vector<char*> pos;
+    for (int i = 0; i < argc; i++) {
+        const std::string a(argv[i]);
+        if ((a == "--batch" || a == "--gpus") && i + 1 < argc) {
+            (a == "--batch" ? o->batch : o->gpus) = std::max(1, std::atoi(argv[++i]));
+            continue;
+        }
+        pos.push_back(argv[i]);
+    }
+    argc = (int)pos.size();
+    argv = pos.data();
     if (argc < 11) {
         std::cerr << "Usage: stixels dir max_disparity segmentation_weight instance_weight disparity_weight "
                      "pairwise stixel_width eps min_pts size_filter\n";
         return false;
     }
     if (argc > 11 && std::atoi(argv[11]) == 1) {
-        std::cerr << "The TensorRT path is not part of this build: provide <base>_probs.npy files.\n";
+        std::cerr << "The TensorRT path is not part of this build: provide <base>_probs.h5 (or .npy) files.\n";
         return false;
     }
     o->dataset = argv[1];
@@ -198,6 +213,23 @@ private:
     bool ready_ = false;
 };
 
+// The segmentation tensor of a frame: the int32 dataset "nlogprobs" of <base>_probs.h5 like the reference
+// (H5Segmentation.cpp:25-49, read without libhdf5 by apps/h5_reader.h), or the same array as <base>_probs.npy.
+isx_apps::NpyInt32 load_segmentation(const std::string& probs) {
+    if (exists(probs + ".h5")) {
+        std::cout << "Opening file " << probs << ".h5\n";
+        isx_apps::H5Int32 h = isx_apps::load_h5_int32(probs + ".h5", "nlogprobs");
+        isx_apps::NpyInt32 out;
+        out.shape = h.shape;
+        out.data.swap(h.data);
+        std::cout << "H5Segmentation shape = (" << (out.shape.empty() ? 0 : out.shape[0]);
+        for (size_t i = 1; i < out.shape.size(); i++) std::cout << ", " << out.shape[i];
+        std::cout << ")\n";
+        return out;
+    }
+    return isx_apps::load_npy_int32(probs + ".npy");
+}
+
 // [cols / stixel_width][21][2^ceil(log2(rows / 8 + 1))]; the reference checks cols / 8 (:363), width 4 needs
 // a tensor at cols / 4 columns.
 bool segmentation_fits(const isx_apps::NpyInt32& seg, int rows, int cols, int column_step) {
@@ -216,11 +248,138 @@ bool segmentation_fits(const isx_apps::NpyInt32& seg, int rows, int cols, int co
     return true;
 }
 
+// ---- extension: --batch B / --gpus G ----
+// The same dataset through the batched entry points: all frames are loaded, the road is estimated per frame, and
+// runs of frames with one geometry go through a StixelsPool (one context + worker thread per GPU, sub-batches of B
+// frames, two in flight) from pinned host buffers.  The .stixels files are the same bytes as the one-frame loop
+// writes; the timed region is the pool call (host buffers in -> Sections and instance maps out), after one
+// discarded warm-up call like the reference's first frame.
+struct LoadedFrame {
+    std::string base;
+    int rows = 0, cols = 0;
+    isx_apps::Camera cam;
+    Stixels::Road road{};
+    size_t slot = 0;  // index inside its group's pinned buffers
+};
+
+template <typename T>
+struct Pinned {
+    T* p = nullptr;
+    size_t n = 0;
+    explicit Pinned(size_t count) : n(count) {
+        p = static_cast<T*>(isx_host_alloc(count * sizeof(T)));
+        if (!p) throw std::runtime_error("out of pinned host memory");
+    }
+    ~Pinned() { isx_host_free(p); }
+    Pinned(const Pinned&) = delete;
+    Pinned& operator=(const Pinned&) = delete;
+};
+
+int run_batched(const Options& opt) {
+    const std::vector<std::string> bases = list_frames(opt.dataset + "/disparities");
+    double total_ms = 0;
+    size_t total_frames = 0;
+    size_t i = 0;
+    RoadEstimation road;
+    while (i < bases.size()) {
+        // ---- one group: consecutive frames with the geometry of the first usable one ----
+        std::vector<LoadedFrame> group;
+        std::vector<std::vector<pixel_t>> disp;
+        std::vector<std::vector<int32_t>> seg;
+        for (; i < bases.size(); i++) {
+            const std::string& base = bases[i];
+            std::cout << base << "_disparity.png" << std::endl;
+            const std::string camera_file = opt.dataset + "/camera/" + base + "_camera.json";
+            try {
+                Disparity d = load_disparity(opt.dataset + "/disparities/" + base + "_disparity.png", opt.config.max_dis);
+                const isx_apps::Camera cam = isx_apps::load_camera(camera_file);
+                if (!group.empty()) {
+                    const LoadedFrame& g = group.front();
+                    if (g.rows != d.rows || g.cols != d.cols || g.cam.baseline != cam.baseline || g.cam.focal != cam.focal ||
+                        g.cam.center_y != cam.center_y)
+                        break;  // next group starts here
+                }
+                isx_apps::NpyInt32 s = load_segmentation(opt.dataset + "/probs/" + base + "_probs");
+                if (!segmentation_fits(s, d.rows, d.cols, opt.config.column_step)) continue;
+                if (group.empty()) {
+                    if (road.IsInitialized()) road.Finish();
+                    road.Initialize(cam.center_y, cam.baseline, cam.focal, d.rows, d.cols, opt.config.max_dis);
+                }
+                if (!road.Compute(d.values)) {
+                    std::printf("Road estimation failed.\n");
+                    continue;
+                }
+                LoadedFrame f;
+                f.base = base;
+                f.rows = d.rows;
+                f.cols = d.cols;
+                f.cam = cam;
+                f.road = Stixels::Road{road.GetHorizonPoint(), road.GetPitch(), road.GetCameraHeight(), road.GetSlope()};
+                if (f.road.camera_tilt == 0 && f.road.camera_height == 0 && f.road.vhor == 0 && f.road.alpha_ground == 0) {
+                    std::printf("Invalid road estimation.\n");
+                    continue;
+                }
+                f.slot = group.size();
+                group.push_back(f);
+                disp.push_back(std::move(d.values));
+                seg.push_back(std::move(s.data));
+            } catch (const std::invalid_argument& err) {
+                std::cerr << err.what() << "\n";
+            }
+        }
+        if (group.empty()) continue;
+        const int n = (int)group.size();
+        StixelConfig cfg = opt.config;
+        cfg.rows = group[0].rows;
+        cfg.cols = group[0].cols;
+        cfg.baseline = group[0].cam.baseline;
+        cfg.focal = group[0].cam.focal;
+        cfg.camera_center_y = group[0].cam.center_y;
+        std::vector<int> devices;
+        for (int g = 0; g < opt.gpus; g++) devices.push_back(g);
+        StixelsPool pool(cfg, devices, opt.batch);
+        const size_t hw = disp[0].size(), se = seg[0].size();
+        Pinned<pixel_t> h_disp((size_t)n * hw);
+        Pinned<int32_t> h_seg((size_t)n * se);
+        std::vector<Stixels::Road> roads;
+        for (int f = 0; f < n; f++) {
+            std::copy(disp[(size_t)f].begin(), disp[(size_t)f].end(), h_disp.p + (size_t)f * hw);
+            std::copy(seg[(size_t)f].begin(), seg[(size_t)f].end(), h_seg.p + (size_t)f * se);
+            roads.push_back(group[(size_t)f].road);
+        }
+        std::vector<Section> sections;
+        std::vector<StixelsPool::InstanceMap> instances;
+        const int warm = std::min(n, opt.batch * opt.gpus);
+        pool.ComputeBatch(opt.pairwise, warm, h_disp.p, h_seg.p, roads.data(), sections, &instances);  // warm-up
+        const auto t0 = std::chrono::steady_clock::now();
+        pool.ComputeBatch(opt.pairwise, n, h_disp.p, h_seg.p, roads.data(), sections, &instances);
+        const auto t1 = std::chrono::steady_clock::now();
+        const double ms = (double)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count() * 1e-3;
+        std::cout << "Done. Time elapsed (s): " << ms * 1e-3 << " for " << n << " frames on " << pool.Size()
+                  << " GPU worker(s), sub-batches of " << opt.batch << "\n";
+        total_ms += ms;
+        total_frames += (size_t)n;
+        const size_t per = (size_t)pool.GetRealCols() * pool.GetMaxSections();
+        for (int f = 0; f < n; f++) {
+            const LoadedFrame& lf = group[(size_t)f];
+            Stixels::SaveStixels(sections.data() + (size_t)f * per, instances[(size_t)f], lf.road.alpha_ground,
+                                 lf.rows - 1 - lf.road.vhor, pool.GetRealCols(), pool.GetMaxSections(),
+                                 (opt.dataset + "/stixels/" + lf.base + ".stixels").c_str());
+        }
+        std::cout << "Finished.\n";
+    }
+    if (road.IsInitialized()) road.Finish();
+    const float mean = (float)(total_ms / (double)total_frames);
+    std::cout << "It took an average of " << mean << " milliseconds, " << 1000.0f / mean << " fps" << std::endl;
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char* argv[]) {
     Options opt;
     if (!parse_options(argc, argv, &opt)) return -1;
+    if (opt.batch > 1 || opt.gpus > 1) return run_batched(opt);
     Pipeline pipeline(opt);
     std::vector<double> frame_ms;
     bool warm = false;
@@ -235,10 +394,7 @@ int main(int argc, char* argv[]) {
             else std::cout << "Warning: Camera file " << camera_file
                            << " does not exist. Falling back to UEYE parameters!\n";
             pipeline.prepare(disparity.rows, disparity.cols, isx_apps::load_camera(camera_file));
-            if (!exists(probs + ".npy") && exists(probs + ".h5"))
-                throw std::invalid_argument("HDF5 is not available in this build: convert " + probs +
-                                            ".h5 with tools/h5_to_npy.py");
-            const isx_apps::NpyInt32 segmentation = isx_apps::load_npy_int32(probs + ".npy");
+            const isx_apps::NpyInt32 segmentation = load_segmentation(probs);
             if (!segmentation_fits(segmentation, disparity.rows, disparity.cols, opt.config.column_step)) continue;
             const double ms = pipeline.run(disparity, segmentation, opt.dataset + "/stixels/" + base + ".stixels");
             if (ms < 0) continue;

@@ -76,7 +76,7 @@ public:
     int GetRealCols() { return isx_real_cols(h_); }
     int GetMaxSections() { return isx_max_sections(h_); }
 
-    void SetConfig(const StixelConfig& c) {
+    static isx_config ToIsxConfig(const StixelConfig& c) {
         isx_config k;
         isx_config_init(&k);
         k.rows = c.rows; k.cols = c.cols; k.max_dis = c.max_dis; k.invalid_disparity = c.invalid_disparity;
@@ -97,6 +97,10 @@ public:
         k.sigma_camera_tilt = c.sigma_camera_tilt; k.sigma_camera_height = c.sigma_camera_height;
         k.median_join = c.median_join; k.epsilon = c.epsilon; k.range_objects_z = c.range_objects_z;
         k.road_vdisparity_threshold = c.road_vdisparity_threshold;
+        return k;
+    }
+    void SetConfig(const StixelConfig& c) {
+        const isx_config k = ToIsxConfig(c);
         check(isx_set_config(h_, &k));
         cfg_ = c;
     }
@@ -204,12 +208,83 @@ public:
         fp << "groundplane" << alpha_ground << "," << vhor << "\n";
     }
 
-    isx_handle handle() { return h_; }  // for the batched C entry points
+    // ---- extensions: batches of independent frames (the reference takes one frame per Compute) ----
+    // Road parameters of one frame of a batch (the arguments of SetRoadParameters).
+    typedef isx_road Road;
+    // Instance ids of one frame of a batch, the map GetInstanceStixels returns.
+    typedef std::map<std::pair<int, int>, int> InstanceMap;
+
+    // n frames, host buffers: disparity [n][rows][cols], segmentation [n][realcols][21][rows_power2_segmentation],
+    // one Road per frame.  Fills `frames` (one StixelsData per frame) and, if given, `instances`.  Synchronous;
+    // n <= Initialize(max_batch).
+    void ComputeBatch(bool pairwise, int n, const pixel_t* disparity, const int32_t* segmentation, const Road* roads,
+                      std::vector<StixelsData>& frames, std::vector<InstanceMap>* instances = nullptr) {
+        sections_.resize((size_t)n * GetRealCols() * GetMaxSections());
+        inst_.resize((size_t)n * (size_t)isx_instance_capacity(h_));
+        offs_.resize((size_t)n + 1);
+        check(isx_compute_batch_host(h_, pairwise ? 1 : 0, n, disparity, segmentation, roads,
+                                     reinterpret_cast<isx_section*>(sections_.data()), inst_.data(), (int)inst_.size(),
+                                     offs_.data()));
+        unpack(n, roads, sections_.data(), frames, instances);
+    }
+    // Streaming form: SubmitBatch enqueues a batch and returns; WaitBatch delivers the OLDEST one.  At most two in
+    // flight (submit, submit, wait, submit, wait, ...); the input buffers must stay valid until their WaitBatch.
+    void SubmitBatch(bool pairwise, int n, const pixel_t* disparity, const int32_t* segmentation, const Road* roads) {
+        Pending& p = pending_[submitted_ & 1];
+        p.n = n;
+        p.roads.assign(roads, roads + n);
+        p.sections.resize((size_t)n * GetRealCols() * GetMaxSections());
+        check(isx_submit_batch_host(h_, pairwise ? 1 : 0, n, disparity, segmentation, roads,
+                                    reinterpret_cast<isx_section*>(p.sections.data())));
+        submitted_++;
+    }
+    void WaitBatch(std::vector<StixelsData>& frames, std::vector<InstanceMap>* instances = nullptr) {
+        Pending& p = pending_[waited_ & 1];
+        inst_.resize((size_t)p.n * (size_t)isx_instance_capacity(h_));
+        offs_.resize((size_t)p.n + 1);
+        check(isx_wait_batch_host(h_, inst_.data(), (int)inst_.size(), offs_.data()));
+        waited_++;
+        unpack(p.n, p.roads.data(), p.sections.data(), frames, instances);
+    }
+
+    isx_handle handle() { return h_; }  // for the other C entry points
 
 private:
     isx_handle h_ = nullptr;
     StixelConfig cfg_;
     isx_frame_meta meta_{};
+    struct Pending {
+        int n = 0;
+        std::vector<Road> roads;
+        std::vector<Section> sections;
+    } pending_[2];
+    unsigned long long submitted_ = 0, waited_ = 0;
+    std::vector<Section> sections_;
+    std::vector<isx_instance> inst_;
+    std::vector<int32_t> offs_;
+
+    void unpack(int n, const Road* roads, const Section* sections, std::vector<StixelsData>& frames,
+                std::vector<InstanceMap>* instances) {
+        const size_t per = (size_t)GetRealCols() * GetMaxSections();
+        frames.resize((size_t)n);
+        if (instances) instances->assign((size_t)n, InstanceMap());
+        for (int f = 0; f < n; f++) {
+            StixelsData& d = frames[(size_t)f];
+            d.sections.assign(sections + (size_t)f * per, sections + (size_t)(f + 1) * per);
+            d.rows = (int)cfg_.rows;
+            d.cols = (int)cfg_.cols;
+            d.realcols = GetRealCols();
+            d.max_sections = GetMaxSections();
+            d.max_dis = cfg_.max_dis;
+            d.column_step = cfg_.column_step;
+            d.semantic_classes = cfg_.n_semantic_classes;
+            d.alpha_ground = roads[f].alpha_ground;
+            d.vhor = (int)cfg_.rows - roads[f].vhor - 1;
+            if (instances)
+                for (int32_t i = offs_[(size_t)f]; i < offs_[(size_t)f + 1]; i++)
+                    (*instances)[(size_t)f][std::make_pair(inst_[(size_t)i].column, inst_[(size_t)i].index)] = inst_[(size_t)i].label;
+        }
+    }
 
     static int device_from_env() {
         const char* e = std::getenv("ISX_DEVICE");
@@ -224,6 +299,56 @@ private:
         if (rc == ISX_ERR_INVALID_ARGUMENT) throw std::invalid_argument(isx_last_error(h_));
         die();
     }
+};
+
+// Extension: one context and worker thread per GPU in this process (isx_pool_*): a call shards its
+// frames into contiguous blocks over the GPUs, frame f -> GPU f * G / n.
+class StixelsPool {
+public:
+    typedef isx_road Road;
+    typedef std::map<std::pair<int, int>, int> InstanceMap;
+
+    StixelsPool(const StixelConfig& c, const std::vector<int>& devices, int max_batch) {
+        cfg_ = c;
+        const isx_config k = to_isx(c);
+        if (isx_pool_create(&p_, devices.data(), (int)devices.size(), &k, max_batch) != ISX_OK) {
+            std::cerr << "instance_stixels_b200: " << isx_pool_last_error(nullptr) << std::endl;
+            std::exit(1);
+        }
+    }
+    ~StixelsPool() { isx_pool_destroy(p_); }
+    StixelsPool(const StixelsPool&) = delete;
+    StixelsPool& operator=(const StixelsPool&) = delete;
+
+    int Size() { return isx_pool_size(p_); }
+    int GetRealCols() { return isx_pool_real_cols(p_); }
+    int GetMaxSections() { return ISX_MAX_STIXELS_PER_COLUMN; }
+
+    // Any n >= 1; layouts as Stixels::ComputeBatch.  `sections` receives [n][realcols][200].
+    void ComputeBatch(bool pairwise, int n, const pixel_t* disparity, const int32_t* segmentation, const Road* roads,
+                      std::vector<Section>& sections, std::vector<InstanceMap>* instances = nullptr) {
+        const size_t per = (size_t)GetRealCols() * GetMaxSections();
+        sections.resize((size_t)n * per);
+        std::vector<isx_instance> inst(instances ? (size_t)n * per : 0);
+        std::vector<int32_t> offs((size_t)n + 1);
+        if (isx_pool_compute_host(p_, pairwise ? 1 : 0, n, disparity, segmentation, roads,
+                                  reinterpret_cast<isx_section*>(sections.data()), instances ? inst.data() : nullptr,
+                                  (int)inst.size(), instances ? offs.data() : nullptr) != ISX_OK) {
+            std::cerr << "instance_stixels_b200: " << isx_pool_last_error(p_) << std::endl;
+            std::exit(1);
+        }
+        if (instances) {
+            instances->assign((size_t)n, InstanceMap());
+            for (int f = 0; f < n; f++)
+                for (int32_t i = offs[(size_t)f]; i < offs[(size_t)f + 1]; i++)
+                    (*instances)[(size_t)f][std::make_pair(inst[(size_t)i].column, inst[(size_t)i].index)] = inst[(size_t)i].label;
+        }
+    }
+
+private:
+    isx_pool_handle p_ = nullptr;
+    StixelConfig cfg_;
+    static isx_config to_isx(const StixelConfig& c) { return Stixels::ToIsxConfig(c); }
 };
 
 #endif  // ISX_DROPIN_STIXELS_HPP_

@@ -276,6 +276,12 @@ uint64_t isx_stream(isx_handle h);
  * consumers on isx_stream() after isx_compute_batch_device calls it first.  Asynchronous. */
 int isx_flush(isx_handle h);
 
+/* Pinned host memory for callers without the CUDA headers (the batched entry points copy from / into the
+ * caller's buffers asynchronously: pageable memory works but is staged by the driver at a fraction of the link
+ * rate).  Portable across devices and mapped, so a Section array allocated here is filled by the device directly. */
+void *isx_host_alloc(size_t bytes);
+void isx_host_free(void *p);
+
 /* ------------------------------------------------------------------ */
 /* Frame pool: one context and one host worker thread per GPU inside ONE process; a call shards
  * its frames into contiguous blocks, frame f -> worker f * G / n, and every worker streams its block through
@@ -318,6 +324,11 @@ typedef enum isx_tensor {
  * chunks[] (number of timed launches per stage) and optionally resets. */
 int isx_set_profiling(isx_handle h, int enable);
 int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, int reset);
+/* Developer trace of the host-batch pipeline while profiling is enabled: per chunk 10 time stamps in ms relative to
+ * the first (input copy begin | end; join | frame tables | column tables | DP begin | DP end; emission begin |
+ * grouping begin | emission end).  Returns the number of chunks written (or a negative status); call it before
+ * isx_get_stage_times, which consumes the same events. */
+int isx_get_chunk_trace(isx_handle h, double *ms, int max_chunks);
 /* Frames per kernel launch (batches are cut into chunks of this many frames). */
 /* DP work since isx_initialize in units of 32 x 32 cells: `total` = every (tile, chunk) pair of every column,
  * `evaluated` = those the kernels actually walked (the unary DP prunes chunks that provably cannot win). */

@@ -27,7 +27,7 @@ EXPORTS = [
     "isx_get_instance_stixels",
     "isx_compute_batch_host", "isx_submit_batch_host", "isx_wait_batch_host", "isx_compute_batch_device", "isx_synchronize", "isx_fetch_batch_results",
     "isx_stream", "isx_tensor_elems", "isx_read_tensor", "isx_set_profiling", "isx_get_stage_times",
-    "isx_chunk_frames",
+    "isx_chunk_frames", "isx_get_chunk_trace", "isx_host_alloc", "isx_host_free",
     # compact results / narrow inputs / frame pool
     "isx_wait_batch_packed", "isx_narrow_segmentation_elems", "isx_compute_batch_host_u16", "isx_submit_batch_host_u16",
     "isx_pool_create", "isx_pool_destroy", "isx_pool_size", "isx_pool_real_cols", "isx_pool_segmentation_elems",
@@ -165,6 +165,11 @@ def _declare(lib):
     lib.isx_set_profiling.argtypes = [H, i]
     lib.isx_get_stage_times.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_long), i, i]
     lib.isx_chunk_frames.argtypes = [H]
+    lib.isx_host_alloc.argtypes = [C.c_size_t]
+    lib.isx_host_alloc.restype = C.c_void_p
+    lib.isx_host_free.argtypes = [C.c_void_p]
+    lib.isx_host_free.restype = None
+    lib.isx_get_chunk_trace.argtypes = [H, C.POINTER(C.c_double), i]
     lib.isx_get_dp_units.argtypes = [H, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     lib.isx_instance_capacity.argtypes = [H]
     lib.isx_set_segmentation_from_cnn_device.argtypes = [H, C.c_void_p, i, i]

@@ -9,6 +9,7 @@
 // chunk's H2D copy, the previous chunk's kernels and the one before's D2H copy
 // overlap on three streams; there is no per-frame cudaMalloc, handle
 // construction or device-wide synchronisation.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -127,6 +128,8 @@ struct isx_context {
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;   // kStages+1 events per enqueued chunk
   size_t prof_used = 0;
+  std::vector<cudaEvent_t> prof_h2d;      // host batches: begin / end of every chunk's input copies (copy stream)
+  size_t prof_h2d_used = 0;
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long stage_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -975,6 +978,16 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
     if (first == 0 && pipeline_idle && n > h->chunk && h->chunk >= 8) cn = h->chunk / 4;
     // H2D of this chunk on the copy stream, once the kernels that last read this slot are done
     ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_in_free[slot], 0));
+    auto mark_h2d = [&]() {
+      if (!h->profiling) return;
+      if (h->prof_h2d_used >= h->prof_h2d.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_h2d.push_back(e);
+      }
+      cudaEventRecord(h->prof_h2d[h->prof_h2d_used++], h->s_h2d);
+    };
+    mark_h2d();
     if (in.narrow()) {
       ISX_TRY(h, cudaMemcpyAsync(h->d_in_disp16[slot], in.disparity16 + first * hw, sizeof(uint16_t) * hw * cn,
                                  cudaMemcpyHostToDevice, h->s_h2d));
@@ -993,6 +1006,7 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
                                    hs2 * sizeof(int32_t), used * sizeof(int32_t), (se / hs2) * cn,
                                    cudaMemcpyHostToDevice, h->s_h2d));
     }
+    mark_h2d();
     ISX_TRY(h, cudaEventRecord(h->ev_in_ready[slot], h->s_h2d));
     ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[slot]));  // pinned ground staging of this slot is reusable
     ISX_TRY(h, cudaStreamWaitEvent(h->s_compute, h->ev_in_ready[slot], 0));
@@ -1233,6 +1247,18 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
   return ISX_OK;
 }
 
+void *isx_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void isx_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 int isx_set_profiling(isx_handle h, int enable) {
   if (!h) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null handle");
   h->profiling = enable != 0;
@@ -1256,6 +1282,7 @@ int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, in
     }
   }
   h->prof_used = 0;
+  h->prof_h2d_used = 0;
   for (int i = 0; i < n_stages && i < 6; i++) {
     if (ms) ms[i] = h->stage_ms[i];
     if (chunks) chunks[i] = h->stage_launches[i];
@@ -1263,6 +1290,31 @@ int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, in
   if (reset)
     for (int i = 0; i < 8; i++) { h->stage_ms[i] = 0; h->stage_launches[i] = 0; }
   return ISX_OK;
+}
+
+// Developer trace of the host-batch pipeline (profiling enabled): per profiled chunk 10 time stamps in ms relative
+// to the first one -- input copy begin | end (copy stream); join | frame tables | column tables | DP begin | DP end
+// (compute stream); emission begin | grouping begin | emission end (emission stream).  Returns the number of chunks
+// written; call before isx_get_stage_times (which consumes the events).
+int isx_get_chunk_trace(isx_handle h, double *ms, int max_chunks) {
+  if (int rc = check_ready(h)) return rc;
+  ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
+  ISX_TRY(h, cudaStreamSynchronize(h->s_emit));
+  ISX_TRY(h, cudaStreamSynchronize(h->s_h2d));
+  const size_t chunks = std::min(h->prof_used / 8, h->prof_h2d_used / 2);
+  int n = 0;
+  if (chunks == 0) return 0;
+  cudaEvent_t t0 = h->prof_h2d[0];
+  for (size_t c = 0; c < chunks && n < max_chunks; c++, n++) {
+    for (int i = 0; i < 10; i++) {
+      cudaEvent_t e = i < 2 ? h->prof_h2d[2 * c + i] : h->prof_events[8 * c + (i - 2)];
+      float t = 0.f;
+      cudaEventElapsedTime(&t, t0, e);
+      ms[(size_t)n * 10 + i] = t;
+    }
+  }
+  h->prof_h2d_used = 0;
+  return n;
 }
 
 int isx_get_dp_units(isx_handle h, unsigned long long *evaluated, unsigned long long *total) {

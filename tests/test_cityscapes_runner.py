@@ -102,7 +102,13 @@ def test_runner_on_a_dataset_directory(tmp_path, pairwise):
         q = np.clip(np.rint(fr.disparity * 256.0), 0, 65535).astype(np.uint16)
         cv2.imwrite(str(tmp_path / "disparities" / f"{base}_disparity.png"), q)
         (tmp_path / "camera" / f"{base}_camera.json").write_text(json.dumps(cam))
-        np.save(tmp_path / "probs" / f"{base}_probs.npy", fr.segmentation)
+        if i == 1:   # the reference's own input format: dataset "nlogprobs" of an HDF5 file (H5Segmentation.cpp:25-49)
+            import sys
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import write_h5
+            write_h5.write_h5(str(tmp_path / "probs" / f"{base}_probs.h5"), "nlogprobs", fr.segmentation)
+        else:
+            np.save(tmp_path / "probs" / f"{base}_probs.npy", fr.segmentation)
         frames[base] = (q.astype(np.float32) / 256.0, fr.segmentation)
     pre = synth.preset("pairwise" if pairwise else "unary", rows, cols, 8)
     args = [APP, str(tmp_path), "128", repr(pre["segmentation_weight"]), repr(pre["instance_weight"]),
@@ -145,3 +151,48 @@ def test_runner_on_a_dataset_directory(tmp_path, pairwise):
                 assert (len(f) == 9) == ((c, j) in inst)
             assert data.sections[c, len(items)]["type"] == -1
     st.Finish()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pairwise", [0, 1])
+def test_batched_runner_writes_the_same_files(tmp_path, pairwise):
+    """--batch B / --gpus G (StixelsPool over the batched C entry points): byte-identical .stixels files to the
+    reference-style one-frame loop, and the same closing line format."""
+    cv2 = pytest.importorskip("cv2")
+    import shutil
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import write_h5
+    build()
+    rows, cols, n = 256, 512, 7
+    for d in ("disparities", "camera", "probs", "stixels"):
+        (tmp_path / d).mkdir()
+    cam = {"extrinsic": {"baseline": 0.209313}, "intrinsic": {"fx": 2262.52, "fy": 2262.52, "u0": 256.0, "v0": 128.0}}
+    for i in range(n):
+        fr = synth.make_frame(50 + i, rows=rows, cols=cols)
+        base = f"city_{i:06d}_000019"
+        q = np.clip(np.rint(fr.disparity * 256.0), 0, 65535).astype(np.uint16)
+        cv2.imwrite(str(tmp_path / "disparities" / f"{base}_disparity.png"), q)
+        (tmp_path / "camera" / f"{base}_camera.json").write_text(json.dumps(cam))
+        write_h5.write_h5(str(tmp_path / "probs" / f"{base}_probs.h5"), "nlogprobs", fr.segmentation)
+    pre = synth.preset("pairwise" if pairwise else "unary", rows, cols, 8)
+    args = [APP, str(tmp_path), "128", repr(pre["segmentation_weight"]), repr(pre["instance_weight"]),
+            repr(pre["disparity_weight"]), str(pairwise), "8", repr(pre["eps"]), str(pre["min_pts"]),
+            str(pre["size_filter"])]
+    p = subprocess.run(args, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:] + p.stdout[-2000:]
+    single = {f: open(tmp_path / "stixels" / f, "rb").read() for f in sorted(os.listdir(tmp_path / "stixels"))}
+    assert len(single) == n
+    gpus = min(2, torch.cuda.device_count())
+    for extra in (["--batch", "3"], ["--batch", "2", "--gpus", str(gpus)], ["--batch", "16"]):
+        shutil.rmtree(tmp_path / "stixels")
+        (tmp_path / "stixels").mkdir()
+        p = subprocess.run(args + extra, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-2000:] + p.stdout[-2000:]
+        batched = {f: open(tmp_path / "stixels" / f, "rb").read() for f in sorted(os.listdir(tmp_path / "stixels"))}
+        assert batched.keys() == single.keys()
+        for f in single:
+            assert batched[f] == single[f], (extra, f)
+        time_line = [l for l in p.stdout.split("\n")[-3:] if l.startswith("It took an average")][0]
+        assert re.search(r"([0-9]*\.[0-9]*) milliseconds", time_line) and time_line.rstrip().endswith("fps")
