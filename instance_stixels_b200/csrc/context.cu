@@ -246,10 +246,11 @@ static const float *road_tables(isx_context *c, const isx_road &r) {
 // Two streams: join -> tables -> LUT -> DP on s_compute; backtracking, candidate
 // collection, grouping and packing (short, latency-bound launches) on s_emit, so
 // that they overlap the next chunk's DP.
-static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const float *d_disp,
-                         const int32_t *d_seg, const isx_road *roads, int slot) {
-  const KParams &kp = c->kp;
-  const int H = kp.rows, C = kp.realcols;
+// The per-frame road tables of a chunk (Stixels.cu:463-493: three blocking copies per frame in the reference) go
+// through the pinned staging half of `slot` to the chunk set on stream `st`.  The caller has made sure that the copy
+// which last read this staging half is done, and orders `st` behind the emission that last read the chunk set.
+static int stage_road_tables(isx_context *c, const isx_road *roads, int n, int slot, cudaStream_t st) {
+  const int H = c->kp.rows;
   float *hg = c->h_ground + (size_t)slot * c->chunk * 3 * H;
   int *hv = c->h_vhor + (size_t)slot * c->chunk;
   for (int i = 0; i < n; i++) {
@@ -257,11 +258,24 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
     hv[i] = H - roads[i].vhor - 1;  // Stixels.cu:377
   }
   const isx_context::ChunkSet &cs = c->sets[slot];
+  ISX_TRY(c, cudaMemcpyAsync(cs.ground, hg, sizeof(float) * 3 * H * n, cudaMemcpyHostToDevice, st));
+  ISX_TRY(c, cudaMemcpyAsync(cs.vhor, hv, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  return ISX_OK;
+}
+
+// `roads_staged`: the caller has already copied the road tables of the chunk (host batches send them on the copy
+// stream IN FRONT of the chunk's images: as a copy on the compute stream they would queue on the copy engine behind
+// the next chunk's images -- several milliseconds of an idle GPU per chunk, measured with isx_get_chunk_trace).
+static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const float *d_disp,
+                         const int32_t *d_seg, const isx_road *roads, int slot, bool roads_staged = false) {
+  const KParams &kp = c->kp;
+  const int H = kp.rows, C = kp.realcols;
+  const isx_context::ChunkSet &cs = c->sets[slot];
   cudaStream_t s = c->s_compute, se = c->s_emit;
   // the emission of the chunk that used this set two chunks ago must be done with it
   ISX_TRY(c, cudaStreamWaitEvent(s, c->ev_emit_done[slot], 0));
-  ISX_TRY(c, cudaMemcpyAsync(cs.ground, hg, sizeof(float) * 3 * H * n, cudaMemcpyHostToDevice, s));
-  ISX_TRY(c, cudaMemcpyAsync(cs.vhor, hv, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  if (!roads_staged)
+    if (int rc = stage_road_tables(c, roads, n, slot, s)) return rc;
   ISX_TRY(c, cudaMemsetAsync(cs.err, 0, sizeof(int) * n, s));  // the error words of THIS chunk's frames
   isx_context::ResultSet &R = c->rs[c->cur];
   BatchBuffers b = c->buf;
@@ -976,8 +990,11 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
     cn = (n - first) < h->chunk ? (n - first) : h->chunk;
     // a short first chunk when nothing is running: its copy is the only one that no kernel hides
     if (first == 0 && pipeline_idle && n > h->chunk && h->chunk >= 8) cn = h->chunk / 4;
-    // H2D of this chunk on the copy stream, once the kernels that last read this slot are done
+    // H2D of this chunk on the copy stream, once the kernels that last read this slot are done (the host waits too:
+    // the pinned staging of the road tables is rewritten next) and the emission that last read the chunk set
+    ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[slot]));
     ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_in_free[slot], 0));
+    ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_emit_done[slot], 0));
     auto mark_h2d = [&]() {
       if (!h->profiling) return;
       if (h->prof_h2d_used >= h->prof_h2d.size()) {
@@ -988,6 +1005,7 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
       cudaEventRecord(h->prof_h2d[h->prof_h2d_used++], h->s_h2d);
     };
     mark_h2d();
+    if (int rc = stage_road_tables(h, roads + first, cn, slot, h->s_h2d)) return rc;
     if (in.narrow()) {
       ISX_TRY(h, cudaMemcpyAsync(h->d_in_disp16[slot], in.disparity16 + first * hw, sizeof(uint16_t) * hw * cn,
                                  cudaMemcpyHostToDevice, h->s_h2d));
@@ -1008,13 +1026,12 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
     }
     mark_h2d();
     ISX_TRY(h, cudaEventRecord(h->ev_in_ready[slot], h->s_h2d));
-    ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[slot]));  // pinned ground staging of this slot is reusable
     ISX_TRY(h, cudaStreamWaitEvent(h->s_compute, h->ev_in_ready[slot], 0));
     if (in.narrow())
       launch_widen_inputs(h->kp, h->d_in_disp16[slot], in.scale, h->d_in_seg16[slot], h->d_in_disp[slot],
                           h->d_in_seg[slot], cn, h->s_compute);
     if (int rc = enqueue_chunk(h, pairwise != 0, first, cn, h->d_in_disp[slot], h->d_in_seg[slot], roads + first,
-                               slot))
+                               slot, /*roads_staged=*/true))
       return rc;
     ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_compute));
     slot ^= 1;
