@@ -24,6 +24,8 @@
 namespace isx {
 
 static thread_local std::string g_last_error;
+constexpr int kProfEvents = 9;    // profiling events per enqueued chunk (enqueue_chunk)
+constexpr int kTraceStamps = 11;  // time stamps per chunk of isx_get_chunk_trace
 
 static int fail(isx_context *ctx, int code, const std::string &msg);
 
@@ -49,8 +51,13 @@ struct isx_context {
   int max_batch = 0, chunk = 0;
   std::string last_error;
 
-  cudaStream_t s_compute = nullptr, s_emit = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  // s_tables: join + table build (HBM-bound), s_compute: the DP (issue-bound), s_emit: backtracking, grouping, packing
+  // (short, latency-bound).  The tables of chunk k+1 are built WHILE the DP of chunk k runs: their CTAs take the
+  // places DP CTAs vacate (12 K registers against 16 K), so the memory-bound and the issue-bound kernel share the SMs.
+  cudaStream_t s_tables = nullptr, s_compute = nullptr, s_emit = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_dp_done[2] = {nullptr, nullptr}, ev_emit_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_tab_done[2] = {nullptr, nullptr};   // tables of the chunk in this set are complete
+  cudaEvent_t ev_user = nullptr;                     // the caller's work on isx_stream() before a device batch
   cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
   cudaEvent_t ev_chunk_done = nullptr;
   // narrow host inputs (isx_*_u16): staging for the raw uint16 / int16 data, allocated on first use
@@ -74,9 +81,13 @@ struct isx_context {
     float4 *dp = nullptr;
     float *pm = nullptr;
     int *err = nullptr;   // [chunk] kErr* bits per frame, zeroed when the chunk is enqueued
+    float *joined = nullptr;      // [chunk][C][H]
+    float *object_lut = nullptr;  // [chunk][C][D][lut_stride]
+    int *col_flags = nullptr;     // [chunk][C]
   } sets[2];
   int last_set = 0;
-  bool emit_join_pending = false;  // results of the last device batch are not yet ordered on s_compute
+  bool overlap_tables = true;      // table build of chunk k+1 beside the DP of chunk k (ISX_OVERLAP_TABLES)
+  bool emit_join_pending = false;  // results of the last device batch are not yet ordered on isx_stream()
   // Results of one batch.  The padded device arrays feed the rasteriser and the fallback copy; what a host caller
   // gets is packed by pack_results_kernel (emit.cu) straight into pinned host memory that is mapped into the
   // device address space (h_* = host address, m_* = the device's address of the same memory).
@@ -243,7 +254,7 @@ static const float *road_tables(isx_context *c, const isx_road &r) {
 // `slot` selects the pinned ground-table staging half and the ChunkSet; results
 // land at frame offset `first` of the per-batch result arrays.
 //
-// Two streams: join -> tables -> LUT -> DP on s_compute; backtracking, candidate
+// Three streams: join -> tables -> LUT on s_tables, the DP on s_compute; backtracking, candidate
 // collection, grouping and packing (short, latency-bound launches) on s_emit, so
 // that they overlap the next chunk's DP.
 // The per-frame road tables of a chunk (Stixels.cu:463-493: three blocking copies per frame in the reference) go
@@ -271,23 +282,26 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
   const KParams &kp = c->kp;
   const int H = kp.rows, C = kp.realcols;
   const isx_context::ChunkSet &cs = c->sets[slot];
-  cudaStream_t s = c->s_compute, se = c->s_emit;
-  // the emission of the chunk that used this set two chunks ago must be done with it
-  ISX_TRY(c, cudaStreamWaitEvent(s, c->ev_emit_done[slot], 0));
+  cudaStream_t st = c->s_tables, s = c->s_compute, se = c->s_emit;
+  // the emission of the chunk that used this set two chunks ago must be done with it (it follows that chunk's DP)
+  ISX_TRY(c, cudaStreamWaitEvent(st, c->ev_emit_done[slot], 0));
+  // ISX_OVERLAP_TABLES=0: the table build waits for the DP of the chunk before it (one kernel at a time on the SMs)
+  if (!c->overlap_tables) ISX_TRY(c, cudaStreamWaitEvent(st, c->ev_dp_done[slot ^ 1], 0));
   if (!roads_staged)
-    if (int rc = stage_road_tables(c, roads, n, slot, s)) return rc;
-  ISX_TRY(c, cudaMemsetAsync(cs.err, 0, sizeof(int) * n, s));  // the error words of THIS chunk's frames
+    if (int rc = stage_road_tables(c, roads, n, slot, st)) return rc;
+  ISX_TRY(c, cudaMemsetAsync(cs.err, 0, sizeof(int) * n, st));  // the error words of THIS chunk's frames
   isx_context::ResultSet &R = c->rs[c->cur];
   BatchBuffers b = c->buf;
   b.ground = cs.ground; b.vhor = cs.vhor; b.stat = cs.stat;
   b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
+  b.joined = cs.joined; b.object_lut = cs.object_lut; b.col_flags = cs.col_flags;
   b.error_flag = cs.err;
   b.disparity = d_disp;
   b.segmentation = d_seg;
   b.sections = R.d_sections + (size_t)first * C * kMaxSections;
   b.n_sections = R.d_nsections + (size_t)first * C;
-  // profiling events per chunk: 0 join | 1 frame tables | 2 column tables + LUT | 3 dp | 4 dp end (s_compute);
-  //                             5 backtrack + collect | 6 grouping + pack | 7 end (s_emit)
+  // profiling events per chunk: 0 join | 1 frame tables | 2 column tables + LUT | 3 end (s_tables); 4 dp | 5 dp end
+  //                             (s_compute); 6 backtrack + collect | 7 grouping + pack | 8 end (s_emit)
   auto mark = [&](cudaStream_t st) {
     if (!c->profiling) return;
     if (c->prof_used >= c->prof_events.size()) {
@@ -297,12 +311,15 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
     }
     cudaEventRecord(c->prof_events[c->prof_used++], st);
   };
-  mark(s);
-  launch_join_columns(kp, b, n, s);
-  mark(s);
-  if (pairwise) launch_frame_tables(kp, b, n, s);
-  mark(s);
-  launch_column_tables(kp, b, n, s);
+  mark(st);
+  launch_join_columns(kp, b, n, st);
+  mark(st);
+  if (pairwise) launch_frame_tables(kp, b, n, st);
+  mark(st);
+  launch_column_tables(kp, b, n, st);
+  mark(st);
+  ISX_TRY(c, cudaEventRecord(c->ev_tab_done[slot], st));
+  ISX_TRY(c, cudaStreamWaitEvent(s, c->ev_tab_done[slot], 0));
   mark(s);
   launch_dp(kp, b, n, pairwise, s);
   {
@@ -400,9 +417,10 @@ static int alloc_result_set(isx_context *c, int i) {
   return ISX_OK;
 }
 
-// Results of every enqueued chunk become visible to work ordered after this on s_compute.
+// Results of every enqueued chunk become visible to work ordered after this on isx_stream() (the table stream: the
+// first stream of the pipeline, where a caller's producers of device inputs and consumers of results run).
 static int join_emit_stream(isx_context *c) {
-  ISX_TRY(c, cudaStreamWaitEvent(c->s_compute, c->ev_emit_done[c->last_set], 0));
+  ISX_TRY(c, cudaStreamWaitEvent(c->s_tables, c->ev_emit_done[c->last_set], 0));
   c->emit_join_pending = false;
   return ISX_OK;
 }
@@ -575,11 +593,18 @@ int isx_initialize(isx_handle h, int max_batch) {
   const size_t cap = C * kMaxSections;
   h->inst_cap = (int)cap;  // every stixel of a frame can be an instance stixel (the reference sizes 8 x this)
 
-  ISX_TRY(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
   {
-    // the emission stream's short kernels should not queue behind the DP's thousands of CTAs
+    // The emission stream's short kernels should not queue behind the DP's thousands of CTAs: highest priority.
+    // The table build runs at the DP's own (lowest) priority: its CTAs then fill the SMs as the DP of the chunk
+    // before drains (B200, 64-frame batches: unary 7581 -> 7995 frames/s, pairwise 2761 -> 2942 against one kernel
+    // at a time); ABOVE the DP they push its CTAs out as they retire and both kernels lose (7581 / 2566).
     int prio_lo = 0, prio_hi = 0;
     ISX_TRY(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    int prio_mid = prio_lo;
+    if (const char *e = std::getenv("ISX_TABLES_PRIO"))   // A/B runs: 1 = between the DP and the emission kernels
+      prio_mid = (std::atoi(e) != 0 && prio_hi < prio_lo - 1) ? prio_hi + 1 : prio_lo;
+    ISX_TRY(h, cudaStreamCreateWithPriority(&h->s_compute, cudaStreamNonBlocking, prio_lo));
+    ISX_TRY(h, cudaStreamCreateWithPriority(&h->s_tables, cudaStreamNonBlocking, prio_mid));
     ISX_TRY(h, cudaStreamCreateWithPriority(&h->s_emit, cudaStreamNonBlocking, prio_hi));
   }
   ISX_TRY(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
@@ -589,8 +614,10 @@ int isx_initialize(isx_handle h, int max_batch) {
     ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_in_free[i], cudaEventDisableTiming));
     ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_dp_done[i], cudaEventDisableTiming));
     ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_emit_done[i], cudaEventDisableTiming));
+    ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_tab_done[i], cudaEventDisableTiming));
   }
   ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_chunk_done, cudaEventDisableTiming));
+  ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
 
   BatchBuffers &b = h->buf;
   for (int i = 0; i < 2; i++) {
@@ -600,7 +627,6 @@ int isx_initialize(isx_handle h, int max_batch) {
   }
   ISX_TRY(h, dev_alloc(h, &h->d_single_disp, H * W));
   ISX_TRY(h, dev_alloc(h, &h->d_single_seg, seg_elems(h)));
-  ISX_TRY(h, dev_alloc(h, &b.joined, ch * C * H));
   for (int i = 0; i < 2; i++) {
     isx_context::ChunkSet &cs = h->sets[i];
     ISX_TRY(h, dev_alloc(h, &cs.ground, ch * 3 * H));
@@ -612,8 +638,11 @@ int isx_initialize(isx_handle h, int max_batch) {
     ISX_TRY(h, cudaMemset(cs.pm, 0, ch * C * H * sizeof(float)));
     ISX_TRY(h, dev_alloc(h, &cs.dp, ch * C * H));
     ISX_TRY(h, dev_alloc(h, &cs.err, ch));
+    ISX_TRY(h, dev_alloc(h, &cs.joined, ch * C * H));
+    ISX_TRY(h, dev_alloc(h, &cs.object_lut, lut_buffer_bytes(ch * C, D * (size_t)kp.lut_stride * 4) / 4));
+    ISX_TRY(h, dev_alloc(h, &cs.col_flags, ch * C));
+    ISX_TRY(h, cudaMemset(cs.col_flags, 0, ch * C * sizeof(int)));
   }
-  ISX_TRY(h, dev_alloc(h, &b.object_lut, lut_buffer_bytes(ch * C, D * (size_t)kp.lut_stride * 4) / 4));
   ISX_TRY(h, dev_alloc(h, &b.cand_count, ch * kInstanceClasses));
   ISX_TRY(h, dev_alloc(h, &b.cand_offset, ch * (C + 1) * kInstanceClasses));
   ISX_TRY(h, dev_alloc(h, &b.cand_xy, ch * kInstanceClasses * cap));
@@ -623,8 +652,6 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &b.cand_scratch, ch * kInstanceClasses * cap));
   ISX_TRY(h, dev_alloc(h, &b.pack_offset, ch * (C + 1)));
   ISX_TRY(h, dev_alloc(h, &b.dp_units, 1));
-  ISX_TRY(h, dev_alloc(h, &b.col_flags, ch * C));
-  ISX_TRY(h, cudaMemset(b.col_flags, 0, ch * C * sizeof(int)));
   if (pairwise_walk_enabled()) {
     ISX_TRY(h, dev_alloc(h, &b.qrows, ch * C * (size_t)kp.rec_stride * kDynWords));
     ISX_TRY(h, cudaMemset(b.qrows, 0, ch * C * (size_t)kp.rec_stride * kDynWords * sizeof(float)));
@@ -660,6 +687,8 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, cudaMallocHost(&h->h_ground, sizeof(float) * 2 * ch * 3 * H));
   ISX_TRY(h, cudaMallocHost(&h->h_vhor, sizeof(int) * 2 * ch));
   h->road_cache.clear();
+  h->overlap_tables = true;
+  if (const char *e = std::getenv("ISX_OVERLAP_TABLES")) h->overlap_tables = std::atoi(e) != 0;
   h->initialized = true;
   h->last_batch = 0;
   return ISX_OK;
@@ -700,8 +729,11 @@ int isx_finish(isx_handle h) {
     cudaEventDestroy(h->ev_in_free[i]);
     cudaEventDestroy(h->ev_dp_done[i]);
     cudaEventDestroy(h->ev_emit_done[i]);
+    cudaEventDestroy(h->ev_tab_done[i]);
   }
   cudaEventDestroy(h->ev_chunk_done);
+  cudaEventDestroy(h->ev_user);
+  cudaStreamDestroy(h->s_tables);
   cudaStreamDestroy(h->s_compute);
   cudaStreamDestroy(h->s_emit);
   cudaStreamDestroy(h->s_h2d);
@@ -720,17 +752,24 @@ int isx_set_disparity_image(isx_handle h, const float *host, size_t n) {
   if (int rc = check_ready(h)) return rc;
   if (!host || n != (size_t)h->kp.rows * h->kp.cols)
     return fail(h, ISX_ERR_INVALID_ARGUMENT, "disparity image must hold rows*cols floats");
-  ISX_TRY(h, cudaMemcpyAsync(h->d_single_disp, host, n * sizeof(float), cudaMemcpyHostToDevice, h->s_compute));
+  ISX_TRY(h, cudaMemcpyAsync(h->d_single_disp, host, n * sizeof(float), cudaMemcpyHostToDevice, h->s_tables));
   return ISX_OK;
 }
 
-float *isx_input_disparity_device(isx_handle h) { return (h && h->initialized) ? h->d_single_disp : nullptr; }
+float *isx_input_disparity_device(isx_handle h) {
+  if (!h || !h->initialized) return nullptr;
+  // the caller hands the pointer to its own kernels (RoadEstimation::Compute(pixel_t *d_im), RoadEstimation.cu:107):
+  // the image SetDisparityImage is still copying must have arrived
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->s_tables);
+  return h->d_single_disp;
+}
 
 int isx_set_segmentation(isx_handle h, const int32_t *host, size_t n) {
   if (int rc = check_ready(h)) return rc;
   if (!host || n != seg_elems(h))
     return fail(h, ISX_ERR_INVALID_ARGUMENT, "segmentation must hold realcols*channels*rows_power2_segmentation ints");
-  ISX_TRY(h, cudaMemcpyAsync(h->d_single_seg, host, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_compute));
+  ISX_TRY(h, cudaMemcpyAsync(h->d_single_seg, host, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_tables));
   return ISX_OK;
 }
 
@@ -749,7 +788,7 @@ int isx_set_segmentation_from_cnn_device(isx_handle h, const float *d_cnn, int c
   if (int rc = check_ready(h)) return rc;
   if (!d_cnn) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
   if (int rc = check_cnn_grid(h, cnn_rows, cnn_cols)) return rc;
-  launch_flip_and_pad(h->kp, d_cnn, h->d_single_seg, 1, cnn_rows, cnn_cols, h->s_compute);
+  launch_flip_and_pad(h->kp, d_cnn, h->d_single_seg, 1, cnn_rows, cnn_cols, h->s_tables);
   ISX_TRY(h, cudaGetLastError());
   return ISX_OK;
 }
@@ -759,7 +798,7 @@ int isx_flip_and_pad_batch_device(isx_handle h, int n, const float *d_cnn, int c
   if (int rc = check_ready(h)) return rc;
   if (!d_cnn || !d_segmentation || n < 1) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument or empty batch");
   if (int rc = check_cnn_grid(h, cnn_rows, cnn_cols)) return rc;
-  launch_flip_and_pad(h->kp, d_cnn, d_segmentation, n, cnn_rows, cnn_cols, h->s_compute);
+  launch_flip_and_pad(h->kp, d_cnn, d_segmentation, n, cnn_rows, cnn_cols, h->s_tables);
   ISX_TRY(h, cudaGetLastError());
   return ISX_OK;
 }
@@ -857,7 +896,7 @@ int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_met
   const int erc = enqueue_chunk(h, pairwise != 0, 0, 1, h->d_single_disp, seg, &h->single_road, 0);
   h->direct_sections = nullptr;
   if (erc) return erc;
-  ISX_TRY(h, cudaEventRecord(h->ev_in_free[0], h->s_compute));
+  ISX_TRY(h, cudaEventRecord(h->ev_in_free[0], h->s_tables));
   if (int rc = join_emit_stream(h)) return rc;
   h->last_batch = 1;
   h->last_roads.assign(1, h->single_road);
@@ -913,7 +952,7 @@ int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_d
     if (int rc = enqueue_chunk(h, pairwise != 0, first, cn, d_disparity + first * hw, d_segmentation + first * se,
                                roads + first, slot))
       return rc;
-    ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_compute));
+    ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_tables));
     slot ^= 1;
   }
   h->host_slot = slot;
@@ -931,7 +970,7 @@ int isx_flush(isx_handle h) {
 int isx_synchronize(isx_handle h) {
   if (int rc = check_ready(h)) return rc;
   if (int rc = ensure_joined(h)) return rc;
-  ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
+  ISX_TRY(h, cudaStreamSynchronize(h->s_tables));
   return ISX_OK;
 }
 
@@ -1026,14 +1065,14 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
     }
     mark_h2d();
     ISX_TRY(h, cudaEventRecord(h->ev_in_ready[slot], h->s_h2d));
-    ISX_TRY(h, cudaStreamWaitEvent(h->s_compute, h->ev_in_ready[slot], 0));
+    ISX_TRY(h, cudaStreamWaitEvent(h->s_tables, h->ev_in_ready[slot], 0));
     if (in.narrow())
       launch_widen_inputs(h->kp, h->d_in_disp16[slot], in.scale, h->d_in_seg16[slot], h->d_in_disp[slot],
-                          h->d_in_seg[slot], cn, h->s_compute);
+                          h->d_in_seg[slot], cn, h->s_tables);
     if (int rc = enqueue_chunk(h, pairwise != 0, first, cn, h->d_in_disp[slot], h->d_in_seg[slot], roads + first,
                                slot, /*roads_staged=*/true))
       return rc;
-    ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_compute));
+    ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_tables));   // the inputs are read by the table build only
     slot ^= 1;
   }
   h->host_slot = slot;
@@ -1112,7 +1151,7 @@ static int submit_batch_host(isx_handle h, int pairwise, int n, const HostInputs
   h->batch_set[par] = h->cur;
   h->batch_sections[par] = sections;
   h->submitted++;
-  h->emit_join_pending = true;  // s_compute itself has not been ordered behind the emission stream
+  h->emit_join_pending = true;  // isx_stream() itself has not been ordered behind the emission stream
   return ISX_OK;
 }
 
@@ -1184,12 +1223,12 @@ int isx_rasterize_batch_device(isx_handle h, int first, int n, uint8_t *d_label_
   const isx_context::ResultSet &R = h->rs[h->cur];
   launch_rasterize(h->kp, R.d_sections + (size_t)first * C * kMaxSections, R.d_nsections + (size_t)first * C,
                    R.d_inst + (size_t)first * h->inst_cap, R.d_inst_count + first, h->inst_cap,
-                   h->d_raster_table, n, d_label_ids, d_instance_ids, d_disparity, h->s_compute);
+                   h->d_raster_table, n, d_label_ids, d_instance_ids, d_disparity, h->s_tables);
   ISX_TRY(h, cudaGetLastError());
   return ISX_OK;
 }
 
-uint64_t isx_stream(isx_handle h) { return (h && h->initialized) ? (uint64_t)(uintptr_t)h->s_compute : 0; }
+uint64_t isx_stream(isx_handle h) { return (h && h->initialized) ? (uint64_t)(uintptr_t)h->s_tables : 0; }
 
 size_t isx_tensor_elems(isx_handle h, int tensor) {
   if (!h || !h->initialized) return 0;
@@ -1218,6 +1257,7 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
   if (local < 0 || local >= h->last_chunk_n)
     return fail(h, ISX_ERR_INVALID_ARGUMENT, "intermediates are only kept for the last chunk of the last batch");
   if (int rc = ensure_joined(h)) return rc;
+  ISX_TRY(h, cudaStreamSynchronize(h->s_tables));
   ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
   const KParams &kp = h->kp;
   const size_t H = kp.rows, C = kp.realcols, D = kp.max_dis;
@@ -1226,6 +1266,7 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
     const isx_context::ChunkSet &cs = h->sets[h->last_set];
     b.ground = cs.ground; b.vhor = cs.vhor; b.stat = cs.stat;
     b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
+    b.joined = cs.joined; b.object_lut = cs.object_lut; b.col_flags = cs.col_flags;
   }
   if (tensor == ISX_T_GROUND_TABLES) {
     ISX_TRY(h, cudaMemcpy(host, b.ground + (size_t)local * 3 * H, need, cudaMemcpyDeviceToHost));
@@ -1284,13 +1325,16 @@ int isx_set_profiling(isx_handle h, int enable) {
 
 int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, int reset) {
   if (int rc = check_ready(h)) return rc;
+  ISX_TRY(h, cudaStreamSynchronize(h->s_tables));
   ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
   ISX_TRY(h, cudaStreamSynchronize(h->s_emit));
-  // 8 events per chunk (enqueue_chunk): stage i < 4 = events i..i+1 on s_compute, stages 4, 5 = events 5..7 on s_emit
-  const int per = 8;
+  // 9 events per chunk (enqueue_chunk): stages 0..2 = events i..i+1 on s_tables, stage 3 = events 4..5 on s_compute,
+  // stages 4, 5 = events 6..8 on s_emit.  The table build of a chunk overlaps the DP of the chunk before it, so the
+  // stage times of a stream of chunks add up to more than the wall time.
+  const int per = kProfEvents;
   for (size_t base = 0; base + per <= h->prof_used; base += per) {
     for (int i = 0; i < 6; i++) {
-      const int e0 = i < 4 ? i : i + 1;
+      const int e0 = i < 3 ? i : i + 1;
       float t = 0.f;
       if (cudaEventElapsedTime(&t, h->prof_events[base + e0], h->prof_events[base + e0 + 1]) == cudaSuccess) {
         h->stage_ms[i] += t;
@@ -1309,25 +1353,26 @@ int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, in
   return ISX_OK;
 }
 
-// Developer trace of the host-batch pipeline (profiling enabled): per profiled chunk 10 time stamps in ms relative
-// to the first one -- input copy begin | end (copy stream); join | frame tables | column tables | DP begin | DP end
-// (compute stream); emission begin | grouping begin | emission end (emission stream).  Returns the number of chunks
-// written; call before isx_get_stage_times (which consumes the events).
+// Developer trace of the host-batch pipeline (profiling enabled): per profiled chunk 11 time stamps in ms relative
+// to the first one -- input copy begin | end (copy stream); join | frame tables | column tables | tables end (table
+// stream); DP begin | DP end (compute stream); emission begin | grouping begin | emission end (emission stream).
+// Returns the number of chunks written; call before isx_get_stage_times (which consumes the events).
 int isx_get_chunk_trace(isx_handle h, double *ms, int max_chunks) {
   if (int rc = check_ready(h)) return rc;
+  ISX_TRY(h, cudaStreamSynchronize(h->s_tables));
   ISX_TRY(h, cudaStreamSynchronize(h->s_compute));
   ISX_TRY(h, cudaStreamSynchronize(h->s_emit));
   ISX_TRY(h, cudaStreamSynchronize(h->s_h2d));
-  const size_t chunks = std::min(h->prof_used / 8, h->prof_h2d_used / 2);
+  const size_t chunks = std::min(h->prof_used / kProfEvents, h->prof_h2d_used / 2);
   int n = 0;
   if (chunks == 0) return 0;
   cudaEvent_t t0 = h->prof_h2d[0];
   for (size_t c = 0; c < chunks && n < max_chunks; c++, n++) {
-    for (int i = 0; i < 10; i++) {
-      cudaEvent_t e = i < 2 ? h->prof_h2d[2 * c + i] : h->prof_events[8 * c + (i - 2)];
+    for (int i = 0; i < kTraceStamps; i++) {
+      cudaEvent_t e = i < 2 ? h->prof_h2d[2 * c + i] : h->prof_events[kProfEvents * c + (i - 2)];
       float t = 0.f;
       cudaEventElapsedTime(&t, t0, e);
-      ms[(size_t)n * 10 + i] = t;
+      ms[(size_t)n * kTraceStamps + i] = t;
     }
   }
   h->prof_h2d_used = 0;

@@ -40,11 +40,11 @@ for kind in ("float", "float_dequantized", "u16", "float", "u16"):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     import ctypes
-    buf = (ctypes.c_double * (10 * 64))()
+    buf = (ctypes.c_double * (11 * 64))()
     nch = st._lib.isx_get_chunk_trace(st._h, buf, 64)
     if os.environ.get("PROBE_TRACE"):
         for c in range(nch):
-            print("   chunk", c, " ".join("%7.2f" % buf[c * 10 + k] for k in range(10)), flush=True)
+            print("   chunk", c, " ".join("%7.2f" % buf[c * 11 + k] for k in range(11)), flush=True)
     stages = st.stage_times(reset=True)
     print(kind, "%.0f frames/s" % (B * n / dt), {k: round(v[0] / max(v[1], 1), 2) for k, v in stages.items()}, st.dp_units(), flush=True)
 st.Finish()
