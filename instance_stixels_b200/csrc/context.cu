@@ -24,6 +24,7 @@
 namespace isx {
 
 static thread_local std::string g_last_error;
+constexpr int kStageSlots = 8;    // pinned staging buffers of the road tables (see isx_context::h_ground)
 constexpr int kProfEvents = 9;    // profiling events per enqueued chunk (enqueue_chunk)
 constexpr int kTraceStamps = 11;  // time stamps per chunk of isx_get_chunk_trace
 
@@ -111,8 +112,12 @@ struct isx_context {
   int *d_export_index = nullptr;
 
   // pinned host staging
-  float *h_ground = nullptr;                      // [2][chunk][3][H]
-  int *h_vhor = nullptr;                          // [2][chunk]
+  // road tables on their way to the device: a ring of kStageSlots pinned buffers, each with the event of the copy
+  // that last read it, so that the enqueueing host thread may run several chunks ahead of the device
+  float *h_ground = nullptr;                      // [kStageSlots][chunk][3][H]
+  int *h_vhor = nullptr;                          // [kStageSlots][chunk]
+  cudaEvent_t ev_stage_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned long long stage_next = 0;
   // isx_submit_batch_host keeps up to two batches in flight: rs[cur] belongs to the batch submitted last, the other
   // set to the one before (the second set is allocated on the first submit).
   cudaEvent_t ev_batch_done[2] = {nullptr, nullptr};  // by ticket parity
@@ -262,8 +267,11 @@ static const float *road_tables(isx_context *c, const isx_road &r) {
 // which last read this staging half is done, and orders `st` behind the emission that last read the chunk set.
 static int stage_road_tables(isx_context *c, const isx_road *roads, int n, int slot, cudaStream_t st) {
   const int H = c->kp.rows;
-  float *hg = c->h_ground + (size_t)slot * c->chunk * 3 * H;
-  int *hv = c->h_vhor + (size_t)slot * c->chunk;
+  const int stage = (int)(c->stage_next++ % kStageSlots);
+  // the copy that read this staging buffer kStageSlots chunks ago must be done (a never-recorded event is complete)
+  ISX_TRY(c, cudaEventSynchronize(c->ev_stage_done[stage]));
+  float *hg = c->h_ground + (size_t)stage * c->chunk * 3 * H;
+  int *hv = c->h_vhor + (size_t)stage * c->chunk;
   for (int i = 0; i < n; i++) {
     std::memcpy(hg + (size_t)i * 3 * H, road_tables(c, roads[i]), sizeof(float) * 3 * H);
     hv[i] = H - roads[i].vhor - 1;  // Stixels.cu:377
@@ -271,6 +279,7 @@ static int stage_road_tables(isx_context *c, const isx_road *roads, int n, int s
   const isx_context::ChunkSet &cs = c->sets[slot];
   ISX_TRY(c, cudaMemcpyAsync(cs.ground, hg, sizeof(float) * 3 * H * n, cudaMemcpyHostToDevice, st));
   ISX_TRY(c, cudaMemcpyAsync(cs.vhor, hv, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  ISX_TRY(c, cudaEventRecord(c->ev_stage_done[stage], st));
   return ISX_OK;
 }
 
@@ -684,8 +693,10 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, cudaMemcpy(d_tmp, m.inverse_height.data(), sizeof(float) * (H + 1), cudaMemcpyHostToDevice));
   b.inverse_height = d_tmp;
 
-  ISX_TRY(h, cudaMallocHost(&h->h_ground, sizeof(float) * 2 * ch * 3 * H));
-  ISX_TRY(h, cudaMallocHost(&h->h_vhor, sizeof(int) * 2 * ch));
+  ISX_TRY(h, cudaMallocHost(&h->h_ground, sizeof(float) * kStageSlots * ch * 3 * H));
+  ISX_TRY(h, cudaMallocHost(&h->h_vhor, sizeof(int) * kStageSlots * ch));
+  for (int i = 0; i < kStageSlots; i++) ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_stage_done[i], cudaEventDisableTiming));
+  h->stage_next = 0;
   h->road_cache.clear();
   h->overlap_tables = true;
   if (const char *e = std::getenv("ISX_OVERLAP_TABLES")) h->overlap_tables = std::atoi(e) != 0;
@@ -703,6 +714,10 @@ int isx_finish(isx_handle h) {
   h->allocations.clear();
   cudaFreeHost(h->h_ground);
   cudaFreeHost(h->h_vhor);
+  for (int i = 0; i < kStageSlots; i++) {
+    if (h->ev_stage_done[i]) cudaEventDestroy(h->ev_stage_done[i]);
+    h->ev_stage_done[i] = nullptr;
+  }
   for (int i = 0; i < 2; i++) {
     isx_context::ResultSet &R = h->rs[i];
     if (R.allocated) {
@@ -888,8 +903,6 @@ int isx_compute(isx_handle h, int pairwise, isx_section *sections, isx_frame_met
   if (!h->single_has_road) return fail(h, ISX_ERR_INVALID_ARGUMENT, "SetRoadParameters has not been called");
   if (int rc = no_batches_in_flight(h)) return rc;
   const int32_t *seg = d_segmentation_local ? d_segmentation_local : h->d_single_seg;
-  // slot 0's pinned road-table staging may still be the source of a copy a device batch has queued
-  ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[0]));
   if (int rc = begin_batch(h)) return rc;
   h->direct_sections = device_view_of(sections);
   const bool direct = h->direct_sections != nullptr;
@@ -947,8 +960,6 @@ int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_d
   if (int rc = begin_batch(h)) return rc;
   for (int first = 0; first < n; first += h->chunk) {
     const int cn = (n - first) < h->chunk ? (n - first) : h->chunk;
-    // the pinned ground staging half must not be rewritten while its copy is in flight
-    ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[slot]));
     if (int rc = enqueue_chunk(h, pairwise != 0, first, cn, d_disparity + first * hw, d_segmentation + first * se,
                                roads + first, slot))
       return rc;
@@ -1029,9 +1040,8 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
     cn = (n - first) < h->chunk ? (n - first) : h->chunk;
     // a short first chunk when nothing is running: its copy is the only one that no kernel hides
     if (first == 0 && pipeline_idle && n > h->chunk && h->chunk >= 8) cn = h->chunk / 4;
-    // H2D of this chunk on the copy stream, once the kernels that last read this slot are done (the host waits too:
-    // the pinned staging of the road tables is rewritten next) and the emission that last read the chunk set
-    ISX_TRY(h, cudaEventSynchronize(h->ev_in_free[slot]));
+    // H2D of this chunk on the copy stream, once the kernels that last read this input slot are done and the emission
+    // that last read the chunk set (device-side waits: the host thread runs ahead)
     ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_in_free[slot], 0));
     ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_emit_done[slot], 0));
     auto mark_h2d = [&]() {
