@@ -682,8 +682,12 @@ int isx_initialize(isx_handle h, int max_batch) {
     std::vector<float> t(D * Dp, 0.0f);
     for (size_t fn = 0; fn < D; fn++)
       for (size_t dis = 0; dis < D; dis++) t[dis * Dp + fn] = m.obj_cost_lut[fn * D + dis];
-    ISX_TRY(h, dev_alloc(h, &d_tmp, D * Dp));
-    ISX_TRY(h, cudaMemcpy(d_tmp, t.data(), sizeof(float) * D * Dp, cudaMemcpyHostToDevice));
+    // object_lut_kernel addresses the table with 32-bit arithmetic on one upper address word: keep it inside one
+    // 4 GB window (room for two copies; the second cannot straddle if the first does)
+    ISX_TRY(h, dev_alloc(h, &d_tmp, 2 * D * Dp));
+    const unsigned long long a0 = (unsigned long long)d_tmp, bytes = sizeof(float) * D * Dp;
+    if (((a0 ^ (a0 + bytes - 1)) >> 32) != 0) d_tmp += D * Dp;
+    ISX_TRY(h, cudaMemcpy(d_tmp, t.data(), bytes, cudaMemcpyHostToDevice));
     b.obj_cost_lut_t = d_tmp;
   }
   ISX_TRY(h, dev_alloc(h, &d_tmp, D));

@@ -330,6 +330,20 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
 constexpr int kLutWarps = 4;
 constexpr int kLutThreads = kLutWarps * 32;
 
+// 32-bit address arithmetic for the two address streams of the kernel (the same trick as the DP's LUT gathers,
+// dp.cu): the transposed cost table (64 KB) and one column of the object LUT (< 4 GB, never straddling a multiple of
+// 4 GB: lut_column_address) each keep ONE upper address word, so an address costs one IMAD / IADD instead of the
+// five instructions of a 64-bit multiply-add (the first version spent 8 instructions per gather, 5 per store).
+__device__ __forceinline__ float ldg_lo_hi(unsigned lo, unsigned hi) {
+  float r;
+  asm("{\n\t.reg .b64 a;\n\tmov.b64 a, {%1, %2};\n\tld.global.nc.f32 %0, [a];\n\t}" : "=f"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void stg_lo_hi(unsigned lo, unsigned hi, float v) {
+  asm volatile("{\n\t.reg .b64 a;\n\tmov.b64 a, {%0, %1};\n\tst.global.f32 [a], %2;\n\t}" ::"r"(lo), "r"(hi), "f"(v)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(kLutThreads)
 object_lut_kernel(const float *__restrict__ joined, const float *__restrict__ cost_t,
                   float *__restrict__ object_lut, KParams p) {
@@ -352,10 +366,17 @@ object_lut_kernel(const float *__restrict__ joined, const float *__restrict__ co
   __syncthreads();
   const int fn0 = (blockIdx.y * kLutWarps + warp) * 32;
   if (fn0 >= D) return;
-  float *lut_col = reinterpret_cast<float *>(lut_column_address(
-      (unsigned long long)object_lut, (size_t)f * C + col, p.lut_cols, (size_t)D * p.lut_stride * 4));
-  const float *cost_fn = cost_t + fn0 + lane;  // column fn of the transposed table (padded, always in range)
+  const unsigned long long lut_addr = lut_column_address((unsigned long long)object_lut, (size_t)f * C + col,
+                                                         p.lut_cols, (size_t)D * p.lut_stride * 4);
+  const unsigned lut_hi = (unsigned)(lut_addr >> 32);
+  const unsigned stride4 = (unsigned)p.lut_stride * 4u;
+  // column fn of the transposed table (padded to 32 columns, always in range); the table does not straddle 4 GB
+  // (isx_initialize checks), so its upper address word is that of its first byte
+  const unsigned long long cost_addr = (unsigned long long)(cost_t + fn0 + lane);
+  const unsigned cost_lo = (unsigned)cost_addr, cost_hi = (unsigned)(cost_addr >> 32);
+  const unsigned row4 = (unsigned)Dp * 4u;   // bytes per disparity row of the transposed table
   float(*tl)[33] = tile[warp];
+  const bool full = fn0 + 32 <= D;           // every row of the 32 x 32 tile exists (D is a multiple of 32)
   float carry = 0.0f;
   for (int i = 0; i < Hc; i += 32) {
     float x[32];
@@ -363,7 +384,10 @@ object_lut_kernel(const float *__restrict__ joined, const float *__restrict__ co
     const uint4 d0 = dq[0], d1 = dq[1];
     const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-    for (int r = 0; r < 32; r++) x[r] = __ldg(cost_fn + ((dw[r >> 2] >> (8 * (r & 3))) & 0xffu) * Dp);
+    for (int r = 0; r < 32; r++) {
+      const unsigned dis = __byte_perm(dw[r >> 2], 0u, 0x4440u | (unsigned)(r & 3));   // byte r & 3, zero-extended
+      x[r] = ldg_lo_hi(dis * row4 + cost_lo, cost_hi);
+    }
     x[0] = fadd(x[0], carry);
 #pragma unroll
     for (int j = 1; j < 32; j <<= 1) {
@@ -377,9 +401,20 @@ object_lut_kernel(const float *__restrict__ joined, const float *__restrict__ co
     __syncwarp();
     const int v = i + lane;
     if (v < H) {
+      unsigned lo = (unsigned)lut_addr + (unsigned)fn0 * stride4 + 4u * (unsigned)v;   // out[v] = LUT[fn][v + 1]
+      if (full) {
 #pragma unroll
-      for (int r = 0; r < 32; r++)
-        if (fn0 + r < D) lut_col[(size_t)(fn0 + r) * p.lut_stride + v] = tl[r][lane];  // out[v] = LUT[fn][v + 1]
+        for (int r = 0; r < 32; r++) {
+          stg_lo_hi(lo, lut_hi, tl[r][lane]);
+          lo += stride4;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+          if (fn0 + r < D) stg_lo_hi(lo, lut_hi, tl[r][lane]);
+          lo += stride4;
+        }
+      }
     }
   }
 }
