@@ -52,8 +52,16 @@ OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
 # summarised in profiles/r1j_{unary,pairwise}_b32.txt (width 8; no capture for width 4).
 # "tables" = join_columns + column_tables + object_lut kernels.
 NCU_CHUNK = 32
-NCU_SOURCE = "profiles/r2_*_b32.txt"
-NCU_TRAFFIC = {}   # (mode, column_step) -> dict(dp=bytes, tables=bytes); filled from the round's ncu captures
+NCU_SOURCE = "profiles/r2b_*_b32.txt"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of a 32-frame chunk, from the `ncu --set full` captures
+# summarised in profiles/r2b_{unary,pairwise}_b32.txt (width 8; no capture for width 4).
+# "tables" = join_columns + (frame_tables) + column_tables + object_lut kernels.
+NCU_TRAFFIC = {
+    ("unary", 8): dict(dp=(1.4432 + 0.1301) * 1e9,     # dp_unary_pruned_kernel
+                       tables=(0.2685 + 0.0269 + 0.1439 + 1.0601 + 0.0337 + 4.2362) * 1e9),
+    ("pairwise", 8): dict(dp=(7.1209 + 0.6449) * 1e9,  # dp_pairwise_walk_kernel
+                          tables=(0.2685 + 0.0269 + 0.0001 + 0.1439 + 1.0601 + 0.0337 + 4.2362) * 1e9),
+}
 
 
 def measured_peaks():
