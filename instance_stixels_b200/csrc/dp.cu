@@ -987,6 +987,9 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records_b,
 #ifndef ISX_WALK_CTAS
 #define ISX_WALK_CTAS 4
 #endif
+#ifndef ISX_WALK_WARPS_PER_SM
+#define ISX_WALK_WARPS_PER_SM 16   // one-warp CTAs per SM the register budget of the walk kernel aims at (128 registers)
+#endif
 #ifndef ISX_PAIRWISE_WALK_DEFAULT
 #define ISX_PAIRWISE_WALK_DEFAULT 1
 #endif
@@ -1026,7 +1029,7 @@ __device__ __forceinline__ float object_prior_floor(const RowInfo &q, bool groun
 }
 
 template <bool HAS_INVALID, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 16 : WARPS == kDpWarps ? ISX_WALK_CTAS : 2)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? ISX_WALK_WARPS_PER_SM : WARPS == kDpWarps ? ISX_WALK_CTAS : 2)
 dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
                         const float *__restrict__ object_lut, const float *__restrict__ stat,
                         const float *__restrict__ ground, float *__restrict__ pm_out, float *__restrict__ qrows,
