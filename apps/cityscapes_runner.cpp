@@ -44,6 +44,7 @@ struct Options {
     StixelConfig config;  // everything that does not depend on the frame
     // extensions (not in the reference's CLI): --batch B frames per batched call, --gpus G GPUs of this box
     int batch = 1, gpus = 1;
+    int replicate = 1;   // --replicate K (measurement only): the timed call streams the loaded frames K times
 };
 
 bool parse_options(int argc, char** argv, Options* o) {
@@ -51,8 +52,8 @@ bool parse_options(int argc, char** argv, Options* o) {
     std::vector<char*> pos;
     for (int i = 0; i < argc; i++) {
         const std::string a(argv[i]);
-        if ((a == "--batch" || a == "--gpus") && i + 1 < argc) {
-            (a == "--batch" ? o->batch : o->gpus) = std::max(1, std::atoi(argv[++i]));
+        if ((a == "--batch" || a == "--gpus" || a == "--replicate") && i + 1 < argc) {
+            (a == "--batch" ? o->batch : a == "--gpus" ? o->gpus : o->replicate) = std::max(1, std::atoi(argv[++i]));
             continue;
         }
         pos.push_back(argv[i]);
@@ -328,7 +329,8 @@ int run_batched(const Options& opt) {
             }
         }
         if (group.empty()) continue;
-        const int n = (int)group.size();
+        const int loaded = (int)group.size();
+        const int n = loaded * opt.replicate;
         StixelConfig cfg = opt.config;
         cfg.rows = group[0].rows;
         cfg.cols = group[0].cols;
@@ -343,9 +345,10 @@ int run_batched(const Options& opt) {
         Pinned<int32_t> h_seg((size_t)n * se);
         std::vector<Stixels::Road> roads;
         for (int f = 0; f < n; f++) {
-            std::copy(disp[(size_t)f].begin(), disp[(size_t)f].end(), h_disp.p + (size_t)f * hw);
-            std::copy(seg[(size_t)f].begin(), seg[(size_t)f].end(), h_seg.p + (size_t)f * se);
-            roads.push_back(group[(size_t)f].road);
+            const size_t src = (size_t)(f % loaded);
+            std::copy(disp[src].begin(), disp[src].end(), h_disp.p + (size_t)f * hw);
+            std::copy(seg[src].begin(), seg[src].end(), h_seg.p + (size_t)f * se);
+            roads.push_back(group[src].road);
         }
         const size_t per_frame = (size_t)pool.GetRealCols() * pool.GetMaxSections();
         Pinned<Section> sections((size_t)n * per_frame);   // pinned: the device writes the Sections into it itself
@@ -362,7 +365,7 @@ int run_batched(const Options& opt) {
         total_ms += ms;
         total_frames += (size_t)n;
         const size_t per = per_frame;
-        for (int f = 0; f < n; f++) {
+        for (int f = 0; f < loaded; f++) {
             const LoadedFrame& lf = group[(size_t)f];
             Stixels::SaveStixels(sections.p + (size_t)f * per, StixelsPool::MapOf(records, offsets, f), lf.road.alpha_ground,
                                  lf.rows - 1 - lf.road.vhor, pool.GetRealCols(), pool.GetMaxSections(),

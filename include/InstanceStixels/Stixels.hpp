@@ -17,6 +17,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <utility>
 #include <vector>
@@ -347,15 +348,22 @@ public:
     void ComputeBatch(bool pairwise, int n, const pixel_t* disparity, const int32_t* segmentation, const Road* roads,
                       Section* sections, std::vector<isx_instance>* records, std::vector<int32_t>* offsets) {
         const size_t per = (size_t)GetRealCols() * GetMaxSections();
-        if (records) records->resize((size_t)n * per);
+        // Worst-case capacity (every stixel an instance stixel) as UNINITIALISED scratch: pages that are never written
+        // cost nothing, while value-initialising a vector of this size would take longer than the GPU work.
+        if (records && scratch_cap_ < (size_t)n * per) {
+            scratch_.reset(new isx_instance[(size_t)n * per]);
+            scratch_cap_ = (size_t)n * per;
+        }
+        std::vector<int32_t> local_offsets;
+        if (records && !offsets) offsets = &local_offsets;
         if (offsets) offsets->resize((size_t)n + 1);
         if (isx_pool_compute_host(p_, pairwise ? 1 : 0, n, disparity, segmentation, roads,
-                                  reinterpret_cast<isx_section*>(sections), records ? records->data() : nullptr,
-                                  records ? (int)records->size() : 0, offsets ? offsets->data() : nullptr) != ISX_OK) {
+                                  reinterpret_cast<isx_section*>(sections), records ? scratch_.get() : nullptr,
+                                  records ? (int)scratch_cap_ : 0, offsets ? offsets->data() : nullptr) != ISX_OK) {
             std::cerr << "instance_stixels_b200: " << isx_pool_last_error(p_) << std::endl;
             std::exit(1);
         }
-        if (records && offsets) records->resize((size_t)(*offsets)[(size_t)n]);
+        if (records) records->assign(scratch_.get(), scratch_.get() + (*offsets)[(size_t)n]);
     }
     static InstanceMap MapOf(const std::vector<isx_instance>& records, const std::vector<int32_t>& offsets, int frame) {
         InstanceMap m;
@@ -367,6 +375,8 @@ public:
 private:
     isx_pool_handle p_ = nullptr;
     StixelConfig cfg_;
+    std::unique_ptr<isx_instance[]> scratch_;
+    size_t scratch_cap_ = 0;
     static isx_config to_isx(const StixelConfig& c) { return Stixels::ToIsxConfig(c); }
 };
 

@@ -14,7 +14,8 @@ import write_h5
 from instance_stixels_b200 import synth
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--frames", type=int, default=128)
+ap.add_argument("--frames", type=int, default=64)
+ap.add_argument("--replicate", type=int, default=10, help="the timed call streams the loaded frames this many times")
 ap.add_argument("--mode", default="unary")
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--gpus", type=int, default=1)
@@ -37,13 +38,13 @@ pre = synth.preset(a.mode, rows, cols, 8)
 pairwise = int(a.mode == "pairwise")
 args = [os.path.join(ROOT, "apps", "cityscapes_runner"), d, "128", repr(pre["segmentation_weight"]), repr(pre["instance_weight"]),
         repr(pre["disparity_weight"]), str(pairwise), "8", repr(pre["eps"]), str(pre["min_pts"]), str(pre["size_filter"]),
-        "--batch", str(a.batch), "--gpus", str(a.gpus)]
+        "--batch", str(a.batch), "--gpus", str(a.gpus), "--replicate", str(a.replicate)]
 env = dict(os.environ, ISX_ALLOW_1024="1")
 p = subprocess.run(args, capture_output=True, text=True, env=env)
 line = [l for l in p.stdout.splitlines() if l.startswith("It took an average")]
 done = [l for l in p.stdout.splitlines() if l.startswith("Done.")]
 m = re.search(r"([0-9.]+) milliseconds, ([0-9.]+) fps", line[0]) if line else None
-print(json.dumps(dict(mode=a.mode, frames=a.frames, batch=a.batch, gpus=a.gpus, runner_fps=float(m.group(2)) if m else None,
+print(json.dumps(dict(mode=a.mode, frames=a.frames, replicate=a.replicate, batch=a.batch, gpus=a.gpus, runner_fps=float(m.group(2)) if m else None,
                       runner_ms_per_frame=float(m.group(1)) if m else None, done_line=done[-1] if done else None,
                       stixels_files=len(os.listdir(os.path.join(d, "stixels"))), rc=p.returncode, stderr=p.stderr[-300:])))
 subprocess.run(["rm", "-rf", d])
