@@ -414,7 +414,9 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
     tab_ms = stages["join"][0] + stages["column_tables"][0]
     tab_launches = max(stages["join"][1], 1)
     tab_avg_s = tab_ms * 1e-3 / tab_launches
-    ncu = NCU_TRAFFIC.get((wl["mode"], wl["step"])) if chunk == NCU_CHUNK else None
+    ncu = NCU_TRAFFIC.get((wl["mode"], wl["step"]))
+    if ncu and ncu.get("chunk", NCU_CHUNK) != chunk:
+        ncu = None
     dp_alg_bytes = (C_ * 128 * H * 4 + C_ * rec_words * rec_stride * 4 + C_ * H * 16) * chunk
     fps = world * B / (ms_max * 1e-3 / steps)
     out.update(

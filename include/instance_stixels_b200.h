@@ -329,7 +329,8 @@ int isx_get_stage_times(isx_handle h, double *ms, long *chunks, int n_stages, in
  * grouping begin | emission end).  Returns the number of chunks written (or a negative status); call it before
  * isx_get_stage_times, which consumes the same events. */
 int isx_get_chunk_trace(isx_handle h, double *ms, int max_chunks);
-/* Frames per kernel launch (batches are cut into chunks of this many frames). */
+/* Frames per kernel launch of the last batch (batches are cut into chunks: 32 frames in unary mode, 64 in pairwise
+ * mode, ISX_CHUNK overrides). */
 /* DP work since isx_initialize in units of 32 x 32 cells: `total` = every (tile, chunk) pair of every column,
  * `evaluated` = those the kernels actually walked (the unary DP prunes chunks that provably cannot win). */
 int isx_get_dp_units(isx_handle h, unsigned long long *evaluated, unsigned long long *total);

@@ -49,7 +49,9 @@ struct isx_context {
   bool initialized = false;
   isx::HostModel model;
   isx::KParams kp{};
-  int max_batch = 0, chunk = 0;
+  int max_batch = 0, chunk = 0;   // chunk: frames the intermediates hold = frames per pairwise launch
+  int chunk_unary = 0;            // frames per unary launch
+  int last_launch_frames = 0;     // of the last enqueued batch (isx_chunk_frames)
   std::string last_error;
 
   // s_tables: join + table build (HBM-bound), s_compute: the DP (issue-bound), s_emit: backtracking, grouping, packing
@@ -589,14 +591,17 @@ int isx_initialize(isx_handle h, int max_batch) {
   const size_t H = kp.rows, W = kp.cols, C = kp.realcols, D = kp.max_dis;
   if (C == 0) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no stixel columns");
   h->max_batch = max_batch;
-  // Frames per launch.  32 frames = 8192 column CTAs = 11-14 waves of the DP: every launch ends with a partly
-  // filled wave, and the next kernel of the stream only starts when the last CTA is done, so few large launches
-  // beat many small ones (resident: 16 -> 32 -> 64 frames = 1997 -> 2049 -> 2092 frames/s unary); but the
-  // copies of a host batch only overlap kernels of OTHER chunks, and at 64 the streaming path loses more than the
-  // launches gain (e2e 1954 -> 1971 -> 1907).  Intermediates take about 7 GB at 32 frames, width 8.
-  int chunk = 32;
-  if (const char *e = std::getenv("ISX_CHUNK")) chunk = std::atoi(e) > 0 ? std::atoi(e) : chunk;
+  // Frames per launch.  Every DP launch ends with a partly filled wave, so few large launches beat many small
+  // ones; but the copies of a host batch only overlap kernels of OTHER chunks.  Measured (B200, 64-frame batches,
+  // frames/s resident | end to end): unary 16 / 32 / 64 frames per launch = 7095 | 4614, 7999 | 4628, 8083 | 4525;
+  // pairwise 2691 | 2473, 2940 | 2817, 3041 | 2855 -- the pairwise walk kernel runs ONE warp per column, 2368 at a
+  // time: 32 frames are 3.46 waves of them, 64 frames 6.9.  So the buffers hold 64 frames (two sets, about 23 GB at
+  // width 8) and unary launches take 32 of them.
+  int chunk = 64, chunk_unary = 32;
+  if (const char *e = std::getenv("ISX_CHUNK")) chunk = chunk_unary = std::atoi(e) > 0 ? std::atoi(e) : chunk;
   h->chunk = chunk < max_batch ? chunk : max_batch;
+  h->chunk_unary = chunk_unary < h->chunk ? chunk_unary : h->chunk;
+  h->last_launch_frames = h->chunk_unary;
   h->kp.lut_cols = h->chunk * (int)C;
   const size_t ch = h->chunk, MB = max_batch;
   const size_t cap = C * kMaxSections;
@@ -962,8 +967,10 @@ int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_d
   const size_t hw = (size_t)h->kp.rows * h->kp.cols, se = seg_elems(h);
   int slot = h->host_slot;  // keeps alternating across batches (see enqueue_host_batch)
   if (int rc = begin_batch(h)) return rc;
-  for (int first = 0; first < n; first += h->chunk) {
-    const int cn = (n - first) < h->chunk ? (n - first) : h->chunk;
+  const int chunk = pairwise ? h->chunk : h->chunk_unary;
+  h->last_launch_frames = chunk;
+  for (int first = 0; first < n; first += chunk) {
+    const int cn = (n - first) < chunk ? (n - first) : chunk;
     if (int rc = enqueue_chunk(h, pairwise != 0, first, cn, d_disparity + first * hw, d_segmentation + first * se,
                                roads + first, slot))
       return rc;
@@ -1039,11 +1046,13 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
   // second-to-last chunk of the batch before it.
   int slot = h->host_slot;
   int cn = 0;
+  const int chunk = pairwise ? h->chunk : h->chunk_unary;
+  h->last_launch_frames = chunk;
   const bool pipeline_idle = h->submitted == h->waited;
   for (int first = 0; first < n; first += cn) {
-    cn = (n - first) < h->chunk ? (n - first) : h->chunk;
+    cn = (n - first) < chunk ? (n - first) : chunk;
     // a short first chunk when nothing is running: its copy is the only one that no kernel hides
-    if (first == 0 && pipeline_idle && n > h->chunk && h->chunk >= 8) cn = h->chunk / 4;
+    if (first == 0 && pipeline_idle && n > chunk && chunk >= 8) cn = chunk / 4;
     // H2D of this chunk on the copy stream, once the kernels that last read this input slot are done and the emission
     // that last read the chunk set (device-side waits: the host thread runs ahead)
     ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_in_free[slot], 0));
@@ -1402,7 +1411,7 @@ int isx_get_dp_units(isx_handle h, unsigned long long *evaluated, unsigned long 
   if (total) *total = h->dp_units_total;
   return ISX_OK;
 }
-int isx_chunk_frames(isx_handle h) { return (h && h->initialized) ? h->chunk : 0; }
+int isx_chunk_frames(isx_handle h) { return (h && h->initialized) ? h->last_launch_frames : 0; }
 int isx_instance_capacity(isx_handle h) { return (h && h->initialized) ? h->inst_cap : 0; }
 
 }  // extern "C"
