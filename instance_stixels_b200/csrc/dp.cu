@@ -976,12 +976,21 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records_b,
 //                    lower bound of its cells does not already exceed the minima carried so far in some row;
 //                (2) the diagonal unit (t, t) -- the wavefront -- by warp 0, which finalises the rows of the tile,
 //                    writes their transition records Q[vB] for all later tiles and the smallest priors of the chunk.
-// Bound of unit (t, j) for row vT (the slots separately):
-//     prior >= smallest prior of any row of chunk j (exactly what the cells use for the ground/sky slot, the
-//              smallest of the candidate priors for the object slot),
-//     seg   >= class sums over the shortest segment (last row of chunk j .. vT), instance term >= -2^-19*iw*sum(means^2),
-//     data  >= rows * min(0, smallest per-row cost),
-// combined with the cell's own monotone float operations, minus the slack of prune_bound().  Minima are merged
+// Bound of unit (t, j) for row vT (the slots separately) -- per class, because the cost of a cell is a minimum over
+// classes of terms that SEPARATE into a part of the top row and a part of the bottom row:
+//     cost_o(vB, vT) >= min_c [ sw * (w_c * dO + dP_c) ] + kmin_o(vB) + dw * data_lb       (dX = X(vT+1) - X(vB))
+//                     = min_c [ F_c(vT+1) + (kmin_o(vB) - F_c(vB)) ] + ...,   F_c(v) = sw * (w_c * O(v) + P_c(v)),
+//   with P_c the class prefix, O the squared-offset prefix (w_c = iw for the non-instance classes; the instance
+//   classes carry the variance term instead, >= -2^-19 * iw * sum(means^2)), kmin_o(vB) the smallest object prior any
+//   cell of row vB can get.  So the diagonal of chunk j leaves M_c[j] = min over its rows of (kmin_o(vB) - F_c(vB)),
+//   16 numbers, and a later tile tests  min_c (F_c(vT+1) + M_c[j])  against its carried minima.  The ground / sky
+//   slot is even exact: its prior k_gs(vB) and its data term (a prefix difference) separate too, classes {road,
+//   sidewalk} or {sky}.
+// r1 bounded the class sums by those of the SHORTEST segment into the chunk and the prior by the chunk's smallest:
+// loose by a whole chunk of accumulated cost (hundreds of units), while the candidates of a column lie more than 5
+// units apart (measured: with an exact bound 0.8 off-diagonal units per tile are needed, the old bound let 5.5
+// through).  The envelopes are floats of magnitude up to 1e6; the slack 2^-21 * (|F| + |M|) covers their <= 6
+// roundings (relative 2^-24 each) with a factor 2, the data terms keep prune_bound()'s slack.  Minima are merged
 // lexicographically by (cost, vB): the reference's "lowest vB wins ties" whatever the order of evaluation.
 // ---------------------------------------------------------------------------
 #ifndef ISX_WALK_CTAS
@@ -994,9 +1003,14 @@ dp_unary_pruned_kernel(const uint32_t *__restrict__ records_b,
 #define ISX_PAIRWISE_WALK_DEFAULT 1
 #endif
 
+// envelope words per chunk: 0..7 classes 2..9 | 8..15 classes 11..18 | 16, 17 road, sidewalk (ground slot) |
+// 18 sky (sky slot) | 19 largest finite |entry| (scale of the slack)
+constexpr int kMWords = 20;
+constexpr float kEnvErr = 4.76837158203125e-07f;   // 2^-21
+
 struct WalkLayout {
   int nt;
-  size_t off_stage, off_bars, off_q, off_sst, off_odr, off_merge, off_cmin, off_qnext, total;
+  size_t off_stage, off_bars, off_q, off_sst, off_odr, off_merge, off_mtab, off_qnext, total;
   __host__ __device__ WalkLayout(int H, int D, int warps) {
     nt = (H + kChunk - 1) / kChunk;
     size_t o = 0;
@@ -1007,7 +1021,7 @@ struct WalkLayout {
     off_sst = o; o += (size_t)kSstWords * 4;
     off_odr = o; o += (size_t)((D + 3) & ~3) * 4;
     off_merge = o; o += (size_t)warps * 32 * 16;
-    off_cmin = o; o += (size_t)3 * nt * 4;  // per chunk: smallest object prior | ground prior | sky prior
+    off_mtab = o; o += (size_t)nt * kMWords * 4;  // per chunk: the class envelopes M_c[j] (see the kernel's header)
     o = (o + 15) & ~(size_t)15;
     off_qnext = o; o += (size_t)kDynWords * 4;
     total = (o + 15) & ~(size_t)15;
@@ -1055,8 +1069,7 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
   float *sst = reinterpret_cast<float *>(smem_raw + L.off_sst);
   float *odr = reinterpret_cast<float *>(smem_raw + L.off_odr);
   float4 *merge = reinterpret_cast<float4 *>(smem_raw + L.off_merge);
-  float *cmin_o = reinterpret_cast<float *>(smem_raw + L.off_cmin);
-  float *cmin_g = cmin_o + nt, *cmin_s = cmin_g + nt;
+  float *mtab = reinterpret_cast<float *>(smem_raw + L.off_mtab);
   float *qnext = reinterpret_cast<float *>(smem_raw + L.off_qnext);
 
   DpConsts c;
@@ -1134,6 +1147,8 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
     const float dneg_gs = fmul(c.dw, fmul(nmaxf, fminf(vTc < vhor ? lb_g : lb_s, 0.0f)));
     const float dslack_o = fmul(c.dw, fmul(fmul(nmaxf, cmax_o), kDataErr));
     const float dslack_gs = fmul(c.dw, fmul(fmul(nmaxf, vTc < vhor ? cmax_g : cmax_s), kDataErr));
+    const float nicA = fmul((float)(int)A[kRecOff], c.iw);   // iw * O(vT + 1)
+    (void)dneg_gs;
 
     // ================= (1) the chunks below the diagonal, nearest first, interleaved over the warps =================
     Best carried{inf, inf, 0, 0};
@@ -1141,28 +1156,43 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
       const int vb0 = j * kChunk;
       bool skip = false;
       if (prune_ok) {
-        const int vbm = vb0 + kChunk - 1;  // chunks below the diagonal are full
-        const uint4 *b4 = reinterpret_cast<const uint4 *>(recb + (size_t)vbm * kRecBWords);
-        uint32_t Bl[20];
+        const float4 *M4 = reinterpret_cast<const float4 *>(mtab + j * kMWords);
+        float M[kMWords];
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-          const uint4 q4 = __ldg(b4 + k);
-          Bl[4 * k] = q4.x; Bl[4 * k + 1] = q4.y; Bl[4 * k + 2] = q4.z; Bl[4 * k + 3] = q4.w;
+        for (int k = 0; k < kMWords / 4; k++) {
+          const float4 m4 = M4[k];
+          M[4 * k] = m4.x; M[4 * k + 1] = m4.y; M[4 * k + 2] = m4.z; M[4 * k + 3] = m4.w;
         }
-        int l_ni = (int)(A[2] - Bl[2]);
+        // object slot: min over the classes of F_c(vT + 1) + M_c[j]
+        float lbo = inf, fmax_o = 0.0f;
 #pragma unroll
-        for (int k = 3; k < 10; k++) l_ni = min(l_ni, (int)(A[k] - Bl[k]));
-        int l_in = (int)(A[11] - Bl[11]);
+        for (int k = 2; k < 10; k++) {
+          const float F = fmul(c.sw, fadd(nicA, (float)(int)A[k]));
+          fmax_o = fmaxf(fmax_o, F);
+          lbo = fminf(lbo, fadd(F, M[k - 2]));
+        }
 #pragma unroll
-        for (int k = 12; k < 19; k++) l_in = min(l_in, (int)(A[k] - Bl[k]));
-        const int l_g = min((int)(A[0] - Bl[0]), (int)(A[1] - Bl[1]));
-        const int l_s = (int)(A[kSkyClass] - Bl[kSkyClass]);
-        const float seg_o_lb = fminf((float)l_ni, fadd(ic_lb, (float)l_in));
-        const float pr_o = cmin_o[j];
-        const float lbo = prune_bound(ffma(seg_o_lb, c.sw, fadd(dneg_o, pr_o)), dneg_o, pr_o, dslack_o);
-        const float seg_gs_lb = (float)(vTc < vhor ? l_g : l_s);
-        const float pr_gs = vTc < vhor ? cmin_g[j] : cmin_s[j];
-        const float lbgs = prune_bound(ffma(seg_gs_lb, c.sw, fadd(dneg_gs, pr_gs)), dneg_gs, pr_gs, dslack_gs);
+        for (int k = 11; k < 19; k++) {
+          const float F = fmul(c.sw, fadd(ic_lb, (float)(int)A[k]));
+          fmax_o = fmaxf(fmax_o, F);
+          lbo = fminf(lbo, fadd(F, M[8 + k - 11]));
+        }
+        if (lbo < inf) lbo = prune_bound(fadd(lbo, dneg_o), dneg_o, 0.0f, ffma(fadd(fmax_o, M[19]), kEnvErr, dslack_o));
+        // ground / sky slot of this lane's row
+        float lbgs = inf, fmax_gs = 0.0f;
+        if (vTc < vhor) {
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const float F = ffma(c.dw, f_(A[kRecGround]), fmul(c.sw, fadd(nicA, (float)(int)A[k])));
+            fmax_gs = fmaxf(fmax_gs, fabsf(F));
+            lbgs = fminf(lbgs, fadd(F, M[16 + k]));
+          }
+        } else {
+          const float F = ffma(c.dw, f_(A[kRecSky]), fmul(c.sw, fadd(nicA, (float)(int)A[kSkyClass])));
+          fmax_gs = fabsf(F);
+          lbgs = fadd(F, M[18]);
+        }
+        if (lbgs < inf) lbgs = prune_bound(lbgs, 0.0f, 0.0f, ffma(fadd(fmax_gs, M[19]), kEnvErr, dslack_gs));
         const bool lane_done = !row_ok || ((lbo > carried.o || lbo == inf) && (lbgs > carried.gs || lbgs == inf));
         skip = __all_sync(full_mask, lane_done);
       }
@@ -1233,14 +1263,6 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
         if (lane < kDynWords) qs_slot[lane] = qnext[lane];
         __syncwarp();
       }
-      // smallest priors of the rows of this chunk (for the bounds of later tiles)
-      float mn_o = inf, mn_g = inf, mn_s = inf;
-      auto note_row = [&](const RowInfo &q, int vB) {
-        const bool ground_side = vB - 1 < vhor;
-        mn_o = fminf(mn_o, object_prior_floor(q, ground_side, c.pw));
-        if (ground_side) mn_g = fminf(mn_g, q.gs_k);
-        else mn_s = fminf(mn_s, q.gs_k);
-      };
       auto finish_row = [&](int vB, int src_lane, float hi_d, float hi_v) {
         const float c_gs = __shfl_sync(full_mask, best.gs, src_lane), c_o = __shfl_sync(full_mask, best.o, src_lane);
         const int o_vb = __shfl_sync(full_mask, best.vb_o, src_lane);
@@ -1270,10 +1292,8 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
             store_row_info(qs_slot + k * kDynWords, q);
             pm_col[vB] = q.pm;
           }
-          note_row(q, vB);
         } else if (vB > 0) {
           q = load_row_info(qs_slot);
-          note_row(q, vB);
         }
         float cost_gs, cost_o;
         if (vB == 0) {
@@ -1286,11 +1306,6 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
         if (live && cost_gs < best.gs) { best.gs = cost_gs; best.vb_gs = vB; }
         if (live && cost_o < best.o) { best.o = cost_o; best.vb_o = vB; lo_d = ps_d; lo_v = ps_v; }
         b_cur = b_next;
-      }
-      if (t == 0) {
-        // the first-segment priors of vB = 0 (the smaller of the two object variants)
-        mn_g = fminf(mn_g, first_k_gs);
-        mn_o = fminf(mn_o, fmul(fadd(fadd(0.0f, p.rows_log), p.max_dis_log), c.pw));
       }
       // Q[vb0 + 32] for the next diagonal (row vb0 + 31 is final now)
       if (vb0 + kChunk < H) {
@@ -1310,7 +1325,55 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
         float4 *dstq = reinterpret_cast<float4 *>(qg + (size_t)(vb0 + lane) * kDynWords);
         if (lane < nsteps) { __stcg(dstq, srcq[0]); __stcg(dstq + 1, srcq[1]); __stcg(dstq + 2, srcq[2]); }
       }
-      if (lane == 0) { cmin_o[t] = mn_o; cmin_g[t] = mn_g; cmin_s[t] = mn_s; }
+      // ---- the class envelopes M_c[t] of this chunk for the bounds of the later tiles (header): lane = row vB ----
+      {
+        const int vBl = vb0 + lane;
+        const bool in_rows = lane < nsteps;
+        float kmin_o = inf, kgs = inf;
+        bool ground_side = true;
+        if (in_rows) {
+          if (vBl == 0) {
+            // the first-segment priors (:189-199), the smaller of the two object variants
+            kmin_o = fmul(fadd(fadd(0.0f, p.rows_log), p.max_dis_log), c.pw);
+            kgs = first_k_gs;
+          } else {
+            const RowInfo ql = load_row_info(qs_slot + lane * kDynWords);
+            ground_side = vBl - 1 < vhor;
+            kmin_o = object_prior_floor(ql, ground_side, c.pw);
+            kgs = ql.gs_k;
+          }
+        }
+        // the record of this lane's row of the staged chunk (per-lane rows: bank conflicts, once per tile)
+        const uint4 *b4 = reinterpret_cast<const uint4 *>(bchunk + lane * kRecBWords);
+        uint32_t Bw[20];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          const uint4 q4 = b4[k];
+          Bw[4 * k] = q4.x; Bw[4 * k + 1] = q4.y; Bw[4 * k + 2] = q4.z; Bw[4 * k + 3] = q4.w;
+        }
+        const uint4 gsw = b4[7];   // words 28 .. 31: ground and sky prefix
+        const float nicB = fmul((float)(int)Bw[kRecOff], c.iw);
+        float mabs = 0.0f;
+        auto publish = [&](int slot, float m) {
+          if (!in_rows) m = inf;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(full_mask, m, d));
+          if (m < inf) mabs = fmaxf(mabs, fabsf(m));
+          if (lane == 0) mtab[t * kMWords + slot] = m;
+        };
+#pragma unroll
+        for (int k = 2; k < 10; k++) publish(k - 2, fsub(kmin_o, fmul(c.sw, fadd(nicB, (float)(int)Bw[k]))));
+#pragma unroll
+        for (int k = 11; k < 19; k++) publish(8 + k - 11, fsub(kmin_o, fmul(c.sw, (float)(int)Bw[k])));
+        // ground slot candidates come from rows at/below the horizon, sky slot candidates from rows above it
+        const float fg0 = ffma(c.dw, f_(gsw.x), fmul(c.sw, fadd(nicB, (float)(int)Bw[0])));
+        const float fg1 = ffma(c.dw, f_(gsw.x), fmul(c.sw, fadd(nicB, (float)(int)Bw[1])));
+        const float fs = ffma(c.dw, f_(gsw.y), fmul(c.sw, fadd(nicB, (float)(int)Bw[kSkyClass])));
+        publish(16, ground_side ? fsub(kgs, fg0) : inf);
+        publish(17, ground_side ? fsub(kgs, fg1) : inf);
+        publish(18, ground_side ? inf : fsub(kgs, fs));
+        if (lane == 0) mtab[t * kMWords + 19] = mabs;
+      }
       my_units++;
     }
     __syncthreads();
