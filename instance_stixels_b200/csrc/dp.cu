@@ -1010,7 +1010,7 @@ constexpr float kEnvErr = 4.76837158203125e-07f;   // 2^-21
 
 struct WalkLayout {
   int nt;
-  size_t off_stage, off_bars, off_q, off_sst, off_odr, off_merge, off_mtab, off_qnext, total;
+  size_t off_stage, off_bars, off_q, off_sst, off_odr, off_merge, off_mtab, off_seed, off_qnext, total;
   __host__ __device__ WalkLayout(int H, int D, int warps) {
     nt = (H + kChunk - 1) / kChunk;
     size_t o = 0;
@@ -1023,6 +1023,7 @@ struct WalkLayout {
     off_merge = o; o += (size_t)warps * 32 * 16;
     off_mtab = o; o += (size_t)nt * kMWords * 4;  // per chunk: the class envelopes M_c[j] (see the kernel's header)
     o = (o + 15) & ~(size_t)15;
+    off_seed = o; o += (size_t)warps * (kRecBWords + kDynWords + 4) * 4 + 16;  // one B row + one Q row per warp | seeds
     off_qnext = o; o += (size_t)kDynWords * 4;
     total = (o + 15) & ~(size_t)15;
   }
@@ -1070,6 +1071,9 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
   float *odr = reinterpret_cast<float *>(smem_raw + L.off_odr);
   float4 *merge = reinterpret_cast<float4 *>(smem_raw + L.off_merge);
   float *mtab = reinterpret_cast<float *>(smem_raw + L.off_mtab);
+  int *seeds = reinterpret_cast<int *>(smem_raw + L.off_seed);                      // [2] argmin vB of the row below the tile
+  uint32_t *seed_row = reinterpret_cast<uint32_t *>(smem_raw + L.off_seed + 16) + warp * (kRecBWords + kDynWords + 4);
+  float *seed_q = reinterpret_cast<float *>(seed_row + kRecBWords);
   float *qnext = reinterpret_cast<float *>(smem_raw + L.off_qnext);
 
   DpConsts c;
@@ -1152,6 +1156,43 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
 
     // ================= (1) the chunks below the diagonal, nearest first, interleaved over the warps =================
     Best carried{inf, inf, 0, 0};
+    // Seeds: the row just below the tile is final, and the best segments of the tile's rows mostly start where ITS best
+    // segments start (the same region goes on).  Those two cells (one step each) give the carried minima a value to
+    // prune against before any unit is walked -- otherwise the nearest chunk is always evaluated.  They are cells of
+    // the column like any other, so the result does not depend on them.
+    if (prune_ok && t > 0) {
+      const int s0 = seeds[0], s1 = seeds[1];
+#pragma unroll 1
+      for (int si = 0; si < 2; si++) {
+        const int vB = si == 0 ? s0 : s1;
+        if ((si == 1 && s1 == s0) || vB < 0 || vB >= t * kChunk) continue;   // only candidates below the tile's own chunk
+        Best local{inf, inf, 0, 0};
+        __syncwarp();
+        seed_row[lane] = __ldg(recb + (size_t)vB * kRecBWords + lane);
+        if (lane < kDynWords) seed_q[lane] = __ldcg(qg + (size_t)vB * kDynWords + lane);
+        __syncwarp();
+        const float nf = (float)(vTc + 1 - vB);
+        if (vB == 0) {
+          // first segment, vB = 0 (:481-594)
+          const CellBase b = cell_base<true, 1, HAS_INVALID>(A, seed_row, ca, lutb, nf, c);
+          RowInfo q{};
+          const float first_k_o = fmul(fadd(fadd((vT <= vhor) ? kLn2 : 0.0f, p.rows_log), p.max_dis_log), c.pw);
+          float cost_gs, cost_o;
+          cell_finish<true, true, 1>(b, 0.0f, q, first_k_gs, first_k_o, c, cost_gs, cost_o);
+          if (cost_gs < local.gs) { local.gs = cost_gs; local.vb_gs = 0; }
+          if (cost_o < local.o) { local.o = cost_o; local.vb_o = 0; }
+        } else {
+          const unsigned cbs = lutb + 4u * (unsigned)(vB - 1);
+          if (vB > vhor)
+            dp_step<true, 0, false, HAS_INVALID, 0>(A, seed_row, ca, cbs, nullptr, nullptr, 0, seed_q, vB, 0, lane, nf, c, local);
+          else if (t * kChunk >= vhor)
+            dp_step<true, 3, false, HAS_INVALID, 0>(A, seed_row, ca, cbs, nullptr, nullptr, 0, seed_q, vB, 0, lane, nf, c, local);
+          else
+            dp_step<true, 1, false, HAS_INVALID, 0>(A, seed_row, ca, cbs, nullptr, nullptr, 0, seed_q, vB, 0, lane, nf, c, local);
+        }
+        merge_best(carried, local);
+      }
+    }
     for (int j = t - 1 - warp; j >= 0; j -= WARPS) {
       const int vb0 = j * kChunk;
       bool skip = false;
@@ -1318,6 +1359,16 @@ dp_pairwise_walk_kernel(const uint32_t *__restrict__ records_b,
         }
       }
       if (row_ok) store_best(out + vT, best);
+      {
+        // the seeds of the next tile: where the best segments of the tile's last row start
+        const int last = nsteps - 1;
+        const int so = __shfl_sync(full_mask, best.vb_o, last), sg = __shfl_sync(full_mask, best.vb_gs, last);
+        const float cg = __shfl_sync(full_mask, best.gs, last);
+        if (lane == 0) {
+          seeds[0] = so;
+          seeds[1] = cg < inf ? sg : -1;
+        }
+      }
       __syncwarp();
       // publish Q of the chunk for the later tiles: shared copy -> global (row k by lane k), and its smallest priors
       {
