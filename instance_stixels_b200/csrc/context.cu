@@ -128,6 +128,7 @@ struct isx_context {
   isx_section *batch_sections[2] = {nullptr, nullptr};  // the caller's padded array the wait expands into
   bool batch_direct[2] = {false, false};                // ... or that the device has already filled (mapped memory)
   isx_section *direct_sections = nullptr;               // device address of the caller's array for the batch being enqueued
+  bool results_stay_on_device = false;                  // set while a device batch is enqueued
   unsigned long long submitted = 0, waited = 0;       // tickets: batches [waited, submitted) are in flight
   unsigned long long dp_units_pairwise = 0;           // ... of which in pairwise mode (never pruned)
   unsigned long long dp_units_total = 0;              // 32 x 32-cell units of all DP launches so far
@@ -356,8 +357,10 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
     a.inst_out = R.d_inst + (size_t)first * c->inst_cap; a.inst_count_out = R.d_inst_count + first;
     a.inst_cap = c->inst_cap; a.cursors = R.d_cursors;
     a.h_padded = c->direct_sections ? c->direct_sections + (size_t)first * C * kMaxSections : nullptr;
-    a.h_sections = R.m_sections; a.h_sections_cap = R.sections_cap;
-    a.h_inst = R.m_inst; a.h_inst_cap = R.inst_cap;
+    // a device batch leaves its results on the device (isx_compute_batch_device): only the counts and descriptors
+    // cross the host link, a later fetch reads the padded device arrays (the frames are flagged like overflows)
+    a.h_sections = R.m_sections; a.h_sections_cap = c->results_stay_on_device ? 0 : R.sections_cap;
+    a.h_inst = R.m_inst; a.h_inst_cap = c->results_stay_on_device ? 0 : R.inst_cap;
     a.h_counts = R.m_counts + (size_t)first * C; a.h_frames = R.m_frames + first;
     launch_pack(kp, a, n, se);
   }
@@ -971,9 +974,11 @@ int isx_compute_batch_device(isx_handle h, int pairwise, int n, const float *d_d
   h->last_launch_frames = chunk;
   for (int first = 0; first < n; first += chunk) {
     const int cn = (n - first) < chunk ? (n - first) : chunk;
-    if (int rc = enqueue_chunk(h, pairwise != 0, first, cn, d_disparity + first * hw, d_segmentation + first * se,
-                               roads + first, slot))
-      return rc;
+    h->results_stay_on_device = true;
+    const int erc = enqueue_chunk(h, pairwise != 0, first, cn, d_disparity + first * hw, d_segmentation + first * se,
+                                  roads + first, slot);
+    h->results_stay_on_device = false;
+    if (erc) return erc;
     ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_tables));
     slot ^= 1;
   }
