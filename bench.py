@@ -52,15 +52,15 @@ OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
 # summarised in profiles/r1j_{unary,pairwise}_b32.txt (width 8; no capture for width 4).
 # "tables" = join_columns + column_tables + object_lut kernels.
 NCU_CHUNK = 32
-NCU_SOURCE = "profiles/r2b_*_b32.txt"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of a 32-frame chunk, from the `ncu --set full` captures
-# summarised in profiles/r2b_{unary,pairwise}_b32.txt (width 8; no capture for width 4).
-# "tables" = join_columns + (frame_tables) + column_tables + object_lut kernels.
+NCU_SOURCE = "profiles/r2c_*.txt"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` captures summarised in
+# profiles/r2c_{unary,pairwise}.txt (width 8; unary launches carry 32 frames, pairwise launches 64; no capture for
+# width 4).  "tables" = join_columns + (frame_tables) + column_tables + object_lut kernels.
 NCU_TRAFFIC = {
-    ("unary", 8): dict(dp=(1.4432 + 0.1301) * 1e9,     # dp_unary_pruned_kernel
-                       tables=(0.2685 + 0.0269 + 0.1439 + 1.0601 + 0.0337 + 4.2362) * 1e9),
-    ("pairwise", 8): dict(dp=(7.1209 + 0.6449) * 1e9,  # dp_pairwise_walk_kernel
-                          tables=(0.2685 + 0.0269 + 0.0001 + 0.1439 + 1.0601 + 0.0337 + 4.2362) * 1e9),
+    ("unary", 8): dict(chunk=32, dp=(1.4443 + 0.1326) * 1e9,     # dp_unary_pruned_kernel
+                       tables=(0.2685 + 0.0271 + 0.1440 + 1.0619 + 0.0337 + 4.2363) * 1e9),
+    ("pairwise", 8): dict(chunk=64, dp=(3.2128 + 1.1244) * 1e9,  # dp_pairwise_walk_kernel
+                          tables=(0.5370 + 0.0607 + 0.0003 + 0.2879 + 2.1774 + 0.0673 + 8.5321) * 1e9),
 }
 
 
