@@ -48,10 +48,6 @@ WORKLOADS = {
 ROWS, COLS = 1024, 2048
 RECORD_WORDS_PER_ROW = 32   # prefix records: one 128-byte row per image row and column (common.cuh kRecBWords)
 OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of a 32-frame chunk, from the `ncu --set full` captures
-# summarised in profiles/r1j_{unary,pairwise}_b32.txt (width 8; no capture for width 4).
-# "tables" = join_columns + column_tables + object_lut kernels.
-NCU_CHUNK = 32
 NCU_SOURCE = "profiles/r2c_*.txt"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` captures summarised in
 # profiles/r2c_{unary,pairwise}.txt (width 8; unary launches carry 32 frames, pairwise launches 64; no capture for
@@ -415,7 +411,7 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
     tab_launches = max(stages["join"][1], 1)
     tab_avg_s = tab_ms * 1e-3 / tab_launches
     ncu = NCU_TRAFFIC.get((wl["mode"], wl["step"]))
-    if ncu and ncu.get("chunk", NCU_CHUNK) != chunk:
+    if ncu and ncu["chunk"] != chunk:
         ncu = None
     dp_alg_bytes = (C_ * 128 * H * 4 + C_ * rec_words * rec_stride * 4 + C_ * H * 16) * chunk
     fps = world * B / (ms_max * 1e-3 / steps)
