@@ -269,6 +269,15 @@ class Env:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather(self, obj):
+        """`obj` of every rank, in rank order (the per-rank step times and clocks of a multi-GPU line)."""
+        if self.world == 1:
+            return [obj]
+        import torch.distributed as dist
+        out = [None] * self.world
+        dist.all_gather_object(out, obj)
+        return out
+
 
 def narrow_inputs(disp, seg):
     """The same frames as a caller with 16-bit data holds them: disparity u16 = round(d * 256) (a 16-bit disparity
@@ -291,7 +300,8 @@ def time_device(env, st, step, steps, stream):
     e1.record(stream)
     st.Synchronize()
     env.barrier()
-    return env.max_over_ranks(e0.elapsed_time(e1))
+    local = e0.elapsed_time(e1)
+    return env.max_over_ranks(local), local
 
 
 def measure(env, name, wl, steps, warmup, primary, extras=True):
@@ -324,7 +334,9 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
     launches0 = st._lib.isx_kernel_launch_count()
     units0 = st.dp_units()
     with ClockSampler(env.local) as clk:
-        ms_max = time_device(env, st, device_step, steps, stream)
+        ms_max, ms_local = time_device(env, st, device_step, steps, stream)
+    per_rank = env.gather(dict(ms_per_step=round(ms_local / steps, 3), sm_mhz=clk.summary().get("sm_mhz"),
+                               reasons=clk.summary().get("reasons"))) if primary else None
     launches = st._lib.isx_kernel_launch_count() - launches0
     units1 = st.dp_units()
     units_eval, units_total = units1[0] - units0[0], units1[1] - units0[1]
@@ -334,9 +346,12 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
     # ---- e2e: host buffers through the public batch API, copies inside the timed region ----
     # One host thread, one context, the streaming form of the batch call: isx_submit_batch_host enqueues a batch
     # (H2D of its inputs from pinned memory, kernels, results packed by the device into pinned host memory) and
-    # isx_wait_batch_host delivers the oldest one into the caller's [C][200] Section array + instance records; two
-    # batches are in flight.  Every step moves its own inputs and reads its own results back.
-    sections_host = [torch.empty((B, C_, 200, 32), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    # isx_wait_batch_host delivers the oldest one into the caller's [C][200] Section array + instance records; three
+    # batches are in flight (the input copies of batch k+2 are queued while batch k still computes: with two, the copy
+    # engine waited for the host thread to come back from the wait).  Every step moves its own inputs and reads its
+    # own results back.
+    DEPTH = 3
+    sections_host = [torch.empty((B, C_, 200, 32), dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
     sec_np = [t.numpy().view(api.L.SECTION_DTYPE).reshape(B, C_, 200) for t in sections_host]
     d16, s16 = narrow_inputs(disp, seg)
     h_d16, h_s16 = torch.from_numpy(d16).pin_memory(), torch.from_numpy(s16).pin_memory()
@@ -345,14 +360,18 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
     def run_e2e(kind, nsteps):
         def submit(i):
             if kind == "u16":
-                st.SubmitBatchU16(pairwise, h_d16.numpy(), 1.0 / 256.0, h_s16.numpy(), roads, sec_np[i & 1])
+                st.SubmitBatchU16(pairwise, h_d16.numpy(), 1.0 / 256.0, h_s16.numpy(), roads, sec_np[i % DEPTH])
             else:
-                st.SubmitBatch(pairwise, h_disp.numpy(), h_seg.numpy(), roads, sec_np[i & 1])
-        for w in range(2):  # warm-up of the path that is timed (the second result set is allocated on first use)
+                st.SubmitBatch(pairwise, h_disp.numpy(), h_seg.numpy(), roads, sec_np[i % DEPTH])
+        for w in range(DEPTH + 1):  # warm-up of the path that is timed (result sets are allocated on first use)
             if kind == "single":
-                st.ComputeBatch(pairwise, h_disp.numpy(), h_seg.numpy(), roads, sections_out=sec_np[w])
+                st.ComputeBatch(pairwise, h_disp.numpy(), h_seg.numpy(), roads, sections_out=sec_np[0])
             else:
                 submit(w)
+                if w >= DEPTH - 1:
+                    st.WaitBatch()
+        if kind != "single":
+            for _ in range(DEPTH - 1):
                 st.WaitBatch()
         env.barrier()
         t0 = time.perf_counter()
@@ -362,9 +381,10 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
         else:
             for i in range(nsteps):
                 submit(i)
-                if i > 0:
+                if i >= DEPTH - 1:
                     _, inst, _ = st.WaitBatch()
-            _, inst, _ = st.WaitBatch()
+            for _ in range(min(DEPTH - 1, nsteps)):
+                _, inst, _ = st.WaitBatch()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         seen["inst"] = len(inst)
@@ -420,7 +440,7 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
         config=workload_config(name, wl, frames_per_step_per_gpu=B, distinct_frames=distinct, chunk_frames=chunk,
                                l2="inputs (%d MB/step) and tables (>2 GB/chunk) exceed the 126 MB L2" % (B * 13.9)),
         e2e=dict(value=world * B / e2e_s, unit="frames/s", h2d_bytes_per_step=h2d_float, d2h_bytes_per_step=d2h_bytes,
-                 pipeline="1 host thread, isx_submit_batch_host / isx_wait_batch_host, 2 batches in flight; float "
+                 pipeline="1 host thread, isx_submit_batch_host / isx_wait_batch_host, 3 batches in flight; float "
                           "disparity + int32 segmentation (the reference's types); results packed by the device into "
                           "pinned host memory and expanded into the caller's [C][200] Section array",
                  h2d_gbs_per_gpu=h2d_float / e2e_s / 1e9),
@@ -430,6 +450,7 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
                               "segmentation, widened on the device"),
         gpu_launches=int(launches),
         clocks=clk.summary(),
+        **(dict(ranks=per_rank) if per_rank and env.world > 1 else {}),
         roofline=dict(bound="alu", kernel="dp_pairwise_walk_kernel" if pairwise else "dp_unary_pruned_kernel",
                       achieved=achieved, peak=peak, unit="Tlane-op/s", frac=achieved / peak,
                       traffic=ncu["dp"] if ncu else None,
@@ -496,7 +517,7 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
         step2()
         st2.Synchronize()
         n2 = max(2, steps // 4)
-        ms2 = time_device(env, st2, step2, n2, stream2)
+        ms2, _ = time_device(env, st2, step2, n2, stream2)
         out["value_no_prune"] = dict(value=world * B / (ms2 * 1e-3 / n2), unit="frames/s",
                                      note="every (tile, chunk) unit evaluated: the floor of the data-dependent pruning")
         st2.Finish()

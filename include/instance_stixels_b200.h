@@ -235,9 +235,10 @@ int isx_synchronize(isx_handle h);
 /* Asynchronous form of isx_compute_batch_host for a streaming caller: isx_submit_batch_host enqueues the
  * copies and kernels of one batch (same arguments, same layouts) and returns once they are queued;
  * isx_wait_batch_host waits for the OLDEST batch in flight, after which that batch's `sections` buffer is
- * complete, and delivers its packed instance records.  At most two batches may be in flight per handle
- * (submit, submit, wait, submit, wait, ...): the head and tail of one batch then hide behind the kernels of
- * the other.  `disparity`, `segmentation` and `sections` must stay valid (and should be pinned) until the
+ * complete, and delivers its packed instance records.  At most three batches may be in flight per handle
+ * (submit, submit, submit, wait, submit, wait, ...): with two, the head and tail of one batch hide behind the
+ * kernels of the other; with three, the input copies of a batch are also queued before the batch two ahead of it
+ * has delivered its results, so the copy engine never waits for the host thread.  `disparity`, `segmentation` and `sections` must stay valid (and should be pinned) until the
  * batch has been waited for.  The synchronous entry points refuse to run while batches are in flight. */
 int isx_submit_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
                           const isx_road *roads, isx_section *sections);
@@ -247,7 +248,7 @@ int isx_wait_batch_host(isx_handle h, isx_instance *instances, int instances_cap
  * arrays, `*counts` = [n][realcols] stixels per column, `*frames` = [n] descriptors (offsets into the packed
  * arrays), `*n` = frames of the batch.  The `sections` buffer given to isx_submit_batch_host (may be NULL for
  * callers that only use this form) is not written.  The pointers stay valid until the second isx_submit_batch_host
- * after this call (two result sets alternate).  Any pointer argument may be NULL. */
+ * after this call.  Any pointer argument may be NULL. */
 int isx_wait_batch_packed(isx_handle h, const isx_section **sections, const int32_t **counts,
                           const isx_instance **instances, const isx_packed_frame **frames, int *n);
 /* Narrow host inputs, extensions beside the float API for callers whose data is narrower at its source (over the

@@ -216,7 +216,7 @@ class Stixels:
     def SubmitBatch(self, pairwise: bool, disparity: np.ndarray, segmentation: np.ndarray, roads: Sequence[dict],
                     sections_out: np.ndarray):
         """Asynchronous ComputeBatch: enqueue one batch (host buffers, which must stay alive and unchanged until
-        the matching WaitBatch) and return.  At most two batches in flight."""
+        the matching WaitBatch) and return.  At most three batches in flight."""
         n = len(roads)
         if disparity.dtype != np.float32 or segmentation.dtype != np.int32 or \
                 not disparity.flags.c_contiguous or not segmentation.flags.c_contiguous:

@@ -25,6 +25,8 @@ namespace isx {
 
 static thread_local std::string g_last_error;
 constexpr int kStageSlots = 8;    // pinned staging buffers of the road tables (see isx_context::h_ground)
+constexpr int kRoadSlots = 4;     // device copies of a chunk's road tables (isx_context::roads)
+constexpr int kResultSets = 4;    // result sets: up to kResultSets - 1 submitted batches in flight + the one waited last
 constexpr int kProfEvents = 9;    // profiling events per enqueued chunk (enqueue_chunk)
 constexpr int kTraceStamps = 11;  // time stamps per chunk of isx_get_chunk_trace
 
@@ -77,8 +79,6 @@ struct isx_context {
   // Buffers the emission stream still reads while the compute stream works on the next chunk exist
   // twice; chunk k uses set k & 1.
   struct ChunkSet {
-    float *ground = nullptr;
-    int *vhor = nullptr;
     float *stat = nullptr;
     uint32_t *records_b = nullptr;
     float4 *dp = nullptr;
@@ -89,6 +89,17 @@ struct isx_context {
     int *col_flags = nullptr;     // [chunk][C]
   } sets[2];
   int last_set = 0;
+  // The road tables of a chunk ([chunk][3][H] + [chunk] horizon rows) arrive on the copy stream in front of the chunk's
+  // images.  They have their own ring: as members of the chunk set their copy had to wait for the emission two chunks
+  // back, and with it every image copy queued behind -- the input copies of a pipelined host batch then started a
+  // whole DP late.  `ev_free` = the emission of the chunk that last read the slot.
+  struct RoadSlot {
+    float *ground = nullptr;
+    int *vhor = nullptr;
+    cudaEvent_t ev_free = nullptr;
+  } roads[isx::kRoadSlots];
+  unsigned long long road_next = 0;
+  int last_road_slot = 0;
   bool overlap_tables = true;      // table build of chunk k+1 beside the DP of chunk k (ISX_OVERLAP_TABLES)
   bool emit_join_pending = false;  // results of the last device batch are not yet ordered on isx_stream()
   // Results of one batch.  The padded device arrays feed the rasteriser and the fallback copy; what a host caller
@@ -106,7 +117,7 @@ struct isx_context {
     int *h_counts = nullptr, *m_counts = nullptr;               // [max_batch][C] stixels per column
     isx_packed_frame *h_frames = nullptr, *m_frames = nullptr;  // [max_batch]
     int sections_cap = 0, inst_cap = 0;           // entries of the packed arrays
-  } rs[2];
+  } rs[isx::kResultSets];
   int cur = 0;                                    // result set of the batch being enqueued / of the last batch
   int *d_raster_table = nullptr;                  // [max_batch][C][200] instance id per stixel (rasteriser)
   int inst_cap = 0;                               // instance records per frame of the device arrays: C * 200
@@ -120,15 +131,17 @@ struct isx_context {
   int *h_vhor = nullptr;                          // [kStageSlots][chunk]
   cudaEvent_t ev_stage_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned long long stage_next = 0;
-  // isx_submit_batch_host keeps up to two batches in flight: rs[cur] belongs to the batch submitted last, the other
-  // set to the one before (the second set is allocated on the first submit).
-  cudaEvent_t ev_batch_done[2] = {nullptr, nullptr};  // by ticket parity
-  int batch_n[2] = {0, 0};                            // frames of the batch in flight with that parity, 0 = none
-  int batch_set[2] = {0, 0};                          // its result set
-  isx_section *batch_sections[2] = {nullptr, nullptr};  // the caller's padded array the wait expands into
-  bool batch_direct[2] = {false, false};                // ... or that the device has already filled (mapped memory)
+  // isx_submit_batch_host keeps up to kResultSets - 1 batches in flight: rs[cur] belongs to the batch submitted last;
+  // a new batch takes the lowest set that is neither in flight nor the one handed out by the last wait (allocated on
+  // first use: a caller with two batches in flight only ever touches three).  Indexed by ticket % kResultSets:
+  cudaEvent_t ev_batch_done[isx::kResultSets] = {};       // behind the packing of the batch's last chunk
+  int batch_n[isx::kResultSets] = {};                     // frames of the batch in flight with that ticket, 0 = none
+  int batch_set[isx::kResultSets] = {};                   // its result set
+  isx_section *batch_sections[isx::kResultSets] = {};     // the caller's padded array the wait expands into
+  bool batch_direct[isx::kResultSets] = {};               // ... or that the device has already filled (mapped memory)
   isx_section *direct_sections = nullptr;               // device address of the caller's array for the batch being enqueued
   bool results_stay_on_device = false;                  // set while a device batch is enqueued
+  int last_waited_set = -1;                           // result set of the batch waited for last (isx_wait_batch_packed)
   unsigned long long submitted = 0, waited = 0;       // tickets: batches [waited, submitted) are in flight
   unsigned long long dp_units_pairwise = 0;           // ... of which in pairwise mode (never pruned)
   unsigned long long dp_units_total = 0;              // 32 x 32-cell units of all DP launches so far
@@ -266,9 +279,9 @@ static const float *road_tables(isx_context *c, const isx_road &r) {
 // collection, grouping and packing (short, latency-bound launches) on s_emit, so
 // that they overlap the next chunk's DP.
 // The per-frame road tables of a chunk (Stixels.cu:463-493: three blocking copies per frame in the reference) go
-// through the pinned staging half of `slot` to the chunk set on stream `st`.  The caller has made sure that the copy
-// which last read this staging half is done, and orders `st` behind the emission that last read the chunk set.
-static int stage_road_tables(isx_context *c, const isx_road *roads, int n, int slot, cudaStream_t st) {
+// through a pinned staging buffer to the next slot of the road ring on stream `st`, behind the emission that last read
+// that slot (kRoadSlots chunks ago).  Returns the slot (>= 0) or an error (< 0).
+static int stage_road_tables(isx_context *c, const isx_road *roads, int n, cudaStream_t st) {
   const int H = c->kp.rows;
   const int stage = (int)(c->stage_next++ % kStageSlots);
   // the copy that read this staging buffer kStageSlots chunks ago must be done (a never-recorded event is complete)
@@ -279,18 +292,21 @@ static int stage_road_tables(isx_context *c, const isx_road *roads, int n, int s
     std::memcpy(hg + (size_t)i * 3 * H, road_tables(c, roads[i]), sizeof(float) * 3 * H);
     hv[i] = H - roads[i].vhor - 1;  // Stixels.cu:377
   }
-  const isx_context::ChunkSet &cs = c->sets[slot];
-  ISX_TRY(c, cudaMemcpyAsync(cs.ground, hg, sizeof(float) * 3 * H * n, cudaMemcpyHostToDevice, st));
-  ISX_TRY(c, cudaMemcpyAsync(cs.vhor, hv, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  const int rslot = (int)(c->road_next++ % kRoadSlots);
+  const isx_context::RoadSlot &rd = c->roads[rslot];
+  ISX_TRY(c, cudaStreamWaitEvent(st, rd.ev_free, 0));
+  ISX_TRY(c, cudaMemcpyAsync(rd.ground, hg, sizeof(float) * 3 * H * n, cudaMemcpyHostToDevice, st));
+  ISX_TRY(c, cudaMemcpyAsync(rd.vhor, hv, sizeof(int) * n, cudaMemcpyHostToDevice, st));
   ISX_TRY(c, cudaEventRecord(c->ev_stage_done[stage], st));
-  return ISX_OK;
+  return rslot;
 }
 
-// `roads_staged`: the caller has already copied the road tables of the chunk (host batches send them on the copy
-// stream IN FRONT of the chunk's images: as a copy on the compute stream they would queue on the copy engine behind
-// the next chunk's images -- several milliseconds of an idle GPU per chunk, measured with isx_get_chunk_trace).
+// `road_slot` >= 0: the caller has already copied the road tables of the chunk into that slot of the ring (host
+// batches send them on the copy stream IN FRONT of the chunk's images: as a copy on the compute stream they would
+// queue on the copy engine behind the next chunk's images -- several milliseconds of an idle GPU per chunk, measured
+// with isx_get_chunk_trace).
 static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const float *d_disp,
-                         const int32_t *d_seg, const isx_road *roads, int slot, bool roads_staged = false) {
+                         const int32_t *d_seg, const isx_road *roads, int slot, int road_slot = -1) {
   const KParams &kp = c->kp;
   const int H = kp.rows, C = kp.realcols;
   const isx_context::ChunkSet &cs = c->sets[slot];
@@ -299,12 +315,15 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
   ISX_TRY(c, cudaStreamWaitEvent(st, c->ev_emit_done[slot], 0));
   // ISX_OVERLAP_TABLES=0: the table build waits for the DP of the chunk before it (one kernel at a time on the SMs)
   if (!c->overlap_tables) ISX_TRY(c, cudaStreamWaitEvent(st, c->ev_dp_done[slot ^ 1], 0));
-  if (!roads_staged)
-    if (int rc = stage_road_tables(c, roads, n, slot, st)) return rc;
+  if (road_slot < 0) {
+    road_slot = stage_road_tables(c, roads, n, st);
+    if (road_slot < 0) return road_slot;
+  }
+  const isx_context::RoadSlot &rd = c->roads[road_slot];
   ISX_TRY(c, cudaMemsetAsync(cs.err, 0, sizeof(int) * n, st));  // the error words of THIS chunk's frames
   isx_context::ResultSet &R = c->rs[c->cur];
   BatchBuffers b = c->buf;
-  b.ground = cs.ground; b.vhor = cs.vhor; b.stat = cs.stat;
+  b.ground = rd.ground; b.vhor = rd.vhor; b.stat = cs.stat;
   b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
   b.joined = cs.joined; b.object_lut = cs.object_lut; b.col_flags = cs.col_flags;
   b.error_flag = cs.err;
@@ -366,11 +385,13 @@ static int enqueue_chunk(isx_context *c, bool pairwise, int first, int n, const 
   }
   mark(se);
   ISX_TRY(c, cudaEventRecord(c->ev_emit_done[slot], se));
+  ISX_TRY(c, cudaEventRecord(rd.ev_free, se));
   ISX_TRY(c, cudaGetLastError());
   c->last_chunk_first = first;
   c->last_chunk_n = n;
   c->last_pairwise = pairwise;
   c->last_set = slot;
+  c->last_road_slot = road_slot;
   return ISX_OK;
 }
 
@@ -637,6 +658,12 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
 
   BatchBuffers &b = h->buf;
+  for (int i = 0; i < kRoadSlots; i++) {
+    ISX_TRY(h, dev_alloc(h, &h->roads[i].ground, ch * 3 * H));
+    ISX_TRY(h, dev_alloc(h, &h->roads[i].vhor, ch));
+    ISX_TRY(h, cudaEventCreateWithFlags(&h->roads[i].ev_free, cudaEventDisableTiming));
+  }
+  h->road_next = 0;
   for (int i = 0; i < 2; i++) {
     ISX_TRY(h, dev_alloc(h, &h->d_in_disp[i], ch * H * W));
     ISX_TRY(h, dev_alloc(h, &h->d_in_seg[i], ch * seg_elems(h)));
@@ -646,8 +673,6 @@ int isx_initialize(isx_handle h, int max_batch) {
   ISX_TRY(h, dev_alloc(h, &h->d_single_seg, seg_elems(h)));
   for (int i = 0; i < 2; i++) {
     isx_context::ChunkSet &cs = h->sets[i];
-    ISX_TRY(h, dev_alloc(h, &cs.ground, ch * 3 * H));
-    ISX_TRY(h, dev_alloc(h, &cs.vhor, ch));
     ISX_TRY(h, dev_alloc(h, &cs.stat, ch * H * kStatWords));
     ISX_TRY(h, dev_alloc(h, &cs.records_b, ch * C * kRecBWords * (size_t)kp.rec_stride));
     ISX_TRY(h, cudaMemset(cs.records_b, 0, ch * C * kRecBWords * (size_t)kp.rec_stride * sizeof(uint32_t)));
@@ -730,7 +755,11 @@ int isx_finish(isx_handle h) {
     if (h->ev_stage_done[i]) cudaEventDestroy(h->ev_stage_done[i]);
     h->ev_stage_done[i] = nullptr;
   }
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < kRoadSlots; i++) {
+    if (h->roads[i].ev_free) cudaEventDestroy(h->roads[i].ev_free);
+    h->roads[i] = isx_context::RoadSlot();
+  }
+  for (int i = 0; i < kResultSets; i++) {
     isx_context::ResultSet &R = h->rs[i];
     if (R.allocated) {
       cudaFreeHost(R.h_sections);
@@ -741,15 +770,18 @@ int isx_finish(isx_handle h) {
     R = isx_context::ResultSet();
     if (h->ev_batch_done[i]) cudaEventDestroy(h->ev_batch_done[i]);
     h->ev_batch_done[i] = nullptr;
+    h->batch_sections[i] = nullptr;
+    h->batch_n[i] = 0;
+  }
+  for (int i = 0; i < 2; i++) {
     h->d_in_disp16[i] = nullptr;
     h->d_in_seg16[i] = nullptr;
-    h->batch_sections[i] = nullptr;
   }
   h->cur = 0;
   h->submitted = h->waited = 0;
+  h->last_waited_set = -1;
   h->host_slot = 0;
   h->dp_units_total = h->dp_units_pairwise = 0;
-  h->batch_n[0] = h->batch_n[1] = 0;
   h->emit_join_pending = false;
   for (int i = 0; i < 2; i++) {
     cudaEventDestroy(h->ev_in_ready[i]);
@@ -1040,7 +1072,10 @@ static int ensure_narrow_staging(isx_handle h) {
 // The copy/kernel pipeline of one host batch: H2D on s_h2d, kernels on s_compute / s_emit; the results reach host
 // memory through pack_results_kernel (no D2H copies).  Blocks the caller only for the reuse of an input slot (two
 // chunks behind).
-static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInputs &in, const isx_road *roads) {
+// `caller_waits`: a synchronous call -- the kernels of the last chunk run with nothing beside them while the caller
+// waits, so the tail goes in quarter pieces like the head.
+static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInputs &in, const isx_road *roads,
+                              bool caller_waits) {
   const size_t hw = (size_t)h->kp.rows * h->kp.cols, se = seg_elems(h), se16 = narrow_seg_elems(h);
   if (in.narrow()) {
     if (hw % 8 != 0) return fail(h, ISX_ERR_UNSUPPORTED, "the uint16 disparity path needs rows*cols to be a multiple of 8");
@@ -1056,12 +1091,16 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
   const bool pipeline_idle = h->submitted == h->waited;
   for (int first = 0; first < n; first += cn) {
     cn = (n - first) < chunk ? (n - first) : chunk;
-    // a short first chunk when nothing is running: its copy is the only one that no kernel hides
-    if (first == 0 && pipeline_idle && n > chunk && chunk >= 8) cn = chunk / 4;
-    // H2D of this chunk on the copy stream, once the kernels that last read this input slot are done and the emission
-    // that last read the chunk set (device-side waits: the host thread runs ahead)
+    // Nothing is running: no kernel hides the input copies, so the first `chunk` frames go in quarter pieces and the
+    // kernels of a piece run under the copy of the next (a synchronous 64-frame pairwise call: copy 13 ms + tables and
+    // DP of the last piece instead of copy + tables and DP of all 64 frames); likewise the last `chunk` frames of a
+    // call whose caller waits.  The shorter launches cost the DP a few per cent -- in between, and once the pipeline
+    // of a streaming caller is filled, launches are whole chunks.
+    const bool head = pipeline_idle && first < chunk, tail = caller_waits && n - first <= chunk;
+    if ((head || tail) && chunk >= 32) cn = cn < chunk / 4 ? cn : chunk / 4;
+    // H2D of this chunk on the copy stream, once the table build that last read this input slot is done (a
+    // device-side wait: the host thread runs ahead)
     ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_in_free[slot], 0));
-    ISX_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_emit_done[slot], 0));
     auto mark_h2d = [&]() {
       if (!h->profiling) return;
       if (h->prof_h2d_used >= h->prof_h2d.size()) {
@@ -1072,7 +1111,8 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
       cudaEventRecord(h->prof_h2d[h->prof_h2d_used++], h->s_h2d);
     };
     mark_h2d();
-    if (int rc = stage_road_tables(h, roads + first, cn, slot, h->s_h2d)) return rc;
+    const int road_slot = stage_road_tables(h, roads + first, cn, h->s_h2d);
+    if (road_slot < 0) return road_slot;
     if (in.narrow()) {
       ISX_TRY(h, cudaMemcpyAsync(h->d_in_disp16[slot], in.disparity16 + first * hw, sizeof(uint16_t) * hw * cn,
                                  cudaMemcpyHostToDevice, h->s_h2d));
@@ -1098,7 +1138,7 @@ static int enqueue_host_batch(isx_handle h, int pairwise, int n, const HostInput
       launch_widen_inputs(h->kp, h->d_in_disp16[slot], in.scale, h->d_in_seg16[slot], h->d_in_disp[slot],
                           h->d_in_seg[slot], cn, h->s_tables);
     if (int rc = enqueue_chunk(h, pairwise != 0, first, cn, h->d_in_disp[slot], h->d_in_seg[slot], roads + first,
-                               slot, /*roads_staged=*/true))
+                               slot, road_slot))
       return rc;
     ISX_TRY(h, cudaEventRecord(h->ev_in_free[slot], h->s_tables));   // the inputs are read by the table build only
     slot ^= 1;
@@ -1124,7 +1164,7 @@ static int compute_batch_host(isx_handle h, int pairwise, int n, const HostInput
   if (!roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
   h->direct_sections = device_view_of(sections);
   const bool direct = h->direct_sections != nullptr;
-  const int erc = enqueue_host_batch(h, pairwise, n, in, roads);
+  const int erc = enqueue_host_batch(h, pairwise, n, in, roads, /*caller_waits=*/true);
   h->direct_sections = nullptr;
   if (erc) return erc;
   if (int rc = join_emit_stream(h)) return rc;
@@ -1160,19 +1200,25 @@ static int submit_batch_host(isx_handle h, int pairwise, int n, const HostInputs
   if (int rc = check_ready(h)) return rc;
   if (n < 1 || n > h->max_batch) return fail(h, ISX_ERR_CAPACITY, "batch size exceeds isx_initialize(max_batch)");
   if (!roads) return fail(h, ISX_ERR_INVALID_ARGUMENT, "null argument");
-  if (h->submitted - h->waited >= 2)
-    return fail(h, ISX_ERR_CAPACITY, "two batches are already in flight: call isx_wait_batch_host first");
-  // the other result set was delivered by the wait before last (or never used)
-  if (int rc = alloc_result_set(h, h->cur ^ 1)) return rc;
-  for (int i = 0; i < 2; i++)
+  if (h->submitted - h->waited >= (unsigned long long)(kResultSets - 1))
+    return fail(h, ISX_ERR_CAPACITY, "three batches are already in flight: call isx_wait_batch_host first");
+  int next = 0;
+  {
+    bool busy[kResultSets] = {};
+    for (unsigned long long t = h->waited; t < h->submitted; t++) busy[h->batch_set[t % kResultSets]] = true;
+    if (h->last_waited_set >= 0) busy[h->last_waited_set] = true;  // its packed arrays may still be read
+    while (busy[next]) next++;
+  }
+  if (int rc = alloc_result_set(h, next)) return rc;
+  for (int i = 0; i < kResultSets; i++)
     if (!h->ev_batch_done[i]) ISX_TRY(h, cudaEventCreateWithFlags(&h->ev_batch_done[i], cudaEventDisableTiming));
-  h->cur ^= 1;
+  h->cur = next;
   h->direct_sections = device_view_of(sections);
   const bool direct = h->direct_sections != nullptr;
-  const int erc = enqueue_host_batch(h, pairwise, n, in, roads);
+  const int erc = enqueue_host_batch(h, pairwise, n, in, roads, /*caller_waits=*/false);
   h->direct_sections = nullptr;
   if (erc) return erc;
-  const int par = (int)(h->submitted & 1);
+  const int par = (int)(h->submitted % kResultSets);
   h->batch_direct[par] = direct;
   ISX_TRY(h, cudaEventRecord(h->ev_batch_done[par], h->s_emit));  // behind the packing of the last chunk
   h->batch_n[par] = n;
@@ -1202,12 +1248,13 @@ int isx_submit_batch_host_u16(isx_handle h, int pairwise, int n, const uint16_t 
   return submit_batch_host(h, pairwise, n, in, roads, sections);
 }
 
-// Waits for the oldest batch in flight; returns its ticket parity (>= 0) or an error (< 0).
+// Waits for the oldest batch in flight; returns its ticket slot (>= 0) or an error (< 0).
 static int wait_oldest(isx_handle h) {
   if (int rc = check_ready(h)) return rc;
   if (h->submitted == h->waited) return fail(h, ISX_ERR_INVALID_ARGUMENT, "no submitted batch is in flight");
-  const int par = (int)(h->waited & 1);
+  const int par = (int)(h->waited % kResultSets);
   ISX_TRY(h, cudaEventSynchronize(h->ev_batch_done[par]));
+  h->last_waited_set = h->batch_set[par];
   h->waited++;
   return par;
 }
@@ -1292,7 +1339,7 @@ int isx_read_tensor(isx_handle h, int tensor, int frame, void *host, size_t byte
   BatchBuffers b = h->buf;
   {
     const isx_context::ChunkSet &cs = h->sets[h->last_set];
-    b.ground = cs.ground; b.vhor = cs.vhor; b.stat = cs.stat;
+    b.ground = h->roads[h->last_road_slot].ground; b.vhor = h->roads[h->last_road_slot].vhor; b.stat = cs.stat;
     b.records_b = cs.records_b; b.dp = cs.dp; b.pm = cs.pm;
     b.joined = cs.joined; b.object_lut = cs.object_lut; b.col_flags = cs.col_flags;
   }

@@ -4,7 +4,7 @@
 // (InstanceStixels/src/Stixels.cu:449-637, frame loop apps/run_cityscapes.cu:249-449).
 //
 // A call shards its n frames into contiguous blocks, worker w takes frames [n*w/G, n*(w+1)/G) and streams them
-// through isx_submit_batch_host / isx_wait_batch_host in sub-batches of at most `max_batch` frames, two in flight.
+// through isx_submit_batch_host / isx_wait_batch_host in sub-batches of at most `max_batch` frames, three in flight.
 // Frames are independent, so there is no collective: every worker writes its frames' Sections into the caller's
 // array at their place; the instance records are concatenated in frame order when all workers are done.
 #include <condition_variable>
@@ -65,7 +65,7 @@ int pool_fail(isx_pool *p, int code, const std::string &msg) {
   return code;
 }
 
-// One block of frames through one context: sub-batches of <= max_batch frames, two in flight.
+// One block of frames through one context: sub-batches of <= max_batch frames, three in flight.
 void run_job(isx_pool *p, Worker *w) {
   const Job &j = w->job;
   w->rc = ISX_OK;
@@ -86,7 +86,7 @@ void run_job(isx_pool *p, Worker *w) {
   auto sub_first = [&](int s) { return s * mb; };
   auto sub_count = [&](int s) { return (j.count - s * mb) < mb ? (j.count - s * mb) : mb; };
   while (waited < nsub) {
-    while (submitted < nsub && submitted - waited < 2 && w->rc == ISX_OK) {
+    while (submitted < nsub && submitted - waited < 3 && w->rc == ISX_OK) {
       const int f0 = j.first + sub_first(submitted), cn = sub_count(submitted);
       const int rc = isx_submit_batch_host(w->h, j.pairwise, cn, j.disparity + (size_t)f0 * p->hw,
                                            j.segmentation + (size_t)f0 * p->seg_elems, j.roads + f0,

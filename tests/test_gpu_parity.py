@@ -424,7 +424,7 @@ def test_device_resident_entry_point_matches_host_entry_point():
 
 
 def test_submit_wait_pipeline_equals_synchronous_batches():
-    """isx_submit_batch_host / isx_wait_batch_host: two batches in flight, results in submission order and
+    """isx_submit_batch_host / isx_wait_batch_host: two and three batches in flight, results in submission order and
     identical to the synchronous entry point; misuse is refused."""
     rows, cols, n = 128, 256, 5
     pre = _preset("pairwise", rows, cols, 8, 0.0, False)
@@ -444,20 +444,23 @@ def test_submit_wait_pipeline_equals_synchronous_batches():
     got = []
     with pytest.raises(api.InvalidArgument):
         st.WaitBatch()
-    for rep in range(2):                # the second round reuses both result sets
+    for rep, depth in enumerate((2, 3, 3, 2)):    # the later rounds reuse the result sets
         got.clear()
+        for o in outs:
+            o[:] = 0
         for i, (disp, seg, roads) in enumerate(batches):
             st.SubmitBatch(True, disp, seg, roads, outs[i])
-            if i == 1:
-                with pytest.raises(api.StixelsError):   # a third batch in flight
+            if i == 2 and depth == 3:
+                with pytest.raises(api.StixelsError):   # a fourth batch in flight
                     st.SubmitBatch(True, disp, seg, roads, outs[i])
                 with pytest.raises(api.InvalidArgument):  # synchronous call while batches are in flight
                     st.ComputeBatch(True, disp, seg, roads)
-            if i >= 1:
+            if i >= depth - 1:
                 sec, inst, offs = st.WaitBatch()
                 got.append((sec.copy(), inst, offs))
-        sec, inst, offs = st.WaitBatch()
-        got.append((sec.copy(), inst, offs))
+        for _ in range(depth - 1):
+            sec, inst, offs = st.WaitBatch()
+            got.append((sec.copy(), inst, offs))
         assert len(got) == len(batches)
         for i, ((ws, wi, wo), (gs, gi, go)) in enumerate(zip(want, got)):
             assert all(parity.same_used_sections(ws[f], gs[f]) for f in range(n)), (rep, i)
