@@ -80,6 +80,8 @@ class ClockSampler:
         self.sm = []
         self.reasons = set()
         self.sm_max = None
+        self.mem_mhz = None
+        self.power_w = None
         self.source = "nvml"
         self._stop = threading.Event()
         self._t = None
@@ -102,6 +104,12 @@ class ClockSampler:
     def _sample_nvml(self):
         nv = self._nv
         self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        if self.mem_mhz is None:
+            try:
+                self.mem_mhz = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_MEM))
+                self.power_w = nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+            except Exception:
+                self.mem_mhz = 0.0
         try:
             bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
         except Exception:
@@ -336,7 +344,7 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
     with ClockSampler(env.local) as clk:
         ms_max, ms_local = time_device(env, st, device_step, steps, stream)
     per_rank = env.gather(dict(ms_per_step=round(ms_local / steps, 3), sm_mhz=clk.summary().get("sm_mhz"),
-                               reasons=clk.summary().get("reasons"))) if primary else None
+                               mem_mhz=clk.mem_mhz, reasons=clk.summary().get("reasons"))) if primary else None
     launches = st._lib.isx_kernel_launch_count() - launches0
     units1 = st.dp_units()
     units_eval, units_total = units1[0] - units0[0], units1[1] - units0[1]

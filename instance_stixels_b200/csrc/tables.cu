@@ -11,6 +11,7 @@
 //
 // Float prefix sums are order-sensitive; both scan orders of the reference are
 // reproduced exactly (see blelloch_prefix_warp / object_lut_rows below).
+#include <cstdlib>
 #include "kernels.h"
 
 namespace isx {
@@ -142,25 +143,28 @@ __device__ void exact_prefix_warp(const T *e, int n, T *ps) {
 constexpr int kTabThreads = 256;
 
 // Dynamic shared memory carve-up (bytes), Hp = H + 1 rounded up to 4.
-// The per-row terms are scanned in place (every scan reads e[v] and writes ps[v] from the same lane), which keeps
-// the CTA at 71 KB so that three of them share an SM.
+// Every array is scanned in place (a scan reads e[v] and writes ps[v] from the same lane; a 1/8-resolution channel
+// value is recovered as ps[q + 1] - ps[q], exact in integers), and the sums of the instance means themselves are
+// 32-bit (only their squares need 64): 50 KB per CTA at 1024 rows, so that FOUR CTAs share an SM (r1/r2a: 71 KB, three).
 struct TabSmem {
   int Hp, nq;
-  size_t off_e[4], off_segps, off_seg, off_i64e, total;
+  size_t off_e[4], off_seg, off_i64, off_i32, total;
   __host__ __device__ TabSmem(int H, int hs2) {
     Hp = (H + 1 + 3) & ~3;
     nq = H / 8 + 1;  // prefix entries per 1/8-res channel (index v>>3 for v <= H)
     size_t o = 0;
-    off_i64e = o; o += (size_t)Hp * 8 * 4;
+    off_i64 = o; o += (size_t)Hp * 8 * 2;
+    off_i32 = o; o += (size_t)Hp * 4 * 2;
     for (int i = 0; i < 4; i++) { off_e[i] = o; o += (size_t)Hp * 4; }
-    off_seg = o; o += (size_t)21 * (nq + 1) * 4;
-    off_segps = o; o += (size_t)21 * (nq + 1) * 4;
+    off_seg = o; o += (size_t)20 * (nq + 1) * 4;
     total = (o + 15) & ~(size_t)15;
     (void)hs2;
   }
 };
 
-__global__ void __launch_bounds__(kTabThreads, 3)
+constexpr int kMeanRowLimit = 1 << 20;  // |instance mean of a row|: 1024 rows of them cannot wrap an int32 sum
+
+__global__ void __launch_bounds__(kTabThreads, 4)
 column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict__ segmentation,
                      const float *__restrict__ ground, const int *__restrict__ vhor_arr,
                      uint32_t *__restrict__ records_b, int *__restrict__ error_flag, int *__restrict__ col_flags,
@@ -174,11 +178,10 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   float *e_valid = reinterpret_cast<float *>(smem + L.off_e[1]);
   float *e_ground = reinterpret_cast<float *>(smem + L.off_e[2]);
   float *e_sky = reinterpret_cast<float *>(smem + L.off_e[3]);
-  float *ps_f[4] = {e_disp, e_valid, e_ground, e_sky};                   // scanned in place
-  long long *e_i64 = reinterpret_cast<long long *>(smem + L.off_i64e);    // [4][Hp]
-  long long *ps_i64 = e_i64;                                              // scanned in place
-  int *seg_s = reinterpret_cast<int *>(smem + L.off_seg);                 // [21][nq+1]
-  int *seg_ps = reinterpret_cast<int *>(smem + L.off_segps);              // [21][nq+1]
+  // the four float arrays are contiguous and scanned in place: array i = e_disp + i * Hp
+  long long *ps_i64 = reinterpret_cast<long long *>(smem + L.off_i64);    // [2][Hp]: sum mx^2, sum my^2
+  int *ps_i32 = reinterpret_cast<int *>(smem + L.off_i32);                // [2][Hp]: sum mx, sum my
+  int *seg_ps = reinterpret_cast<int *>(smem + L.off_seg);                // [20][nq+1]
   const int nq = L.nq, segld = nq + 1;
 
   const float *d_col = joined + ((size_t)f * C + col) * H;
@@ -188,69 +191,93 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   const int vhor = vhor_arr[f];
   const float invalid = p.invalid_disparity;
   const int K = p.n_classes;  // 19; channel K = y offsets, K+1 = x offsets
+  const bool has_oy = K < p.n_channels, has_ox = K + 1 < p.n_channels;
 
   // ---- 1/8-resolution channels: the 19 classes, and as a 20th the sum of the two squared offsets (:411-416; the
-  //      DP only ever uses the sum, ComputeNonInstanceOffsetCost :62-70) ----
+  //      DP only ever uses the sum, ComputeNonInstanceOffsetCost :62-70).  Warp = channel, lane = entry: the loads of
+  //      a thread are independent of each other (the first version waited for every load in turn). ----
   bool negative_class_value = false;
-  for (int i = tid; i < 20 * nq; i += kTabThreads) {
-    const int c = i / nq, q = i - c * nq;
-    int v = 0;
-    if (c < K) {
-      if (c < p.n_channels && q < p.hs2) v = seg_col[(size_t)c * p.hs2 + q];
-      negative_class_value |= v < 0 || v > (1 << 20);   // the int32 prefix sums over <= 1032 rows cannot wrap
-    } else {
-      int oy = 0, ox = 0;
-      if (q < p.hs2 && K < p.n_channels) oy = seg_col[(size_t)K * p.hs2 + q];
-      if (q < p.hs2 && K + 1 < p.n_channels) ox = seg_col[(size_t)(K + 1) * p.hs2 + q];
-      oy = oy * oy;
-      ox = ox * ox;
-      negative_class_value |= oy < 0 || oy > (1 << 19) || ox < 0 || ox > (1 << 19);   // their sum: likewise
-      v = oy + ox;
+#pragma unroll
+  for (int c = warp; c < 20; c += kTabThreads / 32) {
+#pragma unroll 5
+    for (int q = lane; q < nq; q += 32) {
+      int v = 0;
+      if (c < K) {
+        if (c < p.n_channels && q < p.hs2) v = __ldg(seg_col + (size_t)c * p.hs2 + q);
+        negative_class_value |= v < 0 || v > (1 << 20);   // the int32 prefix sums over <= 1032 rows cannot wrap
+      } else {
+        int oy = 0, ox = 0;
+        if (q < p.hs2 && has_oy) oy = __ldg(seg_col + (size_t)K * p.hs2 + q);
+        if (q < p.hs2 && has_ox) ox = __ldg(seg_col + (size_t)(K + 1) * p.hs2 + q);
+        oy = oy * oy;
+        ox = ox * ox;
+        negative_class_value |= oy < 0 || oy > (1 << 19) || ox < 0 || ox > (1 << 19);   // their sum: likewise
+        v = oy + ox;
+      }
+      seg_ps[c * segld + q] = v;
     }
-    seg_s[c * segld + q] = v;
   }
-  // ---- per-row terms (:371-446) ----
-  for (int v = tid; v < H; v += kTabThreads) {
-    const float d = d_col[v];
-    if (invalid >= 0.0f) {
-      const int va = d != invalid;
-      e_valid[v] = (float)va;
-      e_disp[v] = fmul((float)va, d);
-    } else {
-      e_valid[v] = 1.0f;  // unused by the reference in this mode (ComputeMean divides by the height)
-      e_disp[v] = d;
+  // ---- per-row terms (:371-446): four rows per thread, their loads first ----
+  bool out_of_range = false;
+  for (int v0 = tid; v0 < H; v0 += 4 * kTabThreads) {
+    float d4[4], g0[4], gi[4], gn[4];
+    int oy4[4], ox4[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int v = v0 + j * kTabThreads;
+      const bool ok = v < H;
+      const int q = v / kDownsample;
+      d4[j] = ok ? __ldg(d_col + v) : 0.0f;
+      oy4[j] = (ok && q < p.hs2 && has_oy) ? __ldg(seg_col + (size_t)K * p.hs2 + q) : 0;
+      ox4[j] = (ok && q < p.hs2 && has_ox) ? __ldg(seg_col + (size_t)(K + 1) * p.hs2 + q) : 0;
+      const bool gr = ok && v < vhor;
+      g0[j] = gr ? __ldg(gf + v) : 0.0f;
+      gi[j] = gr ? __ldg(inv_g + v) : 0.0f;
+      gn[j] = gr ? __ldg(norm_g + v) : 0.0f;
     }
-    // sky_lut: GetDataCostSky (:201-215), zero below the horizon (:424-433)
-    float sky = 0.0f;
-    if (v >= vhor) {
-      sky = p.pnexists_given_sky_log;
-      if (d != invalid) {
-        const float g = ffma(fmul(d, d), p.inv_sigma2_sky, p.normalization_sky);
-        sky = fadd(fmin_(g, p.puniform_sky), p.nopnexists_given_sky_log);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int v = v0 + j * kTabThreads;
+      if (v >= H) break;
+      const float d = d4[j];
+      if (invalid >= 0.0f) {
+        const int va = d != invalid;
+        e_valid[v] = (float)va;
+        e_disp[v] = fmul((float)va, d);
+      } else {
+        e_valid[v] = 1.0f;  // unused by the reference in this mode (ComputeMean divides by the height)
+        e_disp[v] = d;
       }
-    }
-    e_sky[v] = sky;
-    // ground_lut: GetDataCostGround (:217-234), +inf at/above the horizon (:437-446)
-    float grd = inf_f();
-    if (v < vhor) {
-      grd = p.pnexists_given_ground_log;
-      if (d != invalid) {
-        const float diff = fsub(d, gf[v]);
-        const float g = ffma(fmul(diff, diff), inv_g[v], norm_g[v]);
-        grd = fadd(fmin_(g, p.puniform), p.nopnexists_given_ground_log);
+      // sky_lut: GetDataCostSky (:201-215), zero below the horizon (:424-433)
+      float sky = 0.0f;
+      if (v >= vhor) {
+        sky = p.pnexists_given_sky_log;
+        if (d != invalid) {
+          const float g = ffma(fmul(d, d), p.inv_sigma2_sky, p.normalization_sky);
+          sky = fadd(fmin_(g, p.puniform_sky), p.nopnexists_given_sky_log);
+        }
       }
+      e_sky[v] = sky;
+      // ground_lut: GetDataCostGround (:217-234), +inf at/above the horizon (:437-446)
+      float grd = inf_f();
+      if (v < vhor) {
+        grd = p.pnexists_given_ground_log;
+        if (d != invalid) {
+          const float diff = fsub(d, g0[j]);
+          const float g = ffma(fmul(diff, diff), gi[j], gn[j]);
+          grd = fadd(fmin_(g, p.puniform), p.nopnexists_given_ground_log);
+        }
+      }
+      e_ground[v] = grd;
+      // instance means (:400-409): C++ double arithmetic truncated toward zero
+      const long long mx = (long long)((p.column_step * col + 0.5 * (p.column_step - 1.0)) + ox4[j] + 0.5);
+      const long long my = (long long)(v - oy4[j] + 0.5);
+      out_of_range |= mx <= -kMeanRowLimit || mx >= kMeanRowLimit || my <= -kMeanRowLimit || my >= kMeanRowLimit;
+      ps_i32[0 * L.Hp + v] = (int)mx;
+      ps_i32[1 * L.Hp + v] = (int)my;
+      ps_i64[0 * L.Hp + v] = mx * mx;
+      ps_i64[1 * L.Hp + v] = my * my;
     }
-    e_ground[v] = grd;
-    // instance means (:400-409): C++ double arithmetic truncated toward zero
-    const int q = v / kDownsample;
-    const int off_y = (q < p.hs2 && K < p.n_channels) ? seg_col[(size_t)K * p.hs2 + q] : 0;
-    const int off_x = (q < p.hs2 && K + 1 < p.n_channels) ? seg_col[(size_t)(K + 1) * p.hs2 + q] : 0;
-    const long long mx = (long long)((p.column_step * col + 0.5 * (p.column_step - 1.0)) + off_x + 0.5);
-    const long long my = (long long)(v - off_y + 0.5);
-    e_i64[0 * L.Hp + v] = mx;
-    e_i64[1 * L.Hp + v] = my;
-    e_i64[2 * L.Hp + v] = mx * mx;
-    e_i64[3 * L.Hp + v] = my * my;
   }
   // The pruning DP kernels bound a segment's class sums from below by those of a shorter one, which needs
   // non-negative values whose int32 prefix sums do not wrap (they are trunc(8 * -log softmax) and squared pixel
@@ -258,60 +285,56 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   const int any_negative = __syncthreads_or(negative_class_value ? 1 : 0);
   if (tid == 0) col_flags[(size_t)f * C + col] = any_negative;
 
-  // ---- prefix sums: warps 0-3 float (Blelloch order), 4-7 int64, all: 1/8-res ints ----
+  // ---- prefix sums, in place: warps 0-3 float (Blelloch order), 4-5 int64, 6-7 int32; then all: 1/8-res ints ----
   if (warp < 4) {
-    const float *src = warp == 0 ? e_disp : warp == 1 ? e_valid : warp == 2 ? e_ground : e_sky;
-    blelloch_prefix_warp(src, H, ps_f[warp]);
+    blelloch_prefix_warp(e_disp + warp * L.Hp, H, e_disp + warp * L.Hp);
+  } else if (warp < 6) {
+    exact_prefix_warp<long long>(ps_i64 + (warp - 4) * L.Hp, H, ps_i64 + (warp - 4) * L.Hp);
   } else {
-    exact_prefix_warp<long long>(e_i64 + (warp - 4) * L.Hp, H, ps_i64 + (warp - 4) * L.Hp);
+    exact_prefix_warp<int>(ps_i32 + (warp - 6) * L.Hp, H, ps_i32 + (warp - 6) * L.Hp);
   }
-  for (int c = warp; c < 20; c += kTabThreads / 32) exact_prefix_warp<int>(seg_s + c * segld, nq, seg_ps + c * segld);
+  // 20 channels over 8 warps: the integer warps (done first) take three each, the float warps two
+  for (int c = 19 - ((warp + 4) & 7); c >= 0; c -= kTabThreads / 32)
+    exact_prefix_warp<int>(seg_ps + c * segld, nq, seg_ps + c * segld);
   __syncthreads();
 
   // ---- records, v in [0, H]: one 128-byte row per v (common.cuh).  Eight lanes share a row, lane g writes words
   //      4g .. 4g+3 as one 16-byte store, so a warp instruction stores 512 contiguous bytes (four full lines).
-  //      Groups 0-4 are the 20 integer words (one formula), 5-7 the float words. ----
+  //      Groups 0-4 are the 20 integer words (one formula, evaluated by every lane: no branch), 5-7 the float words
+  //      (one more branch for those three lanes, which select their words). ----
   uint4 *recb_col = reinterpret_cast<uint4 *>(records_b + ((size_t)f * C + col) * (size_t)p.rec_stride * kRecBWords);
-  bool out_of_range = false;
-  const long long lim1 = 1ll << 24, lim2 = 1ll << (24 + kSqSplitBits);
+  const long long lim2 = 1ll << (24 + kSqSplitBits);
+  const int lim1 = 1 << 24;
   const long long lomask = (1ll << kSqSplitBits) - 1;
   for (int idx = tid; idx < (H + 1) * (kRecBWords / 4); idx += kTabThreads) {
     const int v = idx >> 3, g = idx & 7;
     uint4 w;
-    if (g < 5) {
-      // P_c(v) = 8*ps[q] + seg[q]*r  (Cityscapes.h:28-42); word 19 = the same for the summed squared offsets
+    {
+      // P_c(v) = 8*ps[q] + seg[q]*r  (Cityscapes.h:28-42), seg[q] = ps[q+1] - ps[q]; word 19 = the same for the
+      // summed squared offsets
       const int q = v >> 3, r = v & 7;
-      const int *ps = seg_ps + (4 * g) * segld + q, *sg = seg_s + (4 * g) * segld + q;
-      w.x = (uint32_t)(ps[0] * kDownsample + sg[0] * r);
-      w.y = (uint32_t)(ps[segld] * kDownsample + sg[segld] * r);
-      w.z = (uint32_t)(ps[2 * segld] * kDownsample + sg[2 * segld] * r);
-      w.w = (uint32_t)(ps[3 * segld] * kDownsample + sg[3 * segld] * r);
-    } else if (g == 5) {
-      // instance-mean sums as exactly representable floats (see common.cuh): words 20 .. 23
-      const long long smx = ps_i64[0 * L.Hp + v], smy = ps_i64[1 * L.Hp + v], smx2 = ps_i64[2 * L.Hp + v];
-      out_of_range |= smx <= -lim1 || smx >= lim1 || smy <= -lim1 || smy >= lim1 || smx2 >= lim2;
-      w.x = __float_as_uint((float)smx);
-      w.y = __float_as_uint((float)smy);
-      w.z = __float_as_uint((float)(smx2 & ~lomask));
-      w.w = __float_as_uint((float)(smx2 & lomask));
-    } else if (g == 6) {
-      // words 24 .. 27
-      const long long smy2 = ps_i64[3 * L.Hp + v];
-      out_of_range |= smy2 >= lim2;
-      w.x = __float_as_uint((float)(smy2 & ~lomask));
-      w.y = __float_as_uint((float)(smy2 & lomask));
-      w.z = __float_as_uint(ps_f[0][v]);
-      w.w = __float_as_uint(ps_f[1][v]);
-    } else {
-      // words 28 .. 31
-      w.x = __float_as_uint(ps_f[2][v]);
-      w.y = __float_as_uint(ps_f[3][v]);
-      w.z = w.w = 0u;
+      const int *ps = seg_ps + (4 * (g < 5 ? g : 4)) * segld + q;
+      const int a0 = ps[0], a1 = ps[segld], a2 = ps[2 * segld], a3 = ps[3 * segld];
+      w.x = (uint32_t)(a0 * kDownsample + (ps[1] - a0) * r);
+      w.y = (uint32_t)(a1 * kDownsample + (ps[segld + 1] - a1) * r);
+      w.z = (uint32_t)(a2 * kDownsample + (ps[2 * segld + 1] - a2) * r);
+      w.w = (uint32_t)(a3 * kDownsample + (ps[3 * segld + 1] - a3) * r);
+    }
+    if (g >= 5) {
+      // instance-mean sums as exactly representable floats (see common.cuh): words 20 .. 25; float sums: 26 .. 29
+      const int smx = ps_i32[0 * L.Hp + v], smy = ps_i32[1 * L.Hp + v];
+      const long long smx2 = ps_i64[0 * L.Hp + v], smy2 = ps_i64[1 * L.Hp + v];
+      out_of_range |= smx <= -lim1 || smx >= lim1 || smy <= -lim1 || smy >= lim1 || smx2 >= lim2 || smy2 >= lim2;
+      const float f0 = e_disp[v], f1 = e_valid[v], f2 = e_ground[v], f3 = e_sky[v];
+      const float y2hi = (float)(smy2 & ~lomask), y2lo = (float)(smy2 & lomask);
+      w.x = __float_as_uint(g == 5 ? (float)smx : g == 6 ? y2hi : f2);
+      w.y = __float_as_uint(g == 5 ? (float)smy : g == 6 ? y2lo : f3);
+      w.z = g == 7 ? 0u : __float_as_uint(g == 5 ? (float)(smx2 & ~lomask) : f0);
+      w.w = g == 7 ? 0u : __float_as_uint(g == 5 ? (float)(smx2 & lomask) : f1);
     }
     recb_col[idx] = w;
   }
   if (out_of_range) atomicOr(error_flag + f, kErrOffsetRange);
-  (void)lane;
 }
 
 // ---------------------------------------------------------------------------
@@ -429,15 +452,30 @@ void launch_frame_tables(const KParams &p, const BatchBuffers &b, int nframes, c
 
 static size_t tab_smem_bytes(const KParams &p) { return TabSmem(p.rows, p.hs2).total; }
 
+// ISX_TAB_CTAS_PER_SM=n (experiments): pads the dynamic shared memory of the table kernels so that at most n of their
+// CTAs are resident per SM -- with the table stream above the DP's priority (ISX_TABLES_PRIO=1) the HBM-bound table
+// CTAs then sit BESIDE the issue-bound DP CTAs instead of replacing them.
+static size_t padded_smem(size_t need, size_t static_bytes) {
+  static const int n = [] {
+    const char *e = std::getenv("ISX_TAB_CTAS_PER_SM");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (n <= 0) return need;
+  const size_t per_cta = (size_t)(227 * 1024) / (size_t)(n + 1) + 1024;  // n fit, n + 1 do not
+  const size_t want = per_cta > static_bytes + 1024 ? per_cta - static_bytes - 1024 : 0;   // 1 KB reserved per CTA
+  return want > need ? want : need;
+}
+
 void launch_column_tables(const KParams &p, const BatchBuffers &b, int nframes, cudaStream_t s) {
   dim3 grid(p.realcols, nframes);
-  const size_t smem = tab_smem_bytes(p);
-  static SmemOptIn optin;
+  const size_t smem = padded_smem(tab_smem_bytes(p), 0);
+  static SmemOptIn optin, optin_lut;
   opt_in_smem(column_tables_kernel, optin);
+  opt_in_smem(object_lut_kernel, optin_lut);
   column_tables_kernel<<<grid, kTabThreads, smem, s>>>(b.joined, b.segmentation, b.ground, b.vhor, b.records_b,
                                                         b.error_flag, b.col_flags, p);
   dim3 lgrid(p.realcols, (p.max_dis + 32 * kLutWarps - 1) / (32 * kLutWarps), nframes);
-  object_lut_kernel<<<lgrid, kLutThreads, 0, s>>>(b.joined, b.obj_cost_lut_t, b.object_lut, p);
+  object_lut_kernel<<<lgrid, kLutThreads, padded_smem(0, sizeof(float) * kLutWarps * 32 * 33 + 1056), s>>>(b.joined, b.obj_cost_lut_t, b.object_lut, p);
   g_launch_count += 2;
 }
 

@@ -292,3 +292,42 @@ def test_single_frame_compute_after_an_asynchronous_device_batch():
         single = st.Compute(True)
         assert single.vhor == rows - other_road["vhor"] - 1
     st.Finish()
+
+
+@pytest.mark.parametrize("mode", ["unary", "pairwise"])
+def test_launch_sizes_do_not_change_results(mode, monkeypatch):
+    """How a batch is cut into launches is invisible in the results: the default chunks (64 frames per pairwise
+    launch, 32 per unary launch), the quarter pieces at the head of an idle pipeline and at the tail of a synchronous
+    call, three batches in flight -- all against launches of 5 frames (ISX_CHUNK below 32: no pieces)."""
+    import parity
+    rows, cols, n = 96, 128, 80
+    pairwise = mode == "pairwise"
+    pre = synth.preset(mode, rows, cols, 8)
+    disp, seg, roads = synth.make_batch(16, start=3, rows=rows, cols=cols)
+    disp, seg, roads = np.concatenate([disp] * 5), np.concatenate([seg] * 5), roads * 5
+    monkeypatch.setenv("ISX_CHUNK", "5")
+    ref = api.make_stixels(pre, max_batch=n)
+    monkeypatch.delenv("ISX_CHUNK")
+    want_sec, want_inst, want_offs = ref.ComputeBatch(pairwise, disp, seg, roads)
+    assert ref.chunk_frames() == 5
+    ref.Finish()
+    st = api.make_stixels(pre, max_batch=n)
+    sec, inst, offs = st.ComputeBatch(pairwise, disp, seg, roads)          # head and tail pieces around whole chunks
+    assert st.chunk_frames() == (64 if pairwise else 32)
+    assert all(parity.same_used_sections(want_sec[f], sec[f]) for f in range(n))
+    assert np.array_equal(want_inst.view(np.uint8), inst.view(np.uint8)) and np.array_equal(want_offs, offs)
+    C_, S = st.GetRealCols(), st.GetMaxSections()
+    outs = [np.zeros((n, C_, S), dtype=api.L.SECTION_DTYPE) for _ in range(3)]
+    got = []
+    for i in range(5):                                                     # idle head, then a filled pipeline
+        st.SubmitBatch(pairwise, disp, seg, roads, outs[i % 3])
+        if i >= 2:
+            s_, i_, o_ = st.WaitBatch()
+            got.append((s_.copy(), i_, o_))
+    for _ in range(2):
+        s_, i_, o_ = st.WaitBatch()
+        got.append((s_.copy(), i_, o_))
+    for s_, i_, o_ in got:
+        assert all(parity.same_used_sections(want_sec[f], s_[f]) for f in range(n))
+        assert np.array_equal(want_inst.view(np.uint8), i_.view(np.uint8)) and np.array_equal(want_offs, o_)
+    st.Finish()

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for profiles/: (1) launch list of the bench command, (2) full-set capture of every kernel of one
 # launch-sized chunk (unary 32 frames, pairwise 64).  Usage: bash tools/gpu_profile_r2.sh <tag>
-tag=${1:-r2b}
+tag=${1:-r2d}
 mkdir -p gpurun_out
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_unary_b64.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/${tag}_launches_bench.log 2>&1
