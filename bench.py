@@ -48,15 +48,15 @@ WORKLOADS = {
 ROWS, COLS = 1024, 2048
 RECORD_WORDS_PER_ROW = 32   # prefix records: one 128-byte row per image row and column (common.cuh kRecBWords)
 OPS_PER_CELL = {"unary": 103, "pairwise": 128}  # SURVEY.md 8d minimal op budget
-NCU_SOURCE = "profiles/r2c_*.txt"
+NCU_SOURCE = "profiles/r2d_*.txt"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` captures summarised in
-# profiles/r2c_{unary,pairwise}.txt (width 8; unary launches carry 32 frames, pairwise launches 64; no capture for
+# profiles/r2d_{unary,pairwise}.txt (width 8; unary launches carry 32 frames, pairwise launches 64; no capture for
 # width 4).  "tables" = join_columns + (frame_tables) + column_tables + object_lut kernels.
 NCU_TRAFFIC = {
-    ("unary", 8): dict(chunk=32, dp=(1.4443 + 0.1326) * 1e9,     # dp_unary_pruned_kernel
-                       tables=(0.2685 + 0.0271 + 0.1440 + 1.0619 + 0.0337 + 4.2363) * 1e9),
-    ("pairwise", 8): dict(chunk=64, dp=(3.2128 + 1.1244) * 1e9,  # dp_pairwise_walk_kernel
-                          tables=(0.5370 + 0.0607 + 0.0003 + 0.2879 + 2.1774 + 0.0673 + 8.5321) * 1e9),
+    ("unary", 8): dict(chunk=32, dp=(1.4432 + 0.1301) * 1e9,     # dp_unary_pruned_kernel
+                       tables=(0.2685 + 0.0270 + 0.1440 + 1.0158 + 0.0337 + 4.2360) * 1e9),
+    ("pairwise", 8): dict(chunk=64, dp=(3.2113 + 1.1235) * 1e9,  # dp_pairwise_walk_kernel
+                          tables=(0.5369 + 0.0601 + 0.0003 + 0.2880 + 2.0902 + 0.0674 + 8.5304) * 1e9),
 }
 
 

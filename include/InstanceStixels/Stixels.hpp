@@ -228,10 +228,13 @@ public:
                                      offs_.data()));
         unpack(n, roads, sections_.data(), frames, instances);
     }
-    // Streaming form: SubmitBatch enqueues a batch and returns; WaitBatch delivers the OLDEST one.  At most two in
-    // flight (submit, submit, wait, submit, wait, ...); the input buffers must stay valid until their WaitBatch.
+    // Streaming form: SubmitBatch enqueues a batch and returns; WaitBatch delivers the OLDEST one.  At most three in
+    // flight (submit, submit, submit, wait, submit, wait, ...); the input buffers must stay valid until their
+    // WaitBatch.  ReserveInFlight allocates the result arrays of that many batches up front (otherwise the first
+    // submits do).
+    void ReserveInFlight(int batches) { check(isx_reserve_in_flight(h_, batches)); }
     void SubmitBatch(bool pairwise, int n, const pixel_t* disparity, const int32_t* segmentation, const Road* roads) {
-        Pending& p = pending_[submitted_ & 1];
+        Pending& p = pending_[submitted_ % 3];
         p.n = n;
         p.roads.assign(roads, roads + n);
         p.sections.resize((size_t)n * GetRealCols() * GetMaxSections());
@@ -240,7 +243,7 @@ public:
         submitted_++;
     }
     void WaitBatch(std::vector<StixelsData>& frames, std::vector<InstanceMap>* instances = nullptr) {
-        Pending& p = pending_[waited_ & 1];
+        Pending& p = pending_[waited_ % 3];
         inst_.resize((size_t)p.n * (size_t)isx_instance_capacity(h_));
         offs_.resize((size_t)p.n + 1);
         check(isx_wait_batch_host(h_, inst_.data(), (int)inst_.size(), offs_.data()));
@@ -258,7 +261,7 @@ private:
         int n = 0;
         std::vector<Road> roads;
         std::vector<Section> sections;
-    } pending_[2];
+    } pending_[3];
     unsigned long long submitted_ = 0, waited_ = 0;
     std::vector<Section> sections_;
     std::vector<isx_instance> inst_;

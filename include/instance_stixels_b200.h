@@ -243,6 +243,10 @@ int isx_synchronize(isx_handle h);
 int isx_submit_batch_host(isx_handle h, int pairwise, int n, const float *disparity, const int32_t *segmentation,
                           const isx_road *roads, isx_section *sections);
 int isx_wait_batch_host(isx_handle h, isx_instance *instances, int instances_capacity, int32_t *instance_offsets);
+/* The result arrays of a batch in flight (device arrays + the pinned host arrays the device packs into) are
+ * allocated when a submit first needs them -- tens of milliseconds inside the caller's stream.  A caller that knows
+ * how many batches it keeps in flight (1 .. 3) reserves them up front. */
+int isx_reserve_in_flight(isx_handle h, int batches);
 /* Zero-copy form of isx_wait_batch_host: waits for the oldest batch in flight and hands out the packed results
  * where the device wrote them (pinned host memory owned by the handle): `*sections` / `*instances` are the packed
  * arrays, `*counts` = [n][realcols] stixels per column, `*frames` = [n] descriptors (offsets into the packed

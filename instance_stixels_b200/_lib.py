@@ -25,7 +25,7 @@ EXPORTS = [
     "isx_set_disparity_image", "isx_input_disparity_device", "isx_set_segmentation",
     "isx_set_road_parameters", "isx_compute", "isx_cluster_instances", "isx_dbscan_fit_host", "isx_instance_capacity", "isx_get_dp_units", "isx_flush",
     "isx_get_instance_stixels",
-    "isx_compute_batch_host", "isx_submit_batch_host", "isx_wait_batch_host", "isx_compute_batch_device", "isx_synchronize", "isx_fetch_batch_results",
+    "isx_compute_batch_host", "isx_submit_batch_host", "isx_wait_batch_host", "isx_reserve_in_flight", "isx_compute_batch_device", "isx_synchronize", "isx_fetch_batch_results",
     "isx_stream", "isx_tensor_elems", "isx_read_tensor", "isx_set_profiling", "isx_get_stage_times",
     "isx_chunk_frames", "isx_get_chunk_trace", "isx_host_alloc", "isx_host_free",
     # compact results / narrow inputs / frame pool
@@ -137,6 +137,7 @@ def _declare(lib):
                                            C.c_void_p, i, C.c_void_p]
     lib.isx_submit_batch_host.argtypes = [H, i, i, C.c_void_p, C.c_void_p, C.POINTER(Road), C.c_void_p]
     lib.isx_wait_batch_host.argtypes = [H, C.c_void_p, i, C.c_void_p]
+    lib.isx_reserve_in_flight.argtypes = [H, i]
     lib.isx_wait_batch_packed.argtypes = [H] + [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(i)]
     lib.isx_narrow_segmentation_elems.argtypes = [H]
     lib.isx_narrow_segmentation_elems.restype = C.c_size_t

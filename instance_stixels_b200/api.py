@@ -350,6 +350,11 @@ class Stixels:
         self._check(self._lib.isx_get_stage_times(self._h, ms, ch, 6, int(reset)))
         return {n: (ms[i], ch[i]) for i, n in enumerate(self.STAGES)}
 
+    def ReserveInFlight(self, batches: int):
+        """Allocate the result arrays of `batches` (1 .. 3) batches in flight now instead of inside the first
+        submits (isx_reserve_in_flight)."""
+        self._check(self._lib.isx_reserve_in_flight(self._h, batches))
+
     def chunk_frames(self) -> int:
         return self._lib.isx_chunk_frames(self._h)
 

@@ -1248,6 +1248,16 @@ int isx_submit_batch_host_u16(isx_handle h, int pairwise, int n, const uint16_t 
   return submit_batch_host(h, pairwise, n, in, roads, sections);
 }
 
+int isx_reserve_in_flight(isx_handle h, int batches) {
+  if (int rc = check_ready(h)) return rc;
+  if (batches < 1 || batches > kResultSets - 1)
+    return fail(h, ISX_ERR_INVALID_ARGUMENT, "isx_reserve_in_flight: between one and three batches");
+  cudaSetDevice(h->device);
+  for (int i = 0; i <= batches && i < kResultSets; i++)
+    if (int rc = alloc_result_set(h, i)) return rc;
+  return ISX_OK;
+}
+
 // Waits for the oldest batch in flight; returns its ticket slot (>= 0) or an error (< 0).
 static int wait_oldest(isx_handle h) {
   if (int rc = check_ready(h)) return rc;

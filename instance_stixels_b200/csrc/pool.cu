@@ -143,6 +143,7 @@ int isx_pool_create(isx_pool_handle *out, const int *devices, int n_devices, con
     int rc = isx_create(&w->h, devices[i]);
     if (rc == ISX_OK) rc = isx_set_config(w->h, cfg);
     if (rc == ISX_OK) rc = isx_initialize(w->h, max_batch);
+    if (rc == ISX_OK) rc = isx_reserve_in_flight(w->h, 3);   // run_job keeps three sub-batches in flight
     if (rc != ISX_OK) {
       const std::string msg = std::string("isx_pool_create, device ") + std::to_string(devices[i]) + ": " +
                               isx_last_error(w->h ? w->h : nullptr);
