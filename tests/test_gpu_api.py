@@ -331,3 +331,28 @@ def test_launch_sizes_do_not_change_results(mode, monkeypatch):
         assert all(parity.same_used_sections(want_sec[f], s_[f]) for f in range(n))
         assert np.array_equal(want_inst.view(np.uint8), i_.view(np.uint8)) and np.array_equal(want_offs, o_)
     st.Finish()
+
+
+def test_reserve_in_flight():
+    """isx_reserve_in_flight: one to three batches, before or between submits; a fourth batch in flight is refused
+    whether or not the sets were reserved."""
+    import parity
+    rows, cols, n = 64, 128, 3
+    pre = synth.preset("pairwise", rows, cols, 8)
+    st = api.make_stixels(pre, max_batch=4)
+    for bad in (0, 4):
+        with pytest.raises(api.InvalidArgument):
+            st.ReserveInFlight(bad)
+    st.ReserveInFlight(3)
+    disp, seg, roads = synth.make_batch(n, start=11, rows=rows, cols=cols)
+    want, _, _ = st.ComputeBatch(True, disp, seg, roads)
+    outs = [np.zeros((n, st.GetRealCols(), st.GetMaxSections()), dtype=api.L.SECTION_DTYPE) for _ in range(3)]
+    for o in outs:
+        st.SubmitBatch(True, disp, seg, roads, o)
+    st.ReserveInFlight(2)            # nothing left to allocate: a no-op while batches are in flight
+    with pytest.raises(api.StixelsError):
+        st.SubmitBatch(True, disp, seg, roads, outs[0])
+    for o in outs:
+        sec, _, _ = st.WaitBatch()
+        assert all(parity.same_used_sections(want[f], sec[f]) for f in range(n))
+    st.Finish()
