@@ -252,7 +252,7 @@ bool segmentation_fits(const isx_apps::NpyInt32& seg, int rows, int cols, int co
 // ---- extension: --batch B / --gpus G ----
 // The same dataset through the batched entry points: all frames are loaded, the road is estimated per frame, and
 // runs of frames with one geometry go through a StixelsPool (one context + worker thread per GPU, sub-batches of B
-// frames, two in flight) from pinned host buffers.  The .stixels files are the same bytes as the one-frame loop
+// frames, three in flight) from pinned host buffers.  The .stixels files are the same bytes as the one-frame loop
 // writes; the timed region is the pool call (host buffers in -> Sections and instance maps out), after one
 // discarded warm-up call like the reference's first frame.
 struct LoadedFrame {

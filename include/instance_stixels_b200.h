@@ -290,7 +290,7 @@ void isx_host_free(void *p);
 /* ------------------------------------------------------------------ */
 /* Frame pool: one context and one host worker thread per GPU inside ONE process; a call shards
  * its frames into contiguous blocks, frame f -> worker f * G / n, and every worker streams its block through
- * isx_submit_batch_host / isx_wait_batch_host in sub-batches of `max_batch` frames (two in flight).  No
+ * isx_submit_batch_host / isx_wait_batch_host in sub-batches of `max_batch` frames (three in flight).  No
  * collective: frames are independent, results land in the caller's arrays in frame order.  `devices` may name a
  * GPU more than once (several workers on one GPU).  The reference has no counterpart (one frame per Compute). */
 typedef struct isx_pool *isx_pool_handle;
