@@ -529,6 +529,34 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
         out["value_no_prune"] = dict(value=world * B / (ms2 * 1e-3 / n2), unit="frames/s",
                                      note="every (tile, chunk) unit evaluated: the floor of the data-dependent pruning")
         st2.Finish()
+        del st2
+        # The table kernels on their own: in the pipeline above their CTAs wait for places the DP of the chunk before
+        # vacates, so the stage times around them contain that wait.  ISX_OVERLAP_TABLES=0 runs one kernel at a time.
+        os.environ["ISX_OVERLAP_TABLES"] = "0"
+        try:
+            st3 = api.make_stixels(pre, max_batch=B, device=env.local)
+        finally:
+            del os.environ["ISX_OVERLAP_TABLES"]
+
+        def step3():
+            st3.ComputeBatchDevice(pairwise, B, d_disp.data_ptr(), d_seg.data_ptr(), roads)
+        step3()
+        st3.Synchronize()
+        st3.set_profiling(True)
+        st3.stage_times(reset=True)
+        n3 = max(2, steps // 4)
+        for _ in range(n3):
+            step3()
+        st3.Synchronize()
+        stages3 = st3.stage_times(reset=True)
+        st3.Finish()
+        alone_s = (stages3["join"][0] + stages3["column_tables"][0]) * 1e-3 / max(stages3["join"][1], 1)
+        rt = out["roofline_tables"]
+        rt["achieved_alone"] = tab_bytes / alone_s / 1e9
+        rt["frac_alone"] = rt["achieved_alone"] / peaks["hbm_gbs"]
+        rt["note_alone"] = (f"the same kernels with nothing beside them (ISX_OVERLAP_TABLES=0, {stages3['join'][1]} launches, "
+                            f"{alone_s * 1e3:.2f} ms per launch); `achieved` is from the pipelined run, where the stage "
+                            f"events also see the wait for the DP's CTAs to retire")
     return out
 
 
