@@ -306,14 +306,20 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
   const long long lim2 = 1ll << (24 + kSqSplitBits);
   const int lim1 = 1 << 24;
   const long long lomask = (1ll << kSqSplitBits) - 1;
-  for (int idx = tid; idx < (H + 1) * (kRecBWords / 4); idx += kTabThreads) {
-    const int v = idx >> 3, g = idx & 7;
+  // A thread keeps its lane group g and its row phase r = v & 7 for the whole loop (v advances by 32 rows), so what
+  // depends on them is chosen once: the channel group of the integer words, the 64-bit sum a float lane splits, the
+  // float arrays it copies.
+  const int g = tid & 7, r = (tid >> 3) & 7;
+  const int *ps_grp = seg_ps + (4 * (g < 5 ? g : 4)) * segld;
+  const long long *ps_sq = ps_i64 + (g == 5 ? 0 : L.Hp);          // g == 5: sum mx^2, g == 6: sum my^2
+  const float *pf_a = g == 6 ? e_disp : e_ground, *pf_b = g == 6 ? e_valid : e_sky;
+#pragma unroll 2
+  for (int v = tid >> 3; v <= H; v += kTabThreads / 8) {
     uint4 w;
     {
       // P_c(v) = 8*ps[q] + seg[q]*r  (Cityscapes.h:28-42), seg[q] = ps[q+1] - ps[q]; word 19 = the same for the
       // summed squared offsets
-      const int q = v >> 3, r = v & 7;
-      const int *ps = seg_ps + (4 * (g < 5 ? g : 4)) * segld + q;
+      const int *ps = ps_grp + (v >> 3);
       const int a0 = ps[0], a1 = ps[segld], a2 = ps[2 * segld], a3 = ps[3 * segld];
       w.x = (uint32_t)(a0 * kDownsample + (ps[1] - a0) * r);
       w.y = (uint32_t)(a1 * kDownsample + (ps[segld + 1] - a1) * r);
@@ -323,16 +329,16 @@ column_tables_kernel(const float *__restrict__ joined, const int32_t *__restrict
     if (g >= 5) {
       // instance-mean sums as exactly representable floats (see common.cuh): words 20 .. 25; float sums: 26 .. 29
       const int smx = ps_i32[0 * L.Hp + v], smy = ps_i32[1 * L.Hp + v];
-      const long long smx2 = ps_i64[0 * L.Hp + v], smy2 = ps_i64[1 * L.Hp + v];
-      out_of_range |= smx <= -lim1 || smx >= lim1 || smy <= -lim1 || smy >= lim1 || smx2 >= lim2 || smy2 >= lim2;
-      const float f0 = e_disp[v], f1 = e_valid[v], f2 = e_ground[v], f3 = e_sky[v];
-      const float y2hi = (float)(smy2 & ~lomask), y2lo = (float)(smy2 & lomask);
-      w.x = __float_as_uint(g == 5 ? (float)smx : g == 6 ? y2hi : f2);
-      w.y = __float_as_uint(g == 5 ? (float)smy : g == 6 ? y2lo : f3);
-      w.z = g == 7 ? 0u : __float_as_uint(g == 5 ? (float)(smx2 & ~lomask) : f0);
-      w.w = g == 7 ? 0u : __float_as_uint(g == 5 ? (float)(smx2 & lomask) : f1);
+      const long long sq = ps_sq[v];
+      out_of_range |= (g == 5 && (smx <= -lim1 || smx >= lim1 || smy <= -lim1 || smy >= lim1)) || (g != 7 && sq >= lim2);
+      const float hi = (float)(sq & ~lomask), lo = (float)(sq & lomask);
+      const float fa = pf_a[v], fb = pf_b[v];
+      w.x = __float_as_uint(g == 5 ? (float)smx : g == 6 ? hi : fa);
+      w.y = __float_as_uint(g == 5 ? (float)smy : g == 6 ? lo : fb);
+      w.z = g == 7 ? 0u : __float_as_uint(g == 5 ? hi : fa);
+      w.w = g == 7 ? 0u : __float_as_uint(g == 5 ? lo : fb);
     }
-    recb_col[idx] = w;
+    recb_col[v * (kRecBWords / 4) + g] = w;
   }
   if (out_of_range) atomicOr(error_flag + f, kErrOffsetRange);
 }
