@@ -327,6 +327,13 @@ public:
     int Size() { return isx_pool_size(p_); }
     int GetRealCols() { return isx_pool_real_cols(p_); }
     int GetMaxSections() { return ISX_MAX_STIXELS_PER_COLUMN; }
+    // Frames every worker processed in the last ComputeBatch: its contiguous block, less or plus the sub-batches a
+    // worker that was done took over from the back of another block.
+    std::vector<int> FramesByWorker() {
+        std::vector<int> f((size_t)Size());
+        f.resize((size_t)isx_pool_frames_by_worker(p_, f.data(), (int)f.size()));
+        return f;
+    }
 
     // Any n >= 1; layouts as Stixels::ComputeBatch.  `sections` receives [n][realcols][200].
     void ComputeBatch(bool pairwise, int n, const pixel_t* disparity, const int32_t* segmentation, const Road* roads,

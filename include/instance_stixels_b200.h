@@ -289,10 +289,12 @@ void isx_host_free(void *p);
 
 /* ------------------------------------------------------------------ */
 /* Frame pool: one context and one host worker thread per GPU inside ONE process; a call shards
- * its frames into contiguous blocks, frame f -> worker f * G / n, and every worker streams its block through
- * isx_submit_batch_host / isx_wait_batch_host in sub-batches of `max_batch` frames (three in flight).  No
- * collective: frames are independent, results land in the caller's arrays in frame order.  `devices` may name a
- * GPU more than once (several workers on one GPU).  The reference has no counterpart (one frame per Compute). */
+ * its frames into contiguous blocks, frame f -> worker f * G / n, and every worker streams its block from the front
+ * through isx_submit_batch_host / isx_wait_batch_host in sub-batches of `max_batch` frames (three in flight); a
+ * worker that has used up its block takes sub-batches from the back of the fullest other block, so that a GPU behind
+ * a slower host link does not set the time of the call.  No collective: frames are independent, results land in the
+ * caller's arrays in frame order whoever computed them.  `devices` may name a GPU more than once (several workers
+ * on one GPU).  The reference has no counterpart (one frame per Compute). */
 typedef struct isx_pool *isx_pool_handle;
 int isx_pool_create(isx_pool_handle *out, const int *devices, int n_devices, const isx_config *cfg, int max_batch);
 int isx_pool_destroy(isx_pool_handle p);
@@ -304,6 +306,9 @@ int isx_pool_compute_host(isx_pool_handle p, int pairwise, int n, const float *d
                           const int32_t *segmentation, const isx_road *roads, isx_section *sections,
                           isx_instance *instances, int instances_capacity, int32_t *instance_offsets);
 const char *isx_pool_last_error(isx_pool_handle p);
+/* Frames every worker processed in the last isx_pool_compute_host call (its own block -/+ what was taken over);
+ * returns the number of entries written. */
+int isx_pool_frames_by_worker(isx_pool_handle p, int *frames, int capacity);
 
 /* ------------------------------------------------------------------ */
 /* Introspection for parity tests / profiling (device -> host copies of

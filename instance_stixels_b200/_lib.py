@@ -31,7 +31,7 @@ EXPORTS = [
     # compact results / narrow inputs / frame pool
     "isx_wait_batch_packed", "isx_narrow_segmentation_elems", "isx_compute_batch_host_u16", "isx_submit_batch_host_u16",
     "isx_pool_create", "isx_pool_destroy", "isx_pool_size", "isx_pool_real_cols", "isx_pool_segmentation_elems",
-    "isx_pool_compute_host", "isx_pool_last_error",
+    "isx_pool_compute_host", "isx_pool_last_error", "isx_pool_frames_by_worker",
     # segmentation ingest
     "isx_set_segmentation_from_cnn_device", "isx_flip_and_pad_batch_device",
     # result images
@@ -154,6 +154,7 @@ def _declare(lib):
                                           C.c_void_p]
     lib.isx_pool_last_error.argtypes = [H]
     lib.isx_pool_last_error.restype = C.c_char_p
+    lib.isx_pool_frames_by_worker.argtypes = [H, C.POINTER(C.c_int), i]
     lib.isx_compute_batch_device.argtypes = [H, i, i, C.c_void_p, C.c_void_p, C.POINTER(Road)]
     lib.isx_synchronize.argtypes = [H]
     lib.isx_flush.argtypes = [H]

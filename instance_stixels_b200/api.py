@@ -508,6 +508,13 @@ class StixelsPool:
             raise StixelsError(f"isx_pool_compute_host: {self._lib.isx_pool_last_error(self._p).decode()} ({rc})")
         return sections_out, inst[:offs[n]].copy(), offs
 
+    def frames_by_worker(self):
+        """Frames every worker processed in the last ComputeBatch (its block, less or plus what was taken over)."""
+        n = self.size()
+        buf = (C.c_int * n)()
+        k = self._lib.isx_pool_frames_by_worker(self._p, buf, n)
+        return [int(buf[i]) for i in range(k)]
+
     def close(self):
         if self._p:
             self._lib.isx_pool_destroy(self._p)

@@ -188,8 +188,9 @@ def test_packed_results_equal_the_padded_arrays(budget, monkeypatch):
 
 
 def test_frame_pool_equals_one_context():
-    """isx_pool_*: contiguous frame blocks over several workers (here two workers on GPU 0, and every GPU of the
-    box), sub-batches smaller than a block: same Sections and instance records, in frame order."""
+    """isx_pool_*: contiguous frame blocks over several workers (here two and three workers on GPU 0, and every GPU
+    of the box), sub-batches smaller than a block, idle workers taking sub-batches from the back of the fullest block:
+    same Sections and instance records, in frame order, whoever computed them."""
     import parity
     import torch
     rows, cols, n = 128, 256, 11
@@ -210,6 +211,8 @@ def test_frame_pool_equals_one_context():
             assert all(parity.same_used_sections(want_sec[f], sec[f]) for f in range(n)), devices
             assert np.array_equal(want_offs, offs), devices
             assert np.array_equal(want_inst.view(np.uint8), inst.view(np.uint8)), devices
+            by_worker = pool.frames_by_worker()        # blocks, less or plus what a faster worker took over
+            assert len(by_worker) == len(devices) and sum(by_worker) == n and min(by_worker) >= 0, by_worker
         sec1, inst1, offs1 = pool.ComputeBatch(True, disp[:1], seg[:1], roads[:1])   # fewer frames than workers
         assert parity.same_used_sections(want_sec[0], sec1[0]) and offs1[1] == want_offs[1]
         pool.close()
@@ -356,3 +359,23 @@ def test_reserve_in_flight():
         sec, _, _ = st.WaitBatch()
         assert all(parity.same_used_sections(want[f], sec[f]) for f in range(n))
     st.Finish()
+
+
+def test_frame_pool_work_is_taken_over_from_a_slow_worker():
+    """A worker whose own block is empty (more workers than frames in its share) or used up takes sub-batches from the
+    others: with one frame per sub-batch and many more frames than workers every frame is still computed exactly once
+    and lands at its place."""
+    import parity
+    rows, cols, n = 96, 128, 23
+    pre = synth.preset("unary", rows, cols, 8)
+    disp, seg, roads = synth.make_batch(n, start=5, rows=rows, cols=cols)
+    st = api.make_stixels(pre, max_batch=n)
+    want_sec, want_inst, want_offs = st.ComputeBatch(False, disp, seg, roads)
+    st.Finish()
+    pool = api.StixelsPool(api.StixelConfig(**pre), [0, 0, 0, 0], max_batch=1)
+    for _ in range(3):
+        sec, inst, offs = pool.ComputeBatch(False, disp, seg, roads)
+        assert all(parity.same_used_sections(want_sec[f], sec[f]) for f in range(n))
+        assert np.array_equal(want_offs, offs) and np.array_equal(want_inst.view(np.uint8), inst.view(np.uint8))
+        assert sum(pool.frames_by_worker()) == n
+    pool.close()
