@@ -362,6 +362,11 @@ int run_batched(const Options& opt) {
         const double ms = (double)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count() * 1e-3;
         std::cout << "Done. Time elapsed (s): " << ms * 1e-3 << " for " << n << " frames on " << pool.Size()
                   << " GPU worker(s), sub-batches of " << opt.batch << "\n";
+        {
+            std::cerr << "frames by worker:";   // a worker that is done takes sub-batches over from the fullest block
+            for (int fw : pool.FramesByWorker()) std::cerr << " " << fw;
+            std::cerr << "\n";
+        }
         total_ms += ms;
         total_frames += (size_t)n;
         const size_t per = per_frame;
