@@ -11,8 +11,9 @@ independent, so N GPUs run N shards with no collective in the data path (weak sc
   value : frames/s with inputs already resident in HBM (isx_compute_batch_device), timed with CUDA
           events on the stream the kernels are launched on, max over ranks.
   e2e   : the same batches through the host-buffer entry points (isx_submit_batch_host /
-          isx_wait_batch_host): pinned host inputs -> H2D -> kernels -> results packed by the device into
-          pinned host memory -> expanded into the caller's [C][200] Section array, every step.
+          isx_wait_batch_host, three batches in flight): pinned host inputs -> H2D -> kernels -> the device
+          writes the used Sections into the caller's pinned [C][200] array and packs counts / instance records
+          into pinned host memory, every step.
   e2e_u16: the same with the narrow host inputs (uint16 disparity, unpadded int16 segmentation).
 
 The line's top-level keys describe --workload (default unary_b64 = BASELINE.json configs[1]); `workloads`
@@ -401,10 +402,10 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
     e2e_s = run_e2e("float", steps)
     e2e_u16_s = run_e2e("u16", steps)
     e2e_single_s = run_e2e("single", max(2, steps // 2)) if primary else None
-    # what the device wrote into host memory for one batch: used Sections + per-column counts + instance records
-    # + one descriptor per frame (the caller's padded array is expanded from that on the host)
+    # what the device wrote into host memory for one batch: the used Sections and the terminator of every column
+    # (straight into the caller's pinned padded array) + per-column counts + instance records + one descriptor per frame
     n_stixels = int((sec_np[0]["type"] == -1).argmax(axis=2).sum())
-    d2h_bytes = n_stixels * 32 + B * C_ * 4 + seen["inst"] * 16 + B * 32
+    d2h_bytes = (n_stixels + B * C_) * 32 + B * C_ * 4 + seen["inst"] * 16 + B * 32
     h2d_float = int(h_disp.numel() * 4 + h_seg.numel() * 4 * ((ROWS + 7) // 8) // h_seg.shape[-1] + B * 3 * ROWS * 4)
     h2d_u16 = int(h_d16.numel() * 2 + h_s16.numel() * 2 + B * 3 * ROWS * 4)
 
@@ -449,8 +450,9 @@ def measure(env, name, wl, steps, warmup, primary, extras=True):
                                l2="inputs (%d MB/step) and tables (>2 GB/chunk) exceed the 126 MB L2" % (B * 13.9)),
         e2e=dict(value=world * B / e2e_s, unit="frames/s", h2d_bytes_per_step=h2d_float, d2h_bytes_per_step=d2h_bytes,
                  pipeline="1 host thread, isx_submit_batch_host / isx_wait_batch_host, 3 batches in flight; float "
-                          "disparity + int32 segmentation (the reference's types); results packed by the device into "
-                          "pinned host memory and expanded into the caller's [C][200] Section array",
+                          "disparity + int32 segmentation (the reference's types); the device writes the used "
+                          "Sections straight into the caller's pinned [C][200] array and packs counts and instance "
+                          "records into pinned host memory",
                  h2d_gbs_per_gpu=h2d_float / e2e_s / 1e9),
         e2e_u16=dict(value=world * B / e2e_u16_s, unit="frames/s", h2d_bytes_per_step=h2d_u16,
                      d2h_bytes_per_step=d2h_bytes, h2d_gbs_per_gpu=h2d_u16 / e2e_u16_s / 1e9,
